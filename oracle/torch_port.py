@@ -1,0 +1,98 @@
+"""fp32 functional-PyTorch port of the reference hot path.  TEST INFRASTRUCTURE ONLY.
+
+The reference is a PyTorch program whose CPU path is ``torch.stft`` + oneDNN
+convolutions; this port issues the same library calls on the same shapes, from a
+flat state dict instead of an ``nn.Module`` tree.  ``bench.py`` times it as the CPU
+baseline (``cpu_baseline.kind == "port"``) and ``tests/`` use it as a second checker
+next to ``np_oracle``.  Never imported by the product package.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import np_oracle
+
+_basis_cache = {}
+
+
+def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax,
+                    center=True):
+    """dataset.py:53-91 on CPU tensors."""
+    key = (sampling_rate, n_fft, num_mels, fmin, fmax, win_size)
+    if key not in _basis_cache:
+        basis = torch.from_numpy(np_oracle.mel_filterbank(sampling_rate, n_fft, num_mels, fmin, fmax))
+        _basis_cache[key] = (basis, torch.hann_window(win_size))
+    basis, window = _basis_cache[key]
+    spec = torch.stft(y, n_fft, hop_length=hop_size, win_length=win_size, window=window,
+                      center=True, return_complex=True)
+    return torch.log(torch.clamp(basis @ spec.abs(), min=1e-5))
+
+
+def fold_state(state):
+    """remove_weight_norm (Models/hifigan.py:126-133) on a flat state dict:
+    ``*.weight_g`` / ``*.weight_v`` pairs become ``*.weight``."""
+    out = {}
+    for name, t in state.items():
+        t = torch.as_tensor(t, dtype=torch.float32)
+        if name.endswith(".weight_v"):
+            g = torch.as_tensor(state[name[:-1] + "g"], dtype=torch.float32)
+            norm = t.reshape(t.shape[0], -1).norm(dim=1).reshape(g.shape)
+            out[name[: -len("_v")]] = t * (g / norm)
+        elif name.endswith(".weight_g"):
+            continue
+        else:
+            out[name] = t
+    return out
+
+
+def _resblock(w, prefix, x, k, dilations, two_convs):
+    for m, d in enumerate(dilations):
+        if two_convs:  # ResBlock1, hifigan.py:43-50
+            xt = F.conv1d(F.leaky_relu(x, 0.1), w[f"{prefix}.convs1.{m}.weight"],
+                          w[f"{prefix}.convs1.{m}.bias"], dilation=d,
+                          padding=np_oracle.get_padding(k, d))
+            xt = F.conv1d(F.leaky_relu(xt, 0.1), w[f"{prefix}.convs2.{m}.weight"],
+                          w[f"{prefix}.convs2.{m}.bias"], padding=np_oracle.get_padding(k, 1))
+        else:  # ResBlock2, hifigan.py:71-76
+            xt = F.conv1d(F.leaky_relu(x, 0.1), w[f"{prefix}.convs.{m}.weight"],
+                          w[f"{prefix}.convs.{m}.bias"], dilation=d,
+                          padding=np_oracle.get_padding(k, d))
+        x = xt + x
+    return x
+
+
+def _trunk(w, cfg, mel):
+    x = F.conv1d(mel, w["conv_pre.weight"], w["conv_pre.bias"], padding=3)
+    n_k = len(cfg["resblock_kernel_sizes"])
+    two = str(cfg["resblock"]) == "1"
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        x = F.conv_transpose1d(F.leaky_relu(x, 0.1), w[f"ups.{i}.weight"], w[f"ups.{i}.bias"],
+                               stride=u, padding=(k - u) // 2)
+        xs = None
+        for j, (rk, rd) in enumerate(zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"])):
+            r = _resblock(w, f"resblocks.{i * n_k + j}", x, rk, rd, two)
+            xs = r if xs is None else xs + r
+        x = xs / n_k
+    return x
+
+
+@torch.no_grad()
+def hifigan_forward(folded, cfg, mel):
+    """Models/hifigan.py:108-124 from a folded state dict (see ``fold_state``)."""
+    x = _trunk(folded, cfg, mel)
+    x = F.conv1d(F.leaky_relu(x), folded["conv_post.weight"], folded["conv_post.bias"], padding=3)
+    return torch.tanh(x).squeeze(1)
+
+
+@torch.no_grad()
+def istftnet_forward(folded, cfg, mel):
+    """Models/istftnet.py:299-318."""
+    x = _trunk(folded, cfg, mel)
+    x = F.pad(F.leaky_relu(x), (1, 0), mode="reflect")
+    x = F.conv1d(x, folded["conv_post.weight"], folded["conv_post.bias"], padding=3)
+    n_fft = int(cfg["gen_istft_n_fft"])
+    hop = int(cfg["gen_istft_hop_size"])
+    nb = n_fft // 2 + 1
+    spec = torch.exp(x[:, :nb]) * torch.exp(1j * torch.sin(x[:, nb:]))
+    return torch.istft(spec, n_fft, hop, n_fft, window=torch.hann_window(n_fft))
