@@ -1,0 +1,174 @@
+/* nvse_b200.h -- C ABI of the B200-native (sm_100a) time-domain vocoding hot path.
+ *
+ * The reference (Andong-Li-speech/Neural-Vocoders-as-Speech-Enhancers) is pure Python /
+ * PyTorch and has no FFI of its own; its boundary for this path is a Python API
+ * (SURVEY.md §8b).  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference checkout).  The Python drop-ins in
+ * neural-vocoders-as-speech-enhancers_b200/{dataset.py,Models/} bind these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All tensor pointers are DEVICE
+ *     pointers unless the name ends in _host.  `stream` is a cudaStream_t / CUstream.
+ *   - every function returns 0 on success, non-zero on failure; nvse_last_error()
+ *     returns a thread-local description of the last failure.
+ *   - the caller owns every buffer, including workspaces; the library owns only what a
+ *     handle holds (packed weights, constant tables).  One handle per device, not
+ *     re-entrant per handle.  Work is enqueued on `stream`; nothing synchronises.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef NVSE_B200_H_
+#define NVSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NVSE_API __attribute__((visibility("default")))
+#else
+#define NVSE_API
+#endif
+
+#define NVSE_ABI_VERSION 1
+
+enum {
+  NVSE_OK = 0,
+  NVSE_ERR_INVALID = 1,     /* bad argument / shape */
+  NVSE_ERR_CUDA = 2,        /* CUDA runtime error */
+  NVSE_ERR_UNSUPPORTED = 3, /* valid for the reference, not implemented by this library */
+  NVSE_ERR_STATE = 4        /* handle not ready (e.g. weights missing) */
+};
+
+enum { NVSE_PRECISION_F32 = 0, NVSE_PRECISION_BF16 = 1 };
+enum { NVSE_GEN_HIFIGAN = 0, NVSE_GEN_ISTFTNET = 1 };
+
+NVSE_API int nvse_abi_version(void);
+NVSE_API const char* nvse_last_error(void);
+/* Number of kernel launches issued by this library in the calling process so far
+ * (bench.py reports the delta over the timed region as `gpu_launches`). */
+NVSE_API uint64_t nvse_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Front-end: dataset.mel_spectrogram  (dataset.py:53-91)
+ *   reflect-pad n_fft/2 | frame (n_fft, hop) | x window | R2C FFT | magnitude |
+ *   mel_basis @ . | log(clamp(., 1e-5))        -- one fused kernel, fp32.
+ * The handle replaces the reference's per-parameter cache `mel_window[param_string]`
+ * (dataset.py:45-50,68-76): it holds the window, the mel basis and the FFT twiddles.
+ * ---------------------------------------------------------------------------------- */
+typedef struct nvse_frontend nvse_frontend;
+
+/* window_host: [n_fft] (a win_size < n_fft window must be centre-padded by the caller,
+ * as torch.stft does).  mel_basis_host: [n_mels, n_fft/2+1] row-major (librosa layout).
+ * Supported: n_fft == 1024, hop >= 1, 1 <= n_mels <= 256. */
+NVSE_API int nvse_frontend_create(int n_fft, int hop, int n_mels, const float* window_host,
+                         const float* mel_basis_host, nvse_frontend** out);
+NVSE_API int nvse_frontend_destroy(nvse_frontend* fe);
+/* frames = 1 + T / hop  (torch.stft center=True, dataset.py:78-86) */
+NVSE_API int64_t nvse_frontend_num_frames(const nvse_frontend* fe, int64_t T);
+/* y: [B, T] fp32 with row stride y_row_stride (elements); out: [B, n_mels, F] fp32.
+ * Requires T > n_fft/2 (reflect padding), like torch.stft. */
+NVSE_API int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
+                          int64_t y_row_stride, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Generator: Models.HiFiGAN / Models.iSTFTNet forward
+ *   (Models/hifigan.py:83-133, Models/istftnet.py:271-328), hyper-parameters as in
+ *   cfgs/hifigan_v1_config.json:28-33 and cfgs/istftnet_config.json:28-35.
+ * ---------------------------------------------------------------------------------- */
+#define NVSE_MAX_UPS 8
+#define NVSE_MAX_KERNELS 8
+#define NVSE_MAX_DILATIONS 8
+
+typedef struct nvse_generator_config {
+  int32_t kind;                 /* NVSE_GEN_HIFIGAN | NVSE_GEN_ISTFTNET  (h.model_name) */
+  int32_t in_channels;          /* 80, hard-coded at hifigan.py:89 */
+  int32_t initial_channel;      /* h.upsample_initial_channel */
+  int32_t num_upsamples;        /* len(h.upsample_rates) */
+  int32_t upsample_rates[NVSE_MAX_UPS];
+  int32_t upsample_kernel_sizes[NVSE_MAX_UPS];
+  int32_t resblock_type;        /* 1 | 2  (h.resblock) */
+  int32_t num_kernels;          /* len(h.resblock_kernel_sizes) */
+  int32_t resblock_kernel_sizes[NVSE_MAX_KERNELS];
+  int32_t num_dilations[NVSE_MAX_KERNELS];
+  int32_t resblock_dilations[NVSE_MAX_KERNELS][NVSE_MAX_DILATIONS];
+  int32_t istft_n_fft;          /* h.gen_istft_n_fft  (iSTFTNet only) */
+  int32_t istft_hop;            /* h.gen_istft_hop_size */
+} nvse_generator_config;
+
+typedef struct nvse_generator nvse_generator;
+
+NVSE_API int nvse_generator_create(const nvse_generator_config* cfg, nvse_generator** out);
+NVSE_API int nvse_generator_destroy(nvse_generator* g);
+
+/* Load one FOLDED fp32 tensor (weight-norm already removed, see nvse_weight_norm_fold_f32)
+ * by its reference state-dict name after remove_weight_norm(): "conv_pre.weight",
+ * "conv_pre.bias", "ups.<i>.weight", "resblocks.<n>.convs1.<m>.weight", "conv_post.bias"...
+ * PyTorch layouts: Conv1d [Cout,Cin,k], ConvTranspose1d [Cin,Cout,k], bias [Cout].
+ * The data is copied/re-packed into the handle on `stream`. */
+NVSE_API int nvse_generator_set_weight(nvse_generator* g, const char* name, const float* data,
+                              const int64_t* shape, int ndim, void* stream);
+/* Verifies every tensor was set and builds the bf16 tensor-core weight images. */
+NVSE_API int nvse_generator_finalize(nvse_generator* g, void* stream);
+
+/* samples out per mel frame in: prod(upsample_rates) (* istft_hop for iSTFTNet) */
+NVSE_API int64_t nvse_generator_out_samples(const nvse_generator* g, int64_t frames);
+NVSE_API size_t nvse_generator_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames, int precision);
+/* mel: [B, in_channels, frames] fp32 (the reference's layout); out: [B, out_samples] fp32.
+ * precision: NVSE_PRECISION_F32 (CUDA-core fp32 everywhere) or NVSE_PRECISION_BF16
+ * (tcgen05 bf16 operands / fp32 accumulate for the upsampling and MRF convolutions,
+ * fp32 residual stream, fp32 conv_pre / conv_post). */
+NVSE_API int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
+                           void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Layer-level entry points: the same kernels the generator launches, exposed so the
+ * parity tests can check each shape class in isolation.
+ * Activations here are CHANNELS-LAST fp32 [B, T, C] (the library's internal layout).
+ * ---------------------------------------------------------------------------------- */
+
+/* torch.nn.utils.weight_norm fold (remove_weight_norm, hifigan.py:52-56,126-133):
+ * w[r,:] = g[r] * v[r,:] / ||v[r,:]||_2,  v: [rows, cols]. */
+NVSE_API int nvse_weight_norm_fold_f32(const float* v, const float* g, float* w, int64_t rows, int64_t cols, void* stream);
+
+/* [B, C, T] -> [B, T, C] and back (module-boundary layout changes). */
+NVSE_API int nvse_transpose_bct_to_btc_f32(const float* x, float* y, int64_t B, int64_t C, int64_t T, void* stream);
+NVSE_API int nvse_transpose_btc_to_bct_f32(const float* x, float* y, int64_t B, int64_t T, int64_t C, void* stream);
+
+/* y = [accumulate ? y : 0] + out_scale * ( conv1d(lrelu(x, in_slope), w, dilation, "same") + bias [+ residual] )
+ * w: [Cout, Cin, k] (PyTorch Conv1d layout), k odd.  in_slope = 1 disables the activation.
+ * Covers Conv1d + the fused leaky_relu / residual / MRF-average of hifigan.py:45-49,113-119. */
+NVSE_API int nvse_conv1d_f32(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                    int64_t B, int64_t T, int Cin, int Cout, int k, int dilation,
+                    float in_slope, float out_scale, int accumulate, void* stream);
+/* Same contract on the tcgen05 path (bf16 operands, fp32 accumulate).  Cin, Cout multiples of 16. */
+NVSE_API int nvse_conv1d_bf16(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                     int64_t B, int64_t T, int Cin, int Cout, int k, int dilation,
+                     float in_slope, float out_scale, int accumulate, void* stream);
+
+/* y = conv_transpose1d(lrelu(x, in_slope), w, stride, padding) + bias;  w: [Cin, Cout, k]
+ * (hifigan.py:93-96,111-112).  T_out = (T-1)*stride - 2*padding + k. */
+NVSE_API int nvse_conv_transpose1d_f32(const float* x, const float* w, const float* bias, float* y,
+                              int64_t B, int64_t T, int Cin, int Cout, int k, int stride, int padding,
+                              float in_slope, void* stream);
+NVSE_API int nvse_conv_transpose1d_bf16(const float* x, const float* w, const float* bias, float* y,
+                               int64_t B, int64_t T, int Cin, int Cout, int k, int stride, int padding,
+                               float in_slope, void* stream);
+
+/* iSTFT head, istftnet.py:314-316,183-188:  z: [B, Tp, n_fft+2] channels-last conv_post output;
+ * mag = exp(z[..., :n_fft/2+1]), phase = sin(z[..., n_fft/2+1:]); out: [B, hop*(Tp-1)].
+ * Supported: n_fft in {4..64} even, hop dividing n_fft. */
+NVSE_API int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, void* stream);
+
+/* The tensor-core kernels bound every mbarrier wait (a protocol bug must never hang the GPU); a
+ * tripped timeout sets a device flag and later tensor-core launches return without computing.
+ * *flag = 1 if it is set; reset != 0 clears it.  Synchronises the device. */
+NVSE_API int nvse_tc_abort_status(int reset, int* flag);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVSE_B200_H_ */

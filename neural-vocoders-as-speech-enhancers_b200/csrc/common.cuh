@@ -1,0 +1,57 @@
+// Shared host/device helpers for the nvse_b200 library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/nvse_b200.h"
+
+namespace nvse {
+
+// ---- error plumbing ------------------------------------------------------------------
+std::string& last_error_slot();
+int fail(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define NVSE_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::nvse::fail(NVSE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                          __FILE__, __LINE__);                                             \
+  } while (0)
+
+// Call right after a <<<>>> launch: counts it and surfaces launch-configuration errors.
+#define NVSE_LAUNCH_CHECK(name)                                                            \
+  do {                                                                                     \
+    ::nvse::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess)                                                                 \
+      return ::nvse::fail(NVSE_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define NVSE_REQUIRE(cond, code, ...)                     \
+  do {                                                    \
+    if (!(cond)) return ::nvse::fail(code, __VA_ARGS__);  \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kMaxTaps = 16;
+
+// One "tap-list" convolution over channels-last activations.  A plain dilated Conv1d is a
+// tap list with offsets j*d - pad; one phase of a ConvTranspose1d is a short tap list with
+// an output row map  row = out_mul * t + out_add  (polyphase decomposition).
+struct ConvTaps {
+  int ntaps;
+  int off[kMaxTaps];   // input row offset of tap i relative to the output row index t
+  int widx[kMaxTaps];  // which [Cin x Cout] slice of the packed weight tensor tap i uses
+};
+
+}  // namespace nvse

@@ -1,0 +1,39 @@
+// Launch interface of the fp32 tap-list convolution kernels (conv_f32.cu).
+#pragma once
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace nvse {
+
+struct ConvF32Args {
+  const float* x;     // [B, Tin_actual, Cin] channels-last
+  int64_t x_bstride;  // elements between batch items of x
+  int Tin;            // rows addressable by taps (virtual length when reflect_left > 0)
+  int Cin;
+  const float* w;     // [slices][Cin][Cout]
+  const float* bias;  // [Cout] or null
+  const float* residual;  // same shape as y, or null
+  float* y;           // [B, Tout, Cout]
+  int64_t y_bstride;
+  int Tout;
+  int Cout;
+  ConvTaps taps;
+  int out_mul, out_add;  // output row = out_mul * t + out_add
+  int Trows;             // t runs over [0, Trows)
+  float in_slope;        // leaky_relu slope applied to x on load (1 = identity)
+  float out_scale;       // y = [accumulate ? y : 0] + out_scale * (conv + bias + residual)
+  int accumulate;
+  int out_act;           // 0 none, 1 tanh
+  int reflect_left;      // x is viewed through ReflectionPad1d((reflect_left, 0)) (istftnet.py:296,312)
+};
+
+int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st);
+int launch_repack_weight(const float* src, float* dst, int Cin, int Cout, int k, bool transposed, cudaStream_t st);
+int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st);
+void conv1d_taps(int k, int dilation, ConvTaps* taps);
+// taps of output phase `phase` of a ConvTranspose1d; returns the tap count or -1 if > kMaxTaps
+int conv_transpose_phase_taps(int k, int stride, int padding, int phase, ConvTaps* taps);
+
+}  // namespace nvse

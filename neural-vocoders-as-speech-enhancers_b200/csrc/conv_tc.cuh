@@ -1,0 +1,47 @@
+// Launch interface of the tcgen05 (5th-gen tensor core) tap-list convolution (conv_tc.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace nvse {
+
+// Weight image for the tensor-core kernel: bf16, laid out as the exact shared-memory image of
+// every (tap slice, K-chunk) stage so that one cp.async.bulk (TMA 1-D) moves a stage:
+//   [slice j][ci / KC][(ci % KC) / 8][co][ci % 8],   KC = min(Cin, 64)
+// which is the canonical no-swizzle K-major UMMA layout (8 x 16-byte core matrices).
+inline int tc_kchunk(int Cin) { return Cin < 64 ? Cin : 64; }
+inline size_t tc_weight_image_elems(int Cin, int Cout, int k) { return (size_t)Cin * Cout * k; }
+inline bool tc_supported(int Cin, int Cout) {
+  return (Cin == 32 || Cin == 64 || Cin == 128 || Cin == 256 || Cin == 512) &&
+         (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256);
+}
+
+struct ConvTcArgs {
+  const void* x;       // [B, Tin, Cin] channels-last: fp32 (leaky_relu fused on load) or bf16 (used as is)
+  int64_t x_bstride;   // elements
+  int Tin;
+  int Cin, Cout;
+  int in_bf16;
+  const __nv_bfloat16* wimg;
+  const float* bias;
+  const float* residual;  // fp32, same shape as y (fp32 output only; added after the out_slope activation)
+  void* y;                // [B, Tout, Cout] fp32, or bf16 when out_bf16
+  int64_t y_bstride;
+  int Tout;
+  int out_bf16;           // y = bf16(lrelu(conv + bias, out_slope))
+  ConvTaps taps;
+  int out_mul, out_add, Trows;
+  float in_slope, out_slope, out_scale;
+  int accumulate;
+  int split_act;          // stage activations as hi + lo bf16 planes (fp32 input only): 2 MMAs per K step
+};
+
+// shared memory one CTA of the kernel needs for this shape (used to decide whether split fits)
+size_t tc_smem_bytes(int Cin, int Cout, int tap_span, bool split, int stages);
+bool tc_split_fits(int Cin, int Cout, int tap_span);
+
+int launch_conv_tc(const ConvTcArgs& a, int64_t B, cudaStream_t st);
+// fp32 [k][Cin][Cout] (Layer::w layout) -> bf16 tensor-core image
+int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int k, cudaStream_t st);
+
+}  // namespace nvse

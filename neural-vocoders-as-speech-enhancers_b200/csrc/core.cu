@@ -1,0 +1,108 @@
+// Error plumbing, launch accounting and the small layout / weight-norm kernels.
+#include "common.cuh"
+
+namespace nvse {
+
+std::atomic<uint64_t> g_launches{0};
+
+std::string& last_error_slot() {
+  static thread_local std::string slot;
+  return slot;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_slot() = buf;
+  return code;
+}
+
+namespace {
+
+// w[r,:] = g[r] * v[r,:] / ||v[r,:]||   (one CTA per row)
+__global__ void __launch_bounds__(256) weight_norm_fold_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                                                float* __restrict__ w, int64_t cols) {
+  __shared__ float red[8];
+  __shared__ float scale;
+  const int64_t r = blockIdx.x;
+  const float* vr = v + r * cols;
+  float acc = 0.0f;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) acc = fmaf(vr[c], vr[c], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    scale = g[r] / sqrtf(s);
+  }
+  __syncthreads();
+  const float sc = scale;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) w[r * cols + c] = vr[c] * sc;
+}
+
+// y[b, j, i] = x[b, i, j] for x: [B, R, C]  (32x32 tiles through padded smem)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t R,
+                                                         int64_t C) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* xb = x + b * R * C;
+  float* yb = y + b * R * C;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < R && c < C) ? xb[r * C + c] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t c = c0 + ty + i, r = r0 + tx;
+    if (r < R && c < C) yb[c * R + r] = tile[tx][ty + i];
+  }
+}
+
+}  // namespace
+
+int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st) {
+  if (B == 0 || R == 0 || C == 0) return NVSE_OK;
+  NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "transpose: batch %lld exceeds 65535", (long long)B);
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
+  NVSE_REQUIRE((R + 31) / 32 <= 65535, NVSE_ERR_INVALID, "transpose: too many rows");
+  transpose_kernel<<<grid, 256, 0, st>>>(x, y, R, C);
+  NVSE_LAUNCH_CHECK("transpose_kernel");
+  return NVSE_OK;
+}
+
+}  // namespace nvse
+
+extern "C" int nvse_abi_version(void) { return NVSE_ABI_VERSION; }
+extern "C" const char* nvse_last_error(void) { return nvse::last_error_slot().c_str(); }
+extern "C" uint64_t nvse_launch_count(void) { return nvse::g_launches.load(); }
+
+extern "C" int nvse_weight_norm_fold_f32(const float* v, const float* g, float* w, int64_t rows, int64_t cols,
+                                         void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(v && g && w && rows > 0 && cols > 0, NVSE_ERR_INVALID, "nvse_weight_norm_fold_f32: bad argument");
+  NVSE_REQUIRE(rows <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_weight_norm_fold_f32: too many rows");
+  weight_norm_fold_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(v, g, w, cols);
+  NVSE_LAUNCH_CHECK("weight_norm_fold_kernel");
+  return NVSE_OK;
+}
+
+extern "C" int nvse_transpose_bct_to_btc_f32(const float* x, float* y, int64_t B, int64_t C, int64_t T, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(x && y && B >= 0 && C >= 0 && T >= 0, NVSE_ERR_INVALID, "nvse_transpose_bct_to_btc_f32: bad argument");
+  return launch_transpose(x, y, B, C, T, as_stream(stream));
+}
+
+extern "C" int nvse_transpose_btc_to_bct_f32(const float* x, float* y, int64_t B, int64_t T, int64_t C, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(x && y && B >= 0 && C >= 0 && T >= 0, NVSE_ERR_INVALID, "nvse_transpose_btc_to_bct_f32: bad argument");
+  return launch_transpose(x, y, B, T, C, as_stream(stream));
+}

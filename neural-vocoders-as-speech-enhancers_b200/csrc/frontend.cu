@@ -1,0 +1,330 @@
+// Fused log-mel front-end: dataset.mel_spectrogram (reference dataset.py:53-91).
+//
+//   reflect-pad | frame | x Hann | 1024-pt real FFT | magnitude | mel projection | log-clamp
+//
+// One warp transforms TWO consecutive frames of one utterance at once: the two real frames
+// are packed as z = a + i*b and pushed through ONE 1024-point complex FFT, factored
+// 32 x 32 (Cooley-Tukey): a radix-32 DIF butterfly network entirely in registers over the
+// strided samples each lane owns, a twiddle multiply, a 32x32 transpose through padded
+// shared memory, and a second in-register radix-32 network.  The two spectra are separated
+// with the Hermitian identities using warp shuffles (lane L pairs with lane 32-L), so no
+// post-twiddle is needed.  Magnitudes go to shared memory and the (banded) mel basis is
+// applied from a tap-major packed copy so that lanes read consecutive weights.
+// Nothing but the waveform is read from HBM and nothing but the log-mel is written: the
+// [B,513,F] complex / magnitude tensors of the reference never exist.
+#include "common.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace nvse {
+
+namespace {
+
+constexpr int kNfft = 1024;
+constexpr int kBins = kNfft / 2 + 1;
+constexpr int kWarpsPerCta = 8;
+constexpr int kTransposeStride = 33;                       // 32 + 1 pad: conflict-free both ways
+constexpr int kWarpSmemFloats = 2 * 32 * kTransposeStride;  // re plane + im plane
+
+__host__ __device__ constexpr int brev5(int v) {
+  return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+
+// cos(pi*j/16), j = 0..8
+__device__ __forceinline__ constexpr float c16(int j) {
+  switch (j) {
+    case 0: return 1.0f;
+    case 1: return 0.98078528040323044913f;
+    case 2: return 0.92387953251128675613f;
+    case 3: return 0.83146961230254523708f;
+    case 4: return 0.70710678118654752440f;
+    case 5: return 0.55557023301960222474f;
+    case 6: return 0.38268343236508977173f;
+    case 7: return 0.19509032201612826785f;
+    default: return 0.0f;
+  }
+}
+__device__ __forceinline__ constexpr float cos32(int j) { return j <= 8 ? c16(j) : -c16(16 - j); }  // cos(2*pi*j/32), j<16
+__device__ __forceinline__ constexpr float sin32(int j) { return j <= 8 ? c16(8 - j) : c16(j - 8); }  // sin(2*pi*j/32), j<16
+
+// In-place radix-2 decimation-in-frequency FFT of 32 complex values held in registers.
+// Forward transform (e^{-i...}); X[k] ends up at index brev5(k).  Everything is unrolled so
+// all indices and twiddles are compile-time constants.
+__device__ __forceinline__ void fft32_dif(float (&re)[32], float (&im)[32]) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int g = 0; g < 32; g += 2 * half) {
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const int a = g + i, b = g + i + half;
+        const int tw = i * (16 / half);  // W_32^tw
+        const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
+        re[a] = ar + br;
+        im[a] = ai + bi;
+        const float dr = ar - br, di = ai - bi;
+        if (tw == 0) {
+          re[b] = dr;
+          im[b] = di;
+        } else if (tw == 8) {  // multiply by -i
+          re[b] = di;
+          im[b] = -dr;
+        } else {
+          const float c = cos32(tw), s = sin32(tw);  // W = c - i s
+          re[b] = dr * c + di * s;
+          im[b] = di * c - dr * s;
+        }
+      }
+    }
+  }
+}
+
+struct FrontendParams {
+  const float* y;
+  int64_t y_stride;
+  int64_t T;
+  int64_t B;
+  int64_t F;
+  int64_t pairs;  // ceil(F / 2)
+  int hop;
+  int n_mels;
+  const float* window;   // [1024]
+  const float2* twiddle;  // [32][32]: twiddle[k1*32 + l] = exp(-2*pi*i*l*k1/1024)
+  const float* wpack;     // [max_band][n_mels] tap-major banded mel weights
+  const int* band_lo;     // [n_mels]
+  const int* band_len;    // [n_mels]
+  float* out;             // [B, n_mels, F]
+};
+
+__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t T) {
+  if (i < 0) i = -i;
+  if (i >= T) i = 2 * (T - 1) - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) mel_frontend_kernel(const FrontendParams p) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t task = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  if (task >= p.B * p.pairs) return;  // warp-uniform; only __syncwarp below
+  float* sre = smem + warp * kWarpSmemFloats;
+  float* sim = sre + 32 * kTransposeStride;
+
+  const int64_t b = task / p.pairs;
+  const int64_t f0 = 2 * (task % p.pairs);
+  const bool has_b = (f0 + 1) < p.F;
+  const float* __restrict__ yrow = p.y + b * p.y_stride;
+  const int64_t sa = f0 * p.hop - kNfft / 2;  // first sample of frame a in un-padded coordinates
+  const int64_t sb = sa + p.hop;
+
+  float re[32], im[32];
+  if (sa >= 0 && sb + kNfft <= p.T && has_b) {
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      const int n = lane + 32 * m;
+      const float w = __ldg(p.window + n);
+      re[m] = __ldg(yrow + sa + n) * w;
+      im[m] = __ldg(yrow + sb + n) * w;
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      const int n = lane + 32 * m;
+      const float w = __ldg(p.window + n);
+      re[m] = __ldg(yrow + reflect_index(sa + n, p.T)) * w;
+      im[m] = has_b ? __ldg(yrow + reflect_index(sb + n, p.T)) * w : 0.0f;
+    }
+  }
+
+  // pass 1: 32-point DFTs over m (samples lane + 32 m)
+  fft32_dif(re, im);
+
+  // twiddle by W_1024^(lane*k1), then transpose so that lane k1 owns all 32 values of column k1
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    const int r = brev5(k1);
+    const float2 t = __ldg(p.twiddle + k1 * 32 + lane);
+    sre[k1 * kTransposeStride + lane] = re[r] * t.x - im[r] * t.y;
+    sim[k1 * kTransposeStride + lane] = re[r] * t.y + im[r] * t.x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {
+    re[l] = sre[lane * kTransposeStride + l];
+    im[l] = sim[lane * kTransposeStride + l];
+  }
+  __syncwarp();
+
+  // pass 2: 32-point DFTs over l;  Z[lane + 32*k2] is now at register brev5(k2)
+  fft32_dif(re, im);
+
+  // Separate the two real spectra:  A[k] = (Z[k] + conj Z[N-k]) / 2,  B[k] = (Z[k] - conj Z[N-k]) / 2i.
+  // For lane L != 0 the partner bin N-k lives in lane 32-L at k2' = 31-k2; lane 0 pairs with itself.
+  float* mag_a = sre;  // [513], reuses the transpose planes (each plane holds 1056 floats)
+  float* mag_b = sim;
+  const int src_lane = (32 - lane) & 31;
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+    float pr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], src_lane);
+    float pi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], src_lane);
+    if (lane == 0) {
+      pr = re[brev5((32 - k2) & 31)];
+      pi = im[brev5((32 - k2) & 31)];
+    }
+    const float ar = zr + pr, ai = zi - pi;
+    const float br = zr - pr, bi = zi + pi;
+    mag_a[lane + 32 * k2] = 0.5f * sqrtf(ar * ar + ai * ai);
+    mag_b[lane + 32 * k2] = 0.5f * sqrtf(br * br + bi * bi);
+  }
+  if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
+    mag_a[512] = fabsf(re[brev5(16)]);
+    mag_b[512] = fabsf(im[brev5(16)]);
+  }
+  __syncwarp();
+
+  // mel projection (banded) + log-clamp
+  for (int m = lane; m < p.n_mels; m += 32) {
+    const int lo = __ldg(p.band_lo + m), len = __ldg(p.band_len + m);
+    float acc_a = 0.0f, acc_b = 0.0f;
+    for (int t = 0; t < len; ++t) {
+      const float w = __ldg(p.wpack + (int64_t)t * p.n_mels + m);
+      acc_a = fmaf(w, mag_a[lo + t], acc_a);
+      acc_b = fmaf(w, mag_b[lo + t], acc_b);
+    }
+    float* o = p.out + (b * p.n_mels + m) * p.F + f0;
+    o[0] = logf(fmaxf(acc_a, 1e-5f));
+    if (has_b) o[1] = logf(fmaxf(acc_b, 1e-5f));
+  }
+}
+
+}  // namespace
+
+}  // namespace nvse
+
+struct nvse_frontend {
+  int n_fft, hop, n_mels, max_band;
+  float* window = nullptr;
+  float2* twiddle = nullptr;
+  float* wpack = nullptr;
+  int* band_lo = nullptr;
+  int* band_len = nullptr;
+};
+
+extern "C" int nvse_frontend_create(int n_fft, int hop, int n_mels, const float* window_host,
+                                    const float* mel_basis_host, nvse_frontend** out) {
+  using namespace nvse;
+  NVSE_REQUIRE(out && window_host && mel_basis_host, NVSE_ERR_INVALID, "nvse_frontend_create: null argument");
+  NVSE_REQUIRE(n_fft == kNfft, NVSE_ERR_UNSUPPORTED,
+               "nvse_frontend_create: n_fft=%d not supported (this build implements n_fft=1024)", n_fft);
+  NVSE_REQUIRE(hop >= 1 && n_mels >= 1 && n_mels <= 256, NVSE_ERR_INVALID,
+               "nvse_frontend_create: bad hop=%d / n_mels=%d", hop, n_mels);
+  int ndev = 0;
+  NVSE_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  NVSE_REQUIRE(ndev > 0, NVSE_ERR_CUDA, "nvse_frontend_create: no CUDA device (there is no CPU fallback)");
+
+  // band structure of the mel basis: [lo, lo+len) covers every non-zero of the row
+  std::vector<int> lo(n_mels, 0), len(n_mels, 0);
+  int max_band = 1;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < kBins; ++k)
+      if (mel_basis_host[(size_t)m * kBins + k] != 0.0f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first >= 0) {
+      lo[m] = first;
+      len[m] = last - first + 1;
+      if (len[m] > max_band) max_band = len[m];
+    }
+  }
+  std::vector<float> wpack((size_t)max_band * n_mels, 0.0f);
+  for (int m = 0; m < n_mels; ++m)
+    for (int t = 0; t < len[m]; ++t) wpack[(size_t)t * n_mels + m] = mel_basis_host[(size_t)m * kBins + lo[m] + t];
+  std::vector<float2> tw(32 * 32);
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const double a = -2.0 * M_PI * (double)(l * k1) / (double)kNfft;
+      tw[k1 * 32 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+
+  nvse_frontend* fe = new nvse_frontend();
+  fe->n_fft = n_fft;
+  fe->hop = hop;
+  fe->n_mels = n_mels;
+  fe->max_band = max_band;
+  auto cleanup = [&]() { nvse_frontend_destroy(fe); };
+#define FE_TRY(expr)                                                                           \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      cleanup();                                                                               \
+      return fail(NVSE_ERR_CUDA, "nvse_frontend_create: %s: %s", #expr, cudaGetErrorString(_e)); \
+    }                                                                                          \
+  } while (0)
+  FE_TRY(cudaMalloc(&fe->window, sizeof(float) * kNfft));
+  FE_TRY(cudaMalloc(&fe->twiddle, sizeof(float2) * tw.size()));
+  FE_TRY(cudaMalloc(&fe->wpack, sizeof(float) * wpack.size()));
+  FE_TRY(cudaMalloc(&fe->band_lo, sizeof(int) * n_mels));
+  FE_TRY(cudaMalloc(&fe->band_len, sizeof(int) * n_mels));
+  FE_TRY(cudaMemcpy(fe->window, window_host, sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+  FE_TRY(cudaMemcpy(fe->twiddle, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+  FE_TRY(cudaMemcpy(fe->wpack, wpack.data(), sizeof(float) * wpack.size(), cudaMemcpyHostToDevice));
+  FE_TRY(cudaMemcpy(fe->band_lo, lo.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+  FE_TRY(cudaMemcpy(fe->band_len, len.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+#undef FE_TRY
+  *out = fe;
+  return NVSE_OK;
+}
+
+extern "C" int nvse_frontend_destroy(nvse_frontend* fe) {
+  if (!fe) return NVSE_OK;
+  cudaFree(fe->window);
+  cudaFree(fe->twiddle);
+  cudaFree(fe->wpack);
+  cudaFree(fe->band_lo);
+  cudaFree(fe->band_len);
+  delete fe;
+  return NVSE_OK;
+}
+
+extern "C" int64_t nvse_frontend_num_frames(const nvse_frontend* fe, int64_t T) {
+  if (!fe || T < 0) return -1;
+  return 1 + T / fe->hop;
+}
+
+extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
+                                     int64_t y_row_stride, float* out, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(fe && y && out, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: null argument");
+  NVSE_REQUIRE(B >= 0 && y_row_stride >= T, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: bad B/stride");
+  // torch.stft(center=True, pad_mode='reflect') raises unless pad < T
+  NVSE_REQUIRE(T > fe->n_fft / 2, NVSE_ERR_INVALID,
+               "nvse_frontend_mel_f32: reflect padding needs T > n_fft/2 (T=%lld, n_fft=%d)", (long long)T, fe->n_fft);
+  if (B == 0) return NVSE_OK;
+  FrontendParams p;
+  p.y = y;
+  p.y_stride = y_row_stride;
+  p.T = T;
+  p.B = B;
+  p.F = 1 + T / fe->hop;
+  p.pairs = (p.F + 1) / 2;
+  p.hop = fe->hop;
+  p.n_mels = fe->n_mels;
+  p.window = fe->window;
+  p.twiddle = fe->twiddle;
+  p.wpack = fe->wpack;
+  p.band_lo = fe->band_lo;
+  p.band_len = fe->band_len;
+  p.out = out;
+  const int64_t tasks = B * p.pairs;
+  const int64_t ctas = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;
+  NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: problem too large for one launch");
+  const size_t smem = sizeof(float) * kWarpSmemFloats * kWarpsPerCta;
+  NVSE_CUDA_CHECK(cudaFuncSetAttribute(mel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mel_frontend_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, as_stream(stream)>>>(p);
+  NVSE_LAUNCH_CHECK("mel_frontend_kernel");
+  return NVSE_OK;
+}

@@ -1,0 +1,338 @@
+// Generator handle: HiFiGAN.forward (reference Models/hifigan.py:108-124) and
+// iSTFTNet.forward (Models/istftnet.py:299-318) as a fixed launch sequence over
+// channels-last activations.  The handle owns the packed weights; the caller owns the
+// workspace (four ping-pong activation buffers).
+#include "generator.cuh"
+#include "conv_tc.cuh"
+
+#include <cstring>
+
+namespace nvse {
+
+static int build_layers(nvse_generator* g) {
+  const nvse_generator_config& c = g->cfg;
+  auto add = [&](const std::string& name, bool transposed, int cin, int cout, int k, int dil, int stride, int pad) {
+    Layer L;
+    L.name = name;
+    L.transposed = transposed;
+    L.Cin = cin; L.Cout = cout; L.k = k; L.dilation = dil; L.stride = stride; L.padding = pad;
+    g->index[name] = (int)g->layers.size();
+    g->layers.push_back(L);
+  };
+  const int c0 = c.initial_channel;
+  add("conv_pre", false, c.in_channels, c0, 7, 1, 1, 3);  // hifigan.py:89
+  for (int i = 0; i < c.num_upsamples; ++i) {             // hifigan.py:93-96
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    add("ups." + std::to_string(i), true, c0 >> i, c0 >> (i + 1), k, 1, u, (k - u) / 2);
+  }
+  int ch = c0;
+  for (int i = 0; i < c.num_upsamples; ++i) {  // hifigan.py:98-102
+    ch = c0 >> (i + 1);
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const int k = c.resblock_kernel_sizes[j];
+      const std::string p = "resblocks." + std::to_string(i * c.num_kernels + j);
+      for (int m = 0; m < c.num_dilations[j]; ++m) {
+        const int d = c.resblock_dilations[j][m];
+        if (c.resblock_type == 1) {
+          add(p + ".convs1." + std::to_string(m), false, ch, ch, k, d, 1, (k * d - d) / 2);
+          add(p + ".convs2." + std::to_string(m), false, ch, ch, k, 1, 1, (k - 1) / 2);
+        } else {
+          add(p + ".convs." + std::to_string(m), false, ch, ch, k, d, 1, (k * d - d) / 2);
+        }
+      }
+    }
+  }
+  const int out_ch = c.kind == NVSE_GEN_HIFIGAN ? 1 : c.istft_n_fft + 2;  // hifigan.py:104, istftnet.py:293
+  add("conv_post", false, ch, out_ch, 7, 1, 1, 3);
+  return NVSE_OK;
+}
+
+// floats per batch item of the largest activation the forward ever holds
+static int64_t max_activation_elems(const nvse_generator* g, int64_t F) {
+  const nvse_generator_config& c = g->cfg;
+  int64_t m = std::max<int64_t>(F * c.in_channels, F * c.initial_channel);
+  int64_t T = F;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    T = (T - 1) * u - 2 * ((k - u) / 2) + k;
+    m = std::max<int64_t>(m, T * (c.initial_channel >> (i + 1)));
+  }
+  if (c.kind == NVSE_GEN_ISTFTNET) m = std::max<int64_t>(m, (T + 1) * (c.istft_n_fft + 2));
+  return m;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One Conv1d layer ("same" padding) with the fused prologue/epilogue, on the tensor-core path when
+// `tc` is set and the layer has a bf16 image, otherwise on the fp32 CUDA-core path.
+//   y = [accumulate ? y : 0] + out_scale * (conv(lrelu(x, in_slope)) + bias [+ residual])          (fp32 out)
+//   y = bf16(lrelu(conv(lrelu(x, in_slope)) + bias, out_slope))                                      (bf16 out)
+struct ConvIO {
+  const void* x; bool x_bf16; const float* residual; void* y; bool y_bf16;
+  float in_slope, out_slope, out_scale; int accumulate;
+};
+// fp32 out with out_slope != 1:  y = lrelu(conv + bias, out_slope)  (the fp32 c1 -> c2 intermediate of split layers)
+
+static int run_conv(const Layer& L, bool tc, const ConvIO& io, int64_t B, int64_t T, cudaStream_t st) {
+  ConvTaps taps;
+  conv1d_taps(L.k, L.dilation, &taps);
+  if (tc && L.w_bf16) {
+    ConvTcArgs a{};
+    a.x = io.x; a.x_bstride = T * L.Cin; a.Tin = (int)T; a.Cin = L.Cin; a.Cout = L.Cout; a.in_bf16 = io.x_bf16;
+    a.wimg = reinterpret_cast<const __nv_bfloat16*>(L.w_bf16); a.bias = L.bias; a.residual = io.residual;
+    a.y = io.y; a.y_bstride = T * L.Cout; a.Tout = (int)T; a.out_bf16 = io.y_bf16;
+    a.taps = taps; a.out_mul = 1; a.out_add = 0; a.Trows = (int)T;
+    a.in_slope = io.in_slope; a.out_slope = io.out_slope; a.out_scale = io.out_scale; a.accumulate = io.accumulate;
+    a.split_act = L.tc_split && !io.x_bf16;
+    return launch_conv_tc(a, B, st);
+  }
+  NVSE_REQUIRE(!io.x_bf16 && !io.y_bf16 && io.out_slope == 1.0f, NVSE_ERR_STATE, "layer %s: bf16 activations on the fp32 path", L.name.c_str());
+  ConvF32Args a{};
+  a.x = reinterpret_cast<const float*>(io.x); a.x_bstride = T * L.Cin; a.Tin = (int)T; a.Cin = L.Cin;
+  a.w = L.w; a.bias = L.bias; a.residual = io.residual;
+  a.y = reinterpret_cast<float*>(io.y); a.y_bstride = T * L.Cout; a.Tout = (int)T; a.Cout = L.Cout;
+  a.taps = taps; a.out_mul = 1; a.out_add = 0; a.Trows = (int)T;
+  a.in_slope = io.in_slope; a.out_scale = io.out_scale; a.accumulate = io.accumulate;
+  return launch_conv_f32(a, B, st);
+}
+
+// ConvTranspose1d as `stride` polyphase tap-list convolutions.
+static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
+                              cudaStream_t st) {
+  const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
+  for (int r = 0; r < L.stride && r < Tout; ++r) {
+    ConvTaps taps;
+    const int n = conv_transpose_phase_taps(L.k, L.stride, L.padding, r, &taps);
+    NVSE_REQUIRE(n > 0, NVSE_ERR_UNSUPPORTED, "ConvTranspose1d %s: unsupported k/stride", L.name.c_str());
+    const int trows = (int)((Tout - r + L.stride - 1) / L.stride);
+    if (tc && L.w_bf16) {
+      ConvTcArgs a{};
+      a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout;
+      a.wimg = reinterpret_cast<const __nv_bfloat16*>(L.w_bf16); a.bias = L.bias;
+      a.y = y; a.y_bstride = Tout * L.Cout; a.Tout = (int)Tout;
+      a.taps = taps; a.out_mul = L.stride; a.out_add = r; a.Trows = trows;
+      a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
+      a.split_act = L.tc_split;
+      if (int rc = launch_conv_tc(a, B, st)) return rc;
+    } else {
+      ConvF32Args a{};
+      a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin;
+      a.w = L.w; a.bias = L.bias;
+      a.y = y; a.y_bstride = Tout * L.Cout; a.Tout = (int)Tout; a.Cout = L.Cout;
+      a.taps = taps; a.out_mul = L.stride; a.out_add = r; a.Trows = trows;
+      a.in_slope = in_slope; a.out_scale = 1.0f;
+      if (int rc = launch_conv_f32(a, B, st)) return rc;
+    }
+  }
+  return NVSE_OK;
+}
+
+// tc = false: fp32 CUDA cores everywhere.  tc = true: tcgen05 for the upsamplers and the MRF
+// convolutions (bf16 operands, fp32 accumulate, fp32 residual stream; the c1 -> c2 intermediate of
+// a ResBlock1 pair is stored activated, in bf16); conv_pre / conv_post stay fp32.
+static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B, int64_t F, float* out, float* ws,
+                        int64_t buf_elems, cudaStream_t st) {
+  const nvse_generator_config& c = g->cfg;
+  float* bufA = ws;  // conv_pre output, then the MRF accumulator of every stage
+  float* bufU = ws + buf_elems;
+  float* bufR = ws + 2 * buf_elems;
+  float* bufT = ws + 3 * buf_elems;
+  const float slope = 0.1f;  // LRELU_SLOPE, hifigan.py:7
+
+  // [B, 80, F] -> channels-last, then conv_pre (hifigan.py:109)
+  if (int rc = launch_transpose(mel, bufR, B, c.in_channels, F, st)) return rc;
+  {
+    const ConvIO io{bufR, false, nullptr, bufA, false, 1.0f, 1.0f, 1.0f, 0};
+    if (int rc = run_conv(g->layer("conv_pre"), false, io, B, F, st)) return rc;
+  }
+  int64_t T = F;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const Layer& up = g->layer("ups." + std::to_string(i));
+    if (int rc = run_conv_transpose(up, tc, bufA, B, T, bufU, slope, st)) return rc;  // hifigan.py:111-112
+    T = (T - 1) * up.stride - 2 * up.padding + up.k;
+    const float inv = 1.0f / (float)c.num_kernels;  // hifigan.py:119
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const std::string p = "resblocks." + std::to_string(i * c.num_kernels + j);
+      const int nd = c.num_dilations[j];
+      const float* src = bufU;
+      for (int m = 0; m < nd; ++m) {
+        const bool last = (m == nd - 1);
+        float* dst = last ? bufA : (c.resblock_type == 1 ? bufR : (src == bufR ? bufT : bufR));
+        const float scale = last ? inv : 1.0f;
+        const int accum = last && j > 0;
+        if (c.resblock_type == 1) {  // hifigan.py:43-50
+          const Layer& c1 = g->layer(p + ".convs1." + std::to_string(m));
+          const Layer& c2 = g->layer(p + ".convs2." + std::to_string(m));
+          const bool on_tc = tc && c1.w_bf16 && c2.w_bf16;
+          const bool mid_bf16 = on_tc && !c2.tc_split;  // split layers keep the intermediate in fp32
+          // c1: xt = conv(lrelu(x));  on the tensor-core path xt is stored already activated for c2
+          const ConvIO io1{src, false, nullptr, bufT, mid_bf16, slope, on_tc ? slope : 1.0f, 1.0f, 0};
+          if (int rc = run_conv(c1, tc, io1, B, T, st)) return rc;
+          // c2: x' = conv(lrelu(xt)) + x, MRF scale/accumulate on the last pair
+          const ConvIO io2{bufT, mid_bf16, src, dst, false, on_tc ? 1.0f : slope, 1.0f, scale, accum};
+          if (int rc = run_conv(c2, tc, io2, B, T, st)) return rc;
+        } else {  // hifigan.py:71-76
+          const ConvIO io1{src, false, src, dst, false, slope, 1.0f, scale, accum};
+          if (int rc = run_conv(g->layer(p + ".convs." + std::to_string(m)), tc, io1, B, T, st)) return rc;
+        }
+        src = dst;
+      }
+    }
+  }
+  const Layer& post = g->layer("conv_post");
+  ConvF32Args a{};
+  a.x = bufA; a.x_bstride = T * post.Cin; a.Cin = post.Cin;
+  a.w = post.w; a.bias = post.bias; a.Cout = post.Cout;
+  conv1d_taps(post.k, 1, &a.taps);
+  a.out_mul = 1; a.out_add = 0; a.in_slope = 0.01f; a.out_scale = 1.0f;  // F.leaky_relu default slope, hifigan.py:120
+  if (c.kind == NVSE_GEN_HIFIGAN) {  // hifigan.py:120-124
+    a.Tin = a.Tout = a.Trows = (int)T; a.y = out; a.y_bstride = T * post.Cout; a.out_act = 1;
+    return launch_conv_f32(a, B, st);
+  }
+  // istftnet.py:311-318: lrelu(0.01) -> ReflectionPad1d((1,0)) -> conv_post -> exp / sin -> iSTFT
+  a.reflect_left = 1;
+  a.Tin = a.Tout = a.Trows = (int)T + 1; a.y = bufU; a.y_bstride = (T + 1) * post.Cout;
+  if (int rc = launch_conv_f32(a, B, st)) return rc;
+  return launch_istft_head(bufU, out, B, T + 1, c.istft_n_fft, c.istft_hop, st);
+}
+
+int finalize_bf16(nvse_generator* g, cudaStream_t st) {
+  for (Layer& L : g->layers) {
+    const bool wanted = L.name != "conv_pre" && L.name != "conv_post" && tc_supported(L.Cin, L.Cout);
+    if (!wanted) continue;
+    if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
+    if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_bf16), L.Cin, L.Cout, L.k, st)) return rc;
+    // Where bf16 rounding of the ACTIVATION operand costs the most SNR and the least time (the
+    // upsamplers: 3 % of the FLOPs; the <= 32-channel MRF stage: HBM-bound anyway) activations are
+    // fed as hi + lo bf16 pairs (tools/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
+    if (L.transposed) {
+      L.tc_split = tc_split_fits(L.Cin, L.Cout, (L.k + L.stride - 1) / L.stride - 1);
+    } else {
+      L.tc_split = L.Cout <= 32 && tc_split_fits(L.Cin, L.Cout, (L.k - 1) * L.dilation);
+    }
+  }
+  return NVSE_OK;
+}
+
+}  // namespace nvse
+
+using namespace nvse;
+
+extern "C" int nvse_generator_create(const nvse_generator_config* cfg, nvse_generator** out) {
+  NVSE_REQUIRE(cfg && out, NVSE_ERR_INVALID, "nvse_generator_create: null argument");
+  NVSE_REQUIRE(cfg->kind == NVSE_GEN_HIFIGAN || cfg->kind == NVSE_GEN_ISTFTNET, NVSE_ERR_INVALID, "bad generator kind %d", cfg->kind);
+  NVSE_REQUIRE(cfg->num_upsamples >= 1 && cfg->num_upsamples <= NVSE_MAX_UPS, NVSE_ERR_INVALID, "bad num_upsamples");
+  NVSE_REQUIRE(cfg->num_kernels >= 1 && cfg->num_kernels <= NVSE_MAX_KERNELS, NVSE_ERR_INVALID, "bad num_kernels");
+  NVSE_REQUIRE(cfg->resblock_type == 1 || cfg->resblock_type == 2, NVSE_ERR_INVALID, "resblock must be 1 or 2");
+  NVSE_REQUIRE(cfg->in_channels > 0 && cfg->in_channels % 16 == 0, NVSE_ERR_UNSUPPORTED, "in_channels must be a multiple of 16");
+  NVSE_REQUIRE(cfg->initial_channel > 0 && (cfg->initial_channel >> cfg->num_upsamples) >= 1 &&
+                   (cfg->initial_channel % (1 << cfg->num_upsamples)) == 0,
+               NVSE_ERR_INVALID, "upsample_initial_channel=%d is not divisible by 2^%d", cfg->initial_channel,
+               cfg->num_upsamples);
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+    NVSE_REQUIRE(u >= 1 && k >= u && (k - u) % 2 == 0 && (k + u - 1) / u <= kMaxTaps, NVSE_ERR_UNSUPPORTED,
+                 "upsample stage %d: rate %d / kernel %d unsupported", i, u, k);
+  }
+  for (int j = 0; j < cfg->num_kernels; ++j) {
+    const int k = cfg->resblock_kernel_sizes[j];
+    NVSE_REQUIRE(k >= 1 && (k & 1) && k <= kMaxTaps, NVSE_ERR_UNSUPPORTED, "resblock kernel size %d unsupported (odd, <= %d)", k, kMaxTaps);
+    NVSE_REQUIRE(cfg->num_dilations[j] >= 1 && cfg->num_dilations[j] <= NVSE_MAX_DILATIONS, NVSE_ERR_INVALID, "bad dilation count");
+    for (int m = 0; m < cfg->num_dilations[j]; ++m)
+      NVSE_REQUIRE(cfg->resblock_dilations[j][m] >= 1, NVSE_ERR_INVALID, "bad dilation");
+  }
+  if (cfg->kind == NVSE_GEN_ISTFTNET)
+    NVSE_REQUIRE(cfg->istft_n_fft >= 4 && cfg->istft_hop >= 1 && cfg->istft_n_fft % cfg->istft_hop == 0, NVSE_ERR_UNSUPPORTED,
+                 "istft n_fft=%d hop=%d unsupported", cfg->istft_n_fft, cfg->istft_hop);
+  int ndev = 0;
+  NVSE_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  NVSE_REQUIRE(ndev > 0, NVSE_ERR_CUDA, "nvse_generator_create: no CUDA device (there is no CPU fallback)");
+  nvse_generator* g = new nvse_generator();
+  g->cfg = *cfg;
+  build_layers(g);
+  *out = g;
+  return NVSE_OK;
+}
+
+extern "C" int nvse_generator_destroy(nvse_generator* g) {
+  if (!g) return NVSE_OK;
+  for (Layer& L : g->layers) {
+    cudaFree(L.w);
+    cudaFree(L.bias);
+    cudaFree(L.w_bf16);
+  }
+  delete g;
+  return NVSE_OK;
+}
+
+extern "C" int nvse_generator_set_weight(nvse_generator* g, const char* name, const float* data, const int64_t* shape,
+                                         int ndim, void* stream) {
+  NVSE_REQUIRE(g && name && data && shape, NVSE_ERR_INVALID, "nvse_generator_set_weight: null argument");
+  const std::string full(name);
+  const size_t dot = full.rfind('.');
+  NVSE_REQUIRE(dot != std::string::npos, NVSE_ERR_INVALID, "unknown tensor name '%s'", name);
+  const std::string prefix = full.substr(0, dot), leaf = full.substr(dot + 1);
+  auto it = g->index.find(prefix);
+  NVSE_REQUIRE(it != g->index.end(), NVSE_ERR_INVALID, "unknown tensor name '%s'", name);
+  Layer& L = g->layers[it->second];
+  cudaStream_t st = as_stream(stream);
+  g->finalized = false;
+  if (leaf == "bias") {
+    NVSE_REQUIRE(ndim == 1 && shape[0] == L.Cout, NVSE_ERR_INVALID, "%s: expected shape [%d]", name, L.Cout);
+    if (!L.bias) NVSE_CUDA_CHECK(cudaMalloc(&L.bias, sizeof(float) * L.Cout));
+    NVSE_CUDA_CHECK(cudaMemcpyAsync(L.bias, data, sizeof(float) * L.Cout, cudaMemcpyDeviceToDevice, st));
+    L.have_bias = true;
+    return NVSE_OK;
+  }
+  NVSE_REQUIRE(leaf == "weight", NVSE_ERR_INVALID,
+               "%s: expected a folded '.weight' or '.bias' tensor (fold weight_g/weight_v first)", name);
+  const int64_t d0 = L.transposed ? L.Cin : L.Cout, d1 = L.transposed ? L.Cout : L.Cin;
+  NVSE_REQUIRE(ndim == 3 && shape[0] == d0 && shape[1] == d1 && shape[2] == L.k, NVSE_ERR_INVALID,
+               "%s: expected shape [%lld, %lld, %d]", name, (long long)d0, (long long)d1, L.k);
+  if (!L.w) NVSE_CUDA_CHECK(cudaMalloc(&L.w, sizeof(float) * (size_t)L.Cin * L.Cout * L.k));
+  if (int rc = launch_repack_weight(data, L.w, L.Cin, L.Cout, L.k, L.transposed, st)) return rc;
+  L.have_w = true;
+  return NVSE_OK;
+}
+
+extern "C" int nvse_generator_finalize(nvse_generator* g, void* stream) {
+  NVSE_REQUIRE(g, NVSE_ERR_INVALID, "nvse_generator_finalize: null handle");
+  for (const Layer& L : g->layers)
+    NVSE_REQUIRE(L.have_w && L.have_bias, NVSE_ERR_STATE, "layer '%s' is missing its %s", L.name.c_str(),
+                 L.have_w ? "bias" : "weight");
+  if (int rc = finalize_bf16(g, as_stream(stream))) return rc;
+  g->finalized = true;
+  return NVSE_OK;
+}
+
+extern "C" int64_t nvse_generator_out_samples(const nvse_generator* g, int64_t frames) {
+  if (!g || frames < 0) return -1;
+  int64_t T = frames;
+  for (int i = 0; i < g->cfg.num_upsamples; ++i)
+    T = (T - 1) * g->cfg.upsample_rates[i] - 2 * ((g->cfg.upsample_kernel_sizes[i] - g->cfg.upsample_rates[i]) / 2) +
+        g->cfg.upsample_kernel_sizes[i];
+  if (g->cfg.kind == NVSE_GEN_ISTFTNET) T = T * g->cfg.istft_hop;  // hop * ((T + 1) - 1)
+  return T;
+}
+
+extern "C" size_t nvse_generator_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames, int precision) {
+  if (!g || B < 0 || frames < 0) return 0;
+  const size_t buf = align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256);
+  (void)precision;  // both paths use the same four activation buffers
+  return 4 * buf + 256;
+}
+
+extern "C" int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
+                                      void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  NVSE_REQUIRE(g && mel && out, NVSE_ERR_INVALID, "nvse_generator_forward: null argument");
+  NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_forward: call nvse_generator_finalize first");
+  NVSE_REQUIRE(B >= 0 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_forward: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
+  NVSE_REQUIRE(precision == NVSE_PRECISION_F32 || precision == NVSE_PRECISION_BF16, NVSE_ERR_INVALID, "bad precision %d", precision);
+  if (B == 0) return NVSE_OK;
+  const size_t need = nvse_generator_workspace_bytes(g, B, frames, precision);
+  NVSE_REQUIRE(workspace && workspace_bytes >= need, NVSE_ERR_INVALID, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  NVSE_REQUIRE(max_activation_elems(g, frames) * 4 < (int64_t)1 << 40, NVSE_ERR_INVALID, "utterance too long");
+  const int64_t buf_elems = (int64_t)(align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256) / sizeof(float));
+  float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, out, ws, buf_elems, as_stream(stream));
+}

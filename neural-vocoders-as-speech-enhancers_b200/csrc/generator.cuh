@@ -1,0 +1,40 @@
+// Generator handle internals shared by generator.cu (fp32 path) and generator_bf16.cu.
+#pragma once
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "conv_f32.cuh"
+
+namespace nvse {
+
+struct Layer {
+  std::string name;   // reference state-dict prefix, e.g. "resblocks.4.convs1.2"
+  bool transposed = false;  // ConvTranspose1d
+  int Cin = 0, Cout = 0, k = 0, dilation = 1, stride = 1, padding = 0;
+  float* w = nullptr;     // fp32 [k][Cin][Cout]
+  float* bias = nullptr;  // fp32 [Cout]
+  void* w_bf16 = nullptr;  // tensor-core weight image (see conv_tc.cuh), null for fp32-only layers
+  bool tc_split = false;   // activations as hi+lo bf16 pairs on the tensor-core path (accuracy)
+  bool have_w = false, have_bias = false;
+};
+
+}  // namespace nvse
+
+struct nvse_generator {
+  nvse_generator_config cfg;
+  std::vector<nvse::Layer> layers;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  const nvse::Layer& layer(const std::string& name) const { return layers[index.at(name)]; }
+};
+
+namespace nvse {
+
+int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st);
+
+int finalize_bf16(nvse_generator* g, cudaStream_t st);  // builds the tensor-core weight images
+int tc_abort_status(bool reset, unsigned int* flag);
+
+}  // namespace nvse

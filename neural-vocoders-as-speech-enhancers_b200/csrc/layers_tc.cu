@@ -1,0 +1,78 @@
+// Layer-level C ABI entry points of the tensor-core path (test convenience: they pack the
+// weights on the fly, which the generator handle does once at load time).
+#include "conv_f32.cuh"
+#include "conv_tc.cuh"
+#include "generator.cuh"
+
+using namespace nvse;
+
+namespace {
+struct Scratch {
+  void* p = nullptr;
+  cudaStream_t st;
+  explicit Scratch(cudaStream_t s) : st(s) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+}  // namespace
+
+extern "C" int nvse_conv1d_bf16(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                                int64_t B, int64_t T, int Cin, int Cout, int k, int dilation, float in_slope,
+                                float out_scale, int accumulate, void* stream) {
+  NVSE_REQUIRE(x && w && y && bias, NVSE_ERR_INVALID, "nvse_conv1d_bf16: null argument");
+  NVSE_REQUIRE(B >= 0 && T >= 0 && T <= 0x7fffffff && dilation >= 1, NVSE_ERR_INVALID, "nvse_conv1d_bf16: bad shape");
+  NVSE_REQUIRE(k >= 1 && (k & 1) && k <= kMaxTaps, NVSE_ERR_UNSUPPORTED, "nvse_conv1d_bf16: k=%d (odd k <= %d only)", k, kMaxTaps);
+  NVSE_REQUIRE(tc_supported(Cin, Cout), NVSE_ERR_UNSUPPORTED, "nvse_conv1d_bf16: Cin=%d / Cout=%d unsupported", Cin, Cout);
+  cudaStream_t st = as_stream(stream);
+  Scratch wk(st), img(st);
+  NVSE_CUDA_CHECK(wk.alloc(sizeof(float) * (size_t)Cin * Cout * k));
+  NVSE_CUDA_CHECK(img.alloc(sizeof(__nv_bfloat16) * (size_t)Cin * Cout * k));
+  if (int rc = launch_repack_weight(w, (float*)wk.p, Cin, Cout, k, false, st)) return rc;
+  if (int rc = launch_pack_weight_tc((const float*)wk.p, (__nv_bfloat16*)img.p, Cin, Cout, k, st)) return rc;
+  ConvTcArgs a{};
+  a.x = x; a.x_bstride = T * Cin; a.Tin = (int)T; a.Cin = Cin; a.Cout = Cout;
+  a.wimg = (const __nv_bfloat16*)img.p; a.bias = bias; a.residual = residual;
+  a.y = y; a.y_bstride = T * Cout; a.Tout = (int)T;
+  conv1d_taps(k, dilation, &a.taps);
+  a.out_mul = 1; a.out_add = 0; a.Trows = (int)T;
+  a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = out_scale; a.accumulate = accumulate;
+  return launch_conv_tc(a, B, st);
+}
+
+extern "C" int nvse_conv_transpose1d_bf16(const float* x, const float* w, const float* bias, float* y, int64_t B,
+                                          int64_t T, int Cin, int Cout, int k, int stride, int padding, float in_slope,
+                                          void* stream) {
+  NVSE_REQUIRE(x && w && y && bias, NVSE_ERR_INVALID, "nvse_conv_transpose1d_bf16: null argument");
+  NVSE_REQUIRE(B >= 0 && T >= 1 && stride >= 1 && padding >= 0 && k >= 1, NVSE_ERR_INVALID, "nvse_conv_transpose1d_bf16: bad shape");
+  NVSE_REQUIRE(tc_supported(Cin, Cout), NVSE_ERR_UNSUPPORTED, "nvse_conv_transpose1d_bf16: Cin=%d / Cout=%d unsupported", Cin, Cout);
+  const int64_t Tout = (T - 1) * stride - 2 * padding + k;
+  NVSE_REQUIRE(Tout > 0 && Tout <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_conv_transpose1d_bf16: bad output length");
+  cudaStream_t st = as_stream(stream);
+  Scratch wk(st), img(st);
+  NVSE_CUDA_CHECK(wk.alloc(sizeof(float) * (size_t)Cin * Cout * k));
+  NVSE_CUDA_CHECK(img.alloc(sizeof(__nv_bfloat16) * (size_t)Cin * Cout * k));
+  if (int rc = launch_repack_weight(w, (float*)wk.p, Cin, Cout, k, true, st)) return rc;
+  if (int rc = launch_pack_weight_tc((const float*)wk.p, (__nv_bfloat16*)img.p, Cin, Cout, k, st)) return rc;
+  for (int r = 0; r < stride && r < Tout; ++r) {
+    ConvTcArgs a{};
+    a.x = x; a.x_bstride = T * Cin; a.Tin = (int)T; a.Cin = Cin; a.Cout = Cout;
+    a.wimg = (const __nv_bfloat16*)img.p; a.bias = bias;
+    a.y = y; a.y_bstride = Tout * Cout; a.Tout = (int)Tout;
+    const int n = conv_transpose_phase_taps(k, stride, padding, r, &a.taps);
+    NVSE_REQUIRE(n > 0, NVSE_ERR_UNSUPPORTED, "nvse_conv_transpose1d_bf16: k < stride is not supported");
+    a.out_mul = stride; a.out_add = r; a.Trows = (int)((Tout - r + stride - 1) / stride);
+    a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
+    if (int rc = launch_conv_tc(a, B, st)) return rc;
+  }
+  return NVSE_OK;
+}
+
+extern "C" int nvse_tc_abort_status(int reset, int* flag) {
+  NVSE_REQUIRE(flag, NVSE_ERR_INVALID, "nvse_tc_abort_status: null argument");
+  unsigned int v = 0;
+  if (int rc = tc_abort_status(reset != 0, &v)) return rc;
+  *flag = (int)v;
+  return NVSE_OK;
+}

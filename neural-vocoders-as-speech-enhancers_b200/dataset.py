@@ -1,0 +1,105 @@
+"""Drop-in for the reference ``dataset.mel_spectrogram`` (dataset.py:53-91), computed by
+the fused sm_100a front-end kernel (csrc/frontend.cu) through the C ABI.
+
+Same signature, same positional order, same module-level caches (``mel_window``,
+``param_string``) as the reference, so ``from dataset import mel_spectrogram`` call sites
+(infers/inference_hifigan.py:31-32, train_time_wi_inv.py:177-186, Models/models.py:164)
+work unchanged.  Results live on the device the reference would have used: ``y.device``
+or CPU when ``in_dataset`` -- CPU inputs are staged through the GPU, there is no CPU
+implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .melbasis import slaney_mel_basis
+
+mel_window = {}      # param_string -> (mel_basis, hann_window) tensors, as in dataset.py:45
+inv_mel_window = {}  # kept for dataset.inverse_mel compatibility (dataset.py:46)
+_frontends = {}      # (param_string without device, hop, cuda index) -> nvse_frontend*
+
+
+def param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, device):
+    """dataset.py:49-50."""
+    return f"{sampling_rate}-{n_fft}-{num_mels}-{fmin}-{fmax}-{win_size}-{device}"
+
+
+def dynamic_range_compression_torch(x, C=1, clip_val=1e-5):
+    """dataset.py:27-28 (kept for callers; the kernel applies it in its epilogue)."""
+    return torch.log(torch.clamp(x, min=clip_val) * C)
+
+
+def spectral_normalize_torch(magnitudes):
+    """dataset.py:35-37."""
+    return dynamic_range_compression_torch(magnitudes)
+
+
+def _cuda_device_for(t):
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise _lib.NvseError("mel_spectrogram needs a CUDA device: the B200 front-end has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _frontend(sampling_rate, n_fft, num_mels, hop_size, win_size, fmin, fmax, basis, window, dev):
+    key = (sampling_rate, n_fft, num_mels, fmin, fmax, win_size, hop_size, dev.index)
+    fe = _frontends.get(key)
+    if fe is None:
+        lib = _lib.load()
+        win = window.detach().to("cpu", torch.float32)
+        if win_size < n_fft:  # torch.stft centres a short window inside n_fft
+            left = (n_fft - win_size) // 2
+            win = torch.nn.functional.pad(win, (left, n_fft - win_size - left))
+        win = np.ascontiguousarray(win.numpy())
+        mb = np.ascontiguousarray(basis.detach().to("cpu", torch.float32).numpy())
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.nvse_frontend_create(n_fft, hop_size, num_mels, win.ctypes.data_as(C.c_void_p),
+                                                mb.ctypes.data_as(C.c_void_p), C.byref(handle)))
+        fe = _frontends[key] = handle
+    return fe
+
+
+def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax,
+                    center=True, in_dataset=False):
+    """log-mel spectrogram ``[B, num_mels, 1 + T // hop_size]`` (or ``[num_mels, F]`` for 1-D
+    input) of ``y``.  ``center`` is accepted and ignored exactly as in the reference, which
+    always calls ``torch.stft(center=True)`` (dataset.py:62 vs :84)."""
+    global mel_window
+    if y.dim() not in (1, 2):
+        raise RuntimeError(f"mel_spectrogram expects a 1-D or 2-D waveform tensor, got {tuple(y.shape)}")
+    if torch.is_grad_enabled() and y.requires_grad:
+        raise NotImplementedError("mel_spectrogram backward (STFT adjoint) is not implemented in this build")
+    out_device = torch.device("cpu") if in_dataset else y.device
+    ps = param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, out_device)
+    if ps in mel_window:
+        mel_basis, hann_window = mel_window[ps]
+    else:
+        mel_basis = torch.from_numpy(slaney_mel_basis(sampling_rate, n_fft, num_mels, fmin, fmax)).float().to(out_device)
+        hann_window = torch.hann_window(win_size).to(out_device)
+        mel_window[ps] = (mel_basis, hann_window)
+
+    dev = _cuda_device_for(y)
+    fe = _frontend(sampling_rate, n_fft, num_mels, hop_size, win_size, fmin, fmax, mel_basis, hann_window, dev)
+    squeeze = y.dim() == 1
+    yd = y.detach().to(dev, torch.float32)
+    if squeeze:
+        yd = yd.unsqueeze(0)
+    if yd.stride(-1) != 1:
+        yd = yd.contiguous()
+    batch, samples = yd.shape
+    frames = 1 + samples // hop_size
+    out = torch.empty((batch, num_mels, frames), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.nvse_frontend_mel_f32(fe, _lib.ptr(yd), batch, samples, yd.stride(0) if batch > 1 else samples,
+                                             _lib.ptr(out), C.c_void_p(stream)))
+    if squeeze:
+        out = out[0]
+    return out if out.device == out_device else out.to(out_device)

@@ -1,0 +1,34 @@
+"""Per-utterance sharding of an inference job across the GPUs of one box.
+
+Utterances are independent: weights are replicated, each rank vocodes
+its own share, and there is no collective on the data path.  These helpers are pure host
+logic (tested with a world_size-2 gloo group on CPU)."""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+
+def shard_range(n_items: int, world_size: int, rank: int) -> range:
+    """Contiguous, balanced partition: the first ``n_items % world_size`` ranks get one extra."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank {rank} / world_size {world_size}")
+    base, extra = divmod(max(0, n_items), world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def shard_by_cost(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Ragged utterances: longest-first greedy binning by cost (mel frames).  Deterministic:
+    ties go to the lowest rank; every index appears exactly once."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world_size
+    bins: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda q: (loads[q], q))
+        bins[r].append(i)
+        loads[r] += costs[i]
+    for b in bins:
+        b.sort()
+    return bins

@@ -133,6 +133,19 @@ def main():
                      "mel_seed": mseed, "ref": f"Models/{mod.__name__[4:]}.py {cls}.forward"},
               mel=mel, out=out)
 
+    # ---- constructor parity: state-dict keys, shapes and seeded-init checksums ----------
+    for cfg_key, mod, cls in (("hifigan_v1", ref_hifigan, "HiFiGAN"), ("istftnet", ref_istftnet, "iSTFTNet"),
+                              ("hifigan_small_rb2", ref_hifigan, "HiFiGAN")):
+        cfg = synth.CONFIGS[cfg_key]
+        torch.manual_seed(cfg["seed"])
+        gen = getattr(mod, cls)(synth.AttrDict(cfg))
+        sd = gen.state_dict()
+        table = {k: {"shape": list(v.shape), "sum": float(v.double().sum()), "abs": float(v.double().abs().sum())}
+                 for k, v in sd.items()}
+        with open(os.path.join(HERE, f"state_{cfg_key}.json"), "w") as f:
+            json.dump({"ref": f"{cls}.__init__ under torch.manual_seed({cfg['seed']})", "tensors": table}, f, indent=0)
+        print(f"wrote state_{cfg_key}.json ({len(table)} tensors)")
+
     # ---- iSTFT head alone (istftnet.py:183-188) ----------------------------------
     rng = np.random.default_rng(31)
     mag = np.exp(rng.normal(0, 1, size=(2, 9, 37))).astype(np.float32)

@@ -1,0 +1,306 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in Python API) against the
+oracle, the reference-generated golden vectors and fp32 PyTorch ops.  Needs a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+from oracle import np_oracle
+from util import build_generator, conv1d_cl, conv_transpose1d_cl, lib_mod, pkg, report, stream_ptr
+
+pytestmark = pytest.mark.gpu
+A = synth.HIFIGAN_V1
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _mel(y, fmax=A["fmax"], **kw):
+    return pkg.mel_spectrogram(y, A["n_fft"], A["num_mels"], A["sampling_rate"], A["hop_size"], A["win_size"],
+                               A["fmin"], fmax, **kw)
+
+
+# ------------------------------------------------------------------------------ front-end
+@pytest.mark.parametrize("name", ["mel_b2_t4100", "mel_b1_t513", "mel_b3_t8192_fmax_half", "mel_1d_t22050",
+                                  "mel_tone_silence"])
+def test_mel_matches_reference_golden(name):
+    g = synth.load_golden(name)
+    out = _mel(torch.from_numpy(g["y"]).to(DEV), g["meta"]["fmax"])
+    assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == g["out"].shape
+    ratio = synth.mel_mismatch(out.cpu().numpy(), g["out"])
+    assert ratio <= 1.0, ratio
+    # north_star gate for the front-end: log-mel L1 <= 1e-3 (we are two orders below it even
+    # on the tone fixture, whose near-floor bins are pure fp32 FFT round-off in the reference too)
+    assert np.abs(out.cpu().numpy() - g["out"]).mean() <= 2e-5
+
+
+@pytest.mark.parametrize("batch,samples,seed", [(1, 600, 1), (3, 1024, 2), (2, 1279, 3), (5, 2560, 4), (2, 22051, 5)])
+def test_mel_matches_oracle_ragged_sizes(batch, samples, seed):
+    y = synth.make_wave(batch, samples, seed)
+    out = _mel(torch.from_numpy(y).to(DEV)).cpu().numpy()
+    ref = np_oracle.mel_spectrogram(y, A["n_fft"], A["num_mels"], A["sampling_rate"], A["hop_size"], A["win_size"],
+                                    A["fmin"], A["fmax"])
+    assert out.shape == ref.shape == (batch, 80, 1 + samples // 256)
+    assert synth.mel_mismatch(out, ref) <= 1.0
+
+
+def test_mel_cpu_input_and_in_dataset_return_on_cpu():
+    y = torch.from_numpy(synth.make_wave(2, 3000, 6))
+    a = _mel(y)
+    b = _mel(y.to(DEV), in_dataset=True)
+    assert a.device.type == "cpu" and b.device.type == "cpu"
+    assert torch.equal(a, b)
+    assert any(k.endswith("-cpu") for k in pkg.dataset.mel_window)  # reference cache keys stay populated
+
+
+def test_mel_strided_rows_and_short_input():
+    big = torch.from_numpy(synth.make_wave(4, 5000, 7)).to(DEV)
+    view = big[:, :4096]  # row stride 5000
+    assert torch.equal(_mel(view), _mel(view.contiguous()))
+    with pytest.raises(RuntimeError, match="reflect"):
+        _mel(torch.zeros(1, 512, device=DEV))  # torch.stft also refuses pad >= T
+
+
+def test_mel_full_size_cfg2_properties():
+    """BASELINE cfg2 (64 x 4 s): against torch.stft on the GPU in fp32, plus a size-independent
+    property: shifting the waveform by two hops shifts interior frames by two, bit-exactly."""
+    y = torch.from_numpy(synth.make_wave(64, 88200, 8)).to(DEV)
+    out = _mel(y)
+    assert tuple(out.shape) == (64, 80, 345)
+    basis = torch.from_numpy(np_oracle.mel_filterbank(22050, 1024, 80, 0, 8000)).to(DEV)
+    spec = torch.stft(y, 1024, hop_length=256, win_length=1024, window=torch.hann_window(1024, device=DEV),
+                      center=True, return_complex=True).abs()
+    ref = torch.log(torch.clamp(torch.einsum("mk,bkf->bmf", basis, spec), min=1e-5))
+    assert synth.mel_mismatch(out.cpu().numpy(), ref.cpu().numpy()) <= 1.0
+    shifted = _mel(y[:, 512:])
+    assert torch.equal(shifted[:, :, 2:300], out[:, :, 4:302])
+
+
+# ------------------------------------------------------------------------------ layers
+CONV_CASES = [  # (Cin, Cout, k, d, T, B): every (k, d) of the MRF + the edge layers
+    (32, 32, 3, 1, 300, 2), (32, 32, 3, 3, 257, 1), (32, 32, 3, 5, 64, 2), (32, 32, 7, 1, 129, 2), (32, 32, 7, 3, 500, 1),
+    (32, 32, 7, 5, 200, 1), (32, 32, 11, 1, 128, 1), (32, 32, 11, 3, 100, 2), (32, 32, 11, 5, 333, 1),
+    (64, 64, 7, 3, 260, 2), (128, 128, 11, 5, 140, 1), (256, 256, 3, 1, 70, 1), (80, 512, 7, 1, 33, 2),
+    (32, 1, 7, 1, 700, 2), (128, 18, 7, 1, 513, 2), (64, 64, 3, 1, 1, 1), (64, 64, 11, 5, 7, 1),
+]
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+@pytest.mark.parametrize("cin,cout,k,d,T,B", CONV_CASES)
+def test_conv1d_f32_matches_torch(cin, cout, k, d, T, B):
+    x, w, b = _rand((B, cin, T), 1), _rand((cout, cin, k), 2, 1.0 / np.sqrt(cin * k)), _rand((cout,), 3)
+    ref = F.conv1d(F.leaky_relu(x, 0.1), w, b, dilation=d, padding=(k - 1) * d // 2)
+    out = conv1d_cl(x, w, b, d, in_slope=0.1)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5), float((out - ref).abs().max())
+
+
+def test_conv1d_f32_fused_epilogue():
+    """residual add + MRF 1/3 scaling + accumulate (hifigan.py:49,113-119) in one launch."""
+    x, w, b = _rand((2, 64, 150), 4), _rand((64, 64, 7), 5, 0.05), _rand((64,), 6)
+    res, y0 = _rand((2, 64, 150), 7), _rand((2, 64, 150), 8)
+    ref = y0 + (F.conv1d(F.leaky_relu(x, 0.1), w, b, padding=3) + res) / 3
+    out = conv1d_cl(x, w, b, 1, in_slope=0.1, residual_bct=res, out_scale=1.0 / 3, y0_bct=y0)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,k,u,T,B", [(512, 256, 16, 8, 9, 2), (256, 128, 16, 8, 40, 1), (128, 64, 4, 2, 130, 2),
+                                             (64, 32, 4, 2, 257, 1), (32, 16, 8, 4, 5, 1), (64, 32, 16, 8, 1, 1)])
+def test_conv_transpose1d_f32_matches_torch(cin, cout, k, u, T, B):
+    x, w, b = _rand((B, cin, T), 9), _rand((cin, cout, k), 10, 1.0 / np.sqrt(cin * 2)), _rand((cout,), 11)
+    ref = F.conv_transpose1d(F.leaky_relu(x, 0.1), w, b, stride=u, padding=(k - u) // 2)
+    out = conv_transpose1d_cl(x, w, b, u, (k - u) // 2, in_slope=0.1)
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5), float((out - ref).abs().max())
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+TC_CONV_CASES = [  # every MRF (C, k, d) class of HiFi-GAN V1, plus ragged / tiny T
+    (32, 32, 3, 1, 300, 2), (32, 32, 3, 3, 257, 1), (32, 32, 3, 5, 64, 2), (32, 32, 7, 1, 129, 2), (32, 32, 7, 3, 500, 1),
+    (32, 32, 7, 5, 200, 1), (32, 32, 11, 1, 128, 1), (32, 32, 11, 3, 100, 2), (32, 32, 11, 5, 333, 1),
+    (64, 64, 3, 1, 1, 1), (64, 64, 7, 3, 260, 2), (64, 64, 11, 5, 7, 1), (128, 128, 3, 3, 1000, 1),
+    (128, 128, 11, 5, 140, 1), (256, 256, 3, 1, 70, 1), (256, 256, 7, 5, 129, 2), (256, 256, 11, 5, 400, 1),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,d,T,B", TC_CONV_CASES)
+def test_conv1d_tensor_core_matches_torch_on_bf16_operands(cin, cout, k, d, T, B):
+    """tcgen05 path: products of bf16-rounded operands are exact in fp32, so against an fp32 conv of
+    the rounded operands only the accumulation order differs."""
+    x, w, b = _rand((B, cin, T), 21), _rand((cout, cin, k), 22, 1.0 / np.sqrt(cin * k)), _rand((cout,), 23)
+    res, y0 = _rand((B, cout, T), 24), _rand((B, cout, T), 25)
+    conv = F.conv1d(_bf(F.leaky_relu(x, 0.1)), _bf(w), b, dilation=d, padding=(k - 1) * d // 2)
+    out = conv1d_cl(x, w, b, d, in_slope=0.1, tc=True)
+    assert not lib_mod.tc_abort_status()
+    assert torch.allclose(out, conv, atol=3e-5, rtol=1e-5), float((out - conv).abs().max())
+    out2 = conv1d_cl(x, w, b, d, in_slope=0.1, residual_bct=res, out_scale=1.0 / 3, y0_bct=y0, tc=True)
+    assert torch.allclose(out2, y0 + (conv + res) / 3, atol=3e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("cin,cout,k,u,T,B", [(512, 256, 16, 8, 9, 2), (256, 128, 16, 8, 140, 1), (128, 64, 4, 2, 130, 2),
+                                             (64, 32, 4, 2, 257, 1), (64, 32, 16, 8, 1, 1)])
+def test_conv_transpose1d_tensor_core_matches_torch_on_bf16_operands(cin, cout, k, u, T, B):
+    x, w, b = _rand((B, cin, T), 26), _rand((cin, cout, k), 27, 1.0 / np.sqrt(cin * 2)), _rand((cout,), 28)
+    ref = F.conv_transpose1d(_bf(F.leaky_relu(x, 0.1)), _bf(w), b, stride=u, padding=(k - u) // 2)
+    out = conv_transpose1d_cl(x, w, b, u, (k - u) // 2, in_slope=0.1, tc=True)
+    assert not lib_mod.tc_abort_status()
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, atol=3e-5, rtol=1e-5), float((out - ref).abs().max())
+
+
+def test_weight_norm_fold_both_layouts():
+    lib = lib_mod.load()
+    for shape in [(256, 256, 11), (512, 256, 16), (1, 32, 7)]:  # Conv1d [Cout,Cin,k]; ConvT [Cin,Cout,k]: dim 0 either way
+        v, g = _rand(shape, 12, 0.01), _rand((shape[0], 1, 1), 13).abs() + 0.1
+        w = torch.empty_like(v)
+        lib_mod.check(lib.nvse_weight_norm_fold_f32(lib_mod.ptr(v), lib_mod.ptr(g), lib_mod.ptr(w), shape[0],
+                                                    shape[1] * shape[2], stream_ptr()))
+        ref = np_oracle.weight_norm_fold(v.cpu().numpy(), g.cpu().numpy())
+        assert np.abs(w.cpu().numpy() - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_istft_head_matches_reference_golden_and_edges():
+    g = synth.load_golden("istft_head_t37")
+    lib = lib_mod.load()
+    # the head takes conv_post output z with mag = exp(z[:9]), phase = sin(z[9:]); invert those maps for the fixture
+    z = np.concatenate([np.log(g["mag"]), np.arcsin(np.clip(g["phase"], -1, 1))], axis=1)  # [B, 18, Tp]
+    zt = torch.from_numpy(z.transpose(0, 2, 1).copy()).float().to(DEV)
+    B, Tp = zt.shape[0], zt.shape[1]
+    out = torch.empty((B, 4 * (Tp - 1)), device=DEV)
+    lib_mod.check(lib.nvse_istft_head_f32(lib_mod.ptr(zt), lib_mod.ptr(out), B, Tp, 16, 4, stream_ptr()))
+    scale = np.abs(g["out"]).max()
+    assert np.abs(out.cpu().numpy() - g["out"]).max() <= 2e-5 * scale
+    ref = np_oracle.istft_head(np.exp(z[:, :9]), np.sin(z[:, 9:]), 16, 4)
+    assert np.abs(out.cpu().numpy()[:, :8] - ref[:, :8]).max() <= 2e-5 * scale   # first samples: envelope != 1.5
+    assert np.abs(out.cpu().numpy()[:, -8:] - ref[:, -8:]).max() <= 2e-5 * scale
+
+
+# ------------------------------------------------------------------------------ generators
+GEN_CASES = ["hifigan_v1_init_f6", "hifigan_v1_unit_f9", "hifigan_small_unit_f33", "hifigan_small_f1",
+             "hifigan_small_rb2_f17", "istftnet_init_f5", "istftnet_unit_f7", "istftnet_small_unit_f40"]
+
+
+def _golden_generator(name, remove_wn):
+    g = synth.load_golden(name)
+    m = g["meta"]
+    cfg = synth.CONFIGS[m["cfg"]]
+    gen = build_generator(cfg, synth.make_state(cfg, m["weight_seed"], m["regime"]), DEV, remove_wn)
+    return g, gen
+
+
+@pytest.mark.parametrize("name", GEN_CASES)
+@pytest.mark.parametrize("remove_wn", [False, True])
+def test_generator_fp32_matches_reference_golden(name, remove_wn):
+    """north_star fp32 gate: max-abs waveform error <= 1e-4 vs the reference on the same inputs."""
+    g, gen = _golden_generator(name, remove_wn)
+    gen.precision = "fp32"
+    with torch.no_grad():
+        out = gen(torch.from_numpy(g["mel"]).to(DEV))
+    assert out.is_cuda and tuple(out.shape) == g["out"].shape
+    err = np.abs(out.cpu().numpy() - g["out"]).max()
+    report(f"{name} (weight_norm {'removed' if remove_wn else 'kept'}): fp32 max-abs {err:.2e}")
+    assert err <= 1e-4, err
+
+
+@pytest.mark.parametrize("name", GEN_CASES)
+def test_generator_bf16_matches_reference_golden(name):
+    """north_star bf16 gate: waveform SNR >= 40 dB (Metrics/snr.py:25-31, de-meaned); raw SNR reported too."""
+    g, gen = _golden_generator(name, True)
+    gen.precision = "bf16"
+    with torch.no_grad():
+        out = gen(torch.from_numpy(g["mel"]).to(DEV)).cpu().numpy()
+    snr, raw = np_oracle.snr_db(g["out"], out), np_oracle.snr_db(g["out"], out, demean=False)
+    report(f"{name}: bf16 SNR de-meaned {snr:.1f} dB, raw {raw:.1f} dB, max-abs {np.abs(out - g['out']).max():.2e}")
+    assert snr >= 40.0 and raw >= 40.0
+
+
+def test_e2e_wav_to_wav_matches_reference_golden():
+    """infers/inference_hifigan.py:82-84: x = get_mel(wav); y = generator(x)."""
+    g = synth.load_golden("e2e_hifigan_small_t5000")
+    cfg = synth.CONFIGS[g["meta"]["cfg"]]
+    gen = build_generator(cfg, synth.make_state(cfg, g["meta"]["weight_seed"], g["meta"]["regime"]), DEV, True)
+    gen.precision = "fp32"
+    with torch.no_grad():
+        mel = _mel(torch.from_numpy(g["y"]).to(DEV))
+        out = gen(mel)
+    assert synth.mel_mismatch(mel.cpu().numpy(), g["mel"]) <= 1.0
+    assert np.abs(out.cpu().numpy() - g["out"]).max() <= 1e-4
+
+
+def test_generator_cpu_tensors_are_staged_through_the_gpu():
+    """The shipped inference script forces device = cpu (infers/inference_hifigan.py:129)."""
+    g, gen = _golden_generator("hifigan_small_f1", True)
+    gen = gen.to("cpu")
+    gen.precision = "fp32"
+    with torch.no_grad():
+        out = gen(torch.from_numpy(g["mel"]))
+    assert out.device.type == "cpu"
+    assert np.abs(out.numpy() - g["out"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_generator_batch_items_are_independent(precision):
+    """Per-utterance sharding relies on this: an utterance vocoded alone, or on
+    another rank, gives bit-identical samples to the same utterance inside a batch."""
+    cfg = synth.HIFIGAN_SMALL
+    gen = build_generator(cfg, synth.make_state(cfg, 17, "unit"), DEV, True)
+    gen.precision = precision
+    mel = torch.from_numpy(synth.make_mel(5, 37, 18)).to(DEV)
+    with torch.no_grad():
+        full = gen(mel)
+        parts = [gen(mel[i:i + 1]) for i in (0, 3, 4)]
+        two = gen(mel[pkg.shard_range(5, 2, 1).start:])
+    for p, i in zip(parts, (0, 3, 4)):
+        assert torch.equal(p[0], full[i])
+    assert torch.equal(two, full[pkg.shard_range(5, 2, 1).start:])
+
+
+def test_generator_weight_update_is_picked_up():
+    cfg = synth.HIFIGAN_SMALL
+    gen = build_generator(cfg, synth.make_state(cfg, 19, "unit"), DEV, False)
+    gen.precision = "fp32"
+    mel = torch.from_numpy(synth.make_mel(1, 8, 20)).to(DEV)
+    with torch.no_grad():
+        a = gen(mel)
+        gen.conv_post.bias.add_(0.25)
+        b = gen(mel)
+        gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state(cfg, 19, "unit").items()})
+        c = gen(mel)
+    assert not torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_full_size_cfg3_fp32_vs_bf16_and_torch():
+    """BASELINE cfg3 shape at reduced batch (4 x 8 s, F = 690): fp32 path vs PyTorch fp32 ops on the
+    GPU (max-abs <= 1e-4) and bf16 path vs fp32 path (SNR >= 40 dB), reference-init-like weights."""
+    from oracle import torch_port
+    cfg = synth.HIFIGAN_V1
+    state = synth.make_state(cfg, 1234, "init")
+    gen = build_generator(cfg, state, DEV, True)
+    mel = torch.from_numpy(synth.make_mel(4, 690, 30)).to(DEV)
+    folded = {k: v.to(DEV) for k, v in torch_port.fold_state(state).items()}
+    with torch.no_grad():
+        ref = torch_port.hifigan_forward(folded, cfg, mel)
+        gen.precision = "fp32"
+        o32 = gen(mel)
+        gen.precision = "bf16"
+        o16 = gen(mel)
+    assert tuple(o32.shape) == (4, 176640)
+    assert float((o32 - ref).abs().max()) <= 1e-4
+    snr = np_oracle.snr_db(ref.cpu().numpy(), o16.cpu().numpy())
+    report(f"cfg3-shape (4 x 690 frames, init weights seed 1234): fp32 max-abs {float((o32 - ref).abs().max()):.2e}; "
+           f"bf16 SNR {snr:.1f} dB (de-meaned), raw {np_oracle.snr_db(ref.cpu().numpy(), o16.cpu().numpy(), False):.1f} dB")
+    assert snr >= 40.0
