@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Headline benchmark: HiFi-GAN V1 audio-seconds per second on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                      (the reference's CPU path, oracle port)
+
+One step = one pass of the hot path (wav -> mel_spectrogram -> HiFi-GAN V1 -> wav) over this
+rank's shard of synthetic utterances: per GPU, 128 utterances x 10 s (cfg5 of BASELINE.json is
+1024 such utterances over 8 GPUs, so N = 8 is exactly cfg5 and per-GPU work is fixed: weak
+scaling, no collective on the data path), processed in micro-batches of 32.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+SR = 22050
+FLOP_PER_FRAME = 2 * 307_052_544  # HiFi-GAN V1, SURVEY.md 8(d) / BASELINE.md 2
+METRIC = "HiFi-GAN V1 audio-sec/sec (wav -> mel -> generator -> wav)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--utts-per-gpu", type=int, default=128)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--cpu-utts", type=int, default=2, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference(args, n_utts, steps, warmup):
+    """The reference's CPU path (oracle port: same torch.stft / oneDNN conv calls, fp32, all host
+    threads), one utterance at a time like infers/inference_hifigan.py:67-84."""
+    import synth
+    from oracle import torch_port
+    cfg = synth.HIFIGAN_V1
+    torch.set_num_threads(os.cpu_count() or 1)
+    folded = torch_port.fold_state(synth.make_state(cfg, 1234, "init"))
+    T = int(args.seconds * SR)
+    wav = torch.from_numpy(synth.make_wave(n_utts, T, 0))
+
+    def step():
+        n = 0
+        for u in range(n_utts):
+            mel = torch_port.mel_spectrogram(wav[u:u + 1], cfg["n_fft"], cfg["num_mels"], cfg["sampling_rate"],
+                                             cfg["hop_size"], cfg["win_size"], cfg["fmin"], cfg["fmax"])
+            n += torch_port.hifigan_forward(folded, cfg, mel).shape[-1]
+        return n
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    samples = 0
+    for _ in range(steps):
+        samples += step()
+    dt = time.perf_counter() - t0
+    return samples / SR / dt, dt / steps, torch.get_num_threads()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"cfg5 shard: {args.utts_per_gpu} x {args.seconds:g} s utterances per GPU "
+                f"({args.utts_per_gpu * max(world, args.gpus)} over {max(world, args.gpus)} GPUs), micro-batch {args.micro_batch}")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, sec, cores = cpu_reference(args, args.cpu_utts, args.steps, args.warmup)
+        sample = f"{args.cpu_utts} x {args.seconds:g} s utterances per step, batch 1 each, fp32, torch CPU ({cores} threads)"
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "audio-sec/sec", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "audio-sec/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import synth
+    import __graft_entry__ as entry
+    pkg = entry.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = synth.HIFIGAN_V1
+    h = synth.AttrDict(cfg)
+    torch.manual_seed(cfg["seed"])
+    gen = pkg.HiFiGAN(h)
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state(cfg, 1234, "init").items()})
+    gen = gen.to(dev).eval()
+    gen.remove_weight_norm()
+    gen.precision = args.precision
+    voc = pkg.Vocoder(gen, h, micro_batch=args.micro_batch, device=dev)
+
+    U, T = args.utts_per_gpu, int(args.seconds * SR)
+    # every rank vocodes its own shard of the global utterance list (per-utterance sharding)
+    wav_host = torch.from_numpy(synth.make_wave(U, T, 1000 + rank)).pin_memory()
+    wav_dev = wav_host.to(dev)
+    frames = 1 + T // cfg["hop_size"]
+    t_out = frames * 256
+    out_dev = torch.empty((U, t_out), dtype=torch.float32, device=dev)
+    out_host = torch.empty((U, t_out), dtype=torch.float32).pin_memory()
+    audio_sec_per_step = U * t_out / SR
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    dev_step = lambda: voc.run_device(wav_dev, out_dev)
+    host_step = lambda: voc.run_host(wav_host, out_host)
+
+    for _ in range(args.warmup):
+        dev_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = pkg._lib.launch_count()
+    ms_total = timed(dev_step, args.steps)
+    launches = pkg._lib.launch_count() - l0
+    clocks = sampler.stop()
+    if pkg._lib.tc_abort_status():
+        raise SystemExit("tensor-core kernel tripped its bounded wait; results invalid")
+
+    for _ in range(max(1, args.warmup // 2)):
+        host_step()
+    ms_e2e = timed(host_step, args.steps)
+
+    # per-kernel event timing over the same K steps (separate pass so the events do not perturb `value`)
+    pkg._lib.profile_begin()
+    for _ in range(args.steps):
+        dev_step()
+    torch.cuda.synchronize()
+    prof = pkg._lib.profile_end()
+
+    value = world * audio_sec_per_step * args.steps / (ms_total / 1e3)
+    e2e = world * audio_sec_per_step * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    tc = [k for k in prof if k["kernel"].startswith("conv_tc")]
+    tc_ms, tc_flops, tc_n = sum(k["ms"] for k in tc), sum(k["flops"] for k in tc), sum(k["launches"] for k in tc)
+    all_ms = sum(k["ms"] for k in prof)
+    achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
+    fe = [k for k in prof if k["kernel"].startswith("mel_frontend")]
+    fe_gbs = sum(k["bytes"] for k in fe) / (sum(k["ms"] for k in fe) * 1e-3) / 1e9 if fe else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-sec/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": workload, "weights": "random-init (reference-like N(0,0.01), seed 1234), weight_norm folded",
+                   "l2": "inputs larger than L2 (113 MB waveforms, GB-scale activations per step)",
+                   "frames_per_utt": frames, "flop_per_step_per_gpu": FLOP_PER_FRAME * frames * U},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(U * T * 4), "d2h_bytes_per_step": int(U * t_out * 4),
+                "ms_per_step": ms_e2e / args.steps, "api": "Vocoder.run_host: pinned host wav -> mel_spectrogram -> HiFiGAN -> pinned host wav"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all MRF + upsampling layers)",
+                     "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                     "launches": tc_n, "avg_launch_ms": tc_ms / tc_n if tc_n else None, "share_of_step": tc_ms / all_ms if all_ms else None,
+                     "timing": "per-launch CUDA events on the launching stream, separate pass of the same K steps"},
+        "frontend": {"kernel": "mel_frontend_kernel", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": fe_gbs / pk["hbm_gbs"],
+                     "bound": "hbm (algorithmic bytes: waveform in + log-mel out)"},
+        "kernels": sorted(({"kernel": k["kernel"], "launches": k["launches"], "ms_per_step": k["ms"] / args.steps,
+                            "tflops": k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] else 0.0,
+                            "gbs": k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else 0.0} for k in prof),
+                          key=lambda r: -r["ms_per_step"]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_reference(args, args.cpu_utts, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_utts} x {args.seconds:g} s utterances x 3 steps, batch 1 each, fp32 torch CPU"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

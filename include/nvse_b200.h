@@ -52,6 +52,13 @@ NVSE_API const char* nvse_last_error(void);
  * (bench.py reports the delta over the timed region as `gpu_launches`). */
 NVSE_API uint64_t nvse_launch_count(void);
 
+/* Per-launch timing for bench.py's roofline numbers.  Between begin and end every kernel this
+ * library launches is bracketed by CUDA events on its stream; end() waits for them and writes a
+ * JSON array [{"kernel", "launches", "ms", "flops", "bytes"}...] aggregated per kernel and channel
+ * class (flops/bytes are ALGORITHMIC, as defined in DESIGN.md), then disables timing. */
+NVSE_API int nvse_profile_begin(void);
+NVSE_API int nvse_profile_end(char* json_out, size_t capacity);
+
 /* ------------------------------------------------------------------------------------
  * Front-end: dataset.mel_spectrogram  (dataset.py:53-91)
  *   reflect-pad n_fft/2 | frame (n_fft, hop) | x window | R2C FFT | magnitude |

@@ -43,6 +43,8 @@ PROTOTYPES = {
     "nvse_abi_version": (_i, []),
     "nvse_last_error": (C.c_char_p, []),
     "nvse_launch_count": (C.c_uint64, []),
+    "nvse_profile_begin": (_i, []),
+    "nvse_profile_end": (_i, [C.c_char_p, _sz]),
     "nvse_frontend_create": (_i, [_i, _i, _i, _vp, _vp, C.POINTER(_vp)]),
     "nvse_frontend_destroy": (_i, [_vp]),
     "nvse_frontend_num_frames": (_i64, [_vp, _i64]),
@@ -96,6 +98,18 @@ def check(rc):
 
 def launch_count():
     return int(load().nvse_launch_count())
+
+
+def profile_begin():
+    check(load().nvse_profile_begin())
+
+
+def profile_end():
+    """Per-kernel totals since profile_begin(): list of dicts (kernel, launches, ms, flops, bytes)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(load().nvse_profile_end(buf, len(buf)))
+    return json.loads(buf.value.decode())
 
 
 def tc_abort_status(reset=True):

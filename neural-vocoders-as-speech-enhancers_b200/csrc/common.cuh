@@ -43,6 +43,16 @@ extern std::atomic<uint64_t> g_launches;
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Optional per-launch timing (nvse_profile_begin / nvse_profile_end): when enabled every launch
+// site brackets its kernel with a pair of CUDA events on the launching stream and tags it with
+// its algorithmic FLOPs and bytes; bench.py turns the totals into the roofline numbers.
+struct ProfScope {
+  int slot = -1;
+  cudaStream_t st;
+  ProfScope(const char* kernel, int c_in, int c_out, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
+
 constexpr int kMaxTaps = 16;
 
 // One "tap-list" convolution over channels-last activations.  A plain dilated Conv1d is a

@@ -223,6 +223,9 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
     min_off = std::min(min_off, a.taps.off[i]);
     max_off = std::max(max_off, a.taps.off[i]);
   }
+  const double prows = (double)B * a.Trows;
+  ProfScope prof("conv_f32", a.Cin, a.Cout, 2.0 * prows * a.Cin * a.Cout * a.taps.ntaps,
+                 prows * 4.0 * (a.Cin + a.Cout * (a.accumulate ? 2.0 : 1.0) + (a.residual ? a.Cout : 0.0)), st);
   const bool thin = a.Cout < 32 || a.reflect_left || (a.Cin % BK != 0 && a.Cout <= 32);
   if (thin) {
     NVSE_REQUIRE(a.Cout <= 32, NVSE_ERR_UNSUPPORTED, "thin conv: Cout=%d > 32", a.Cout);

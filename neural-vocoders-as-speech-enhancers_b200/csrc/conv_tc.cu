@@ -397,6 +397,11 @@ int launch_conv_tc(const ConvTcArgs& a, int64_t B, cudaStream_t st) {
   const size_t smem = act_bytes + stages * stage_bytes + tail;
   NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 1024)));
   dim3 grid((unsigned)((a.Trows + kTileM - 1) / kTileM), (unsigned)B);
+  const double rows = (double)B * a.Trows;
+  ProfScope prof("conv_tc", a.Cin, a.Cout, 2.0 * rows * a.Cin * a.Cout * a.taps.ntaps,
+                 rows * (a.Cin * (a.in_bf16 ? 2.0 : 4.0) + a.Cout * (a.out_bf16 ? 2.0 : 4.0) * (a.accumulate ? 2.0 : 1.0) +
+                         (a.residual ? 4.0 * a.Cout : 0.0)),
+                 st);
   conv_tc_kernel<<<grid, kThreads, smem, st>>>(k);
   NVSE_LAUNCH_CHECK("conv_tc_kernel");
   return NVSE_OK;

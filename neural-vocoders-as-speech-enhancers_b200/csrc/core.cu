@@ -1,6 +1,11 @@
 // Error plumbing, launch accounting and the small layout / weight-norm kernels.
 #include "common.cuh"
 
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
 namespace nvse {
 
 std::atomic<uint64_t> g_launches{0};
@@ -18,6 +23,52 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   last_error_slot() = buf;
   return code;
+}
+
+// ---- per-launch profiler ---------------------------------------------------------------------
+namespace {
+struct ProfRecord {
+  std::string key;
+  double flops, bytes;
+  cudaEvent_t start, stop;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(const char* kernel, int c_in, int c_out, double flops, double bytes, cudaStream_t stream) : st(stream) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRecord r;
+  char buf[96];
+  snprintf(buf, sizeof(buf), "%s[%d->%d]", kernel, c_in, c_out);
+  r.key = buf;
+  r.flops = flops;
+  r.bytes = bytes;
+  r.start = take_event();
+  r.stop = take_event();
+  cudaEventRecord(r.start, st);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].stop, st);
 }
 
 namespace {
@@ -84,6 +135,49 @@ int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, 
 extern "C" int nvse_abi_version(void) { return NVSE_ABI_VERSION; }
 extern "C" const char* nvse_last_error(void) { return nvse::last_error_slot().c_str(); }
 extern "C" uint64_t nvse_launch_count(void) { return nvse::g_launches.load(); }
+
+extern "C" int nvse_profile_begin(void) {
+  using namespace nvse;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (ProfRecord& r : g_prof) {
+    g_event_pool.push_back(r.start);
+    g_event_pool.push_back(r.stop);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return NVSE_OK;
+}
+
+extern "C" int nvse_profile_end(char* json_out, size_t capacity) {
+  using namespace nvse;
+  NVSE_REQUIRE(json_out && capacity > 2, NVSE_ERR_INVALID, "nvse_profile_end: bad buffer");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  struct Agg { uint64_t n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (ProfRecord& r : g_prof) {
+    NVSE_CUDA_CHECK(cudaEventSynchronize(r.stop));
+    float ms = 0.0f;
+    NVSE_CUDA_CHECK(cudaEventElapsedTime(&ms, r.start, r.stop));
+    Agg& a = agg[r.key];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    g_event_pool.push_back(r.start);
+    g_event_pool.push_back(r.stop);
+  }
+  g_prof.clear();
+  std::string js = "[";
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s{\"kernel\": \"%s\", \"launches\": %llu, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             js.size() > 1 ? ", " : "", kv.first.c_str(), (unsigned long long)kv.second.n, kv.second.ms, kv.second.flops,
+             kv.second.bytes);
+    js += buf;
+  }
+  js += "]";
+  NVSE_REQUIRE(js.size() + 1 <= capacity, NVSE_ERR_INVALID, "nvse_profile_end: buffer too small (%zu needed)", js.size() + 1);
+  memcpy(json_out, js.c_str(), js.size() + 1);
+  return NVSE_OK;
+}
 
 extern "C" int nvse_weight_norm_fold_f32(const float* v, const float* g, float* w, int64_t rows, int64_t cols,
                                          void* stream) {

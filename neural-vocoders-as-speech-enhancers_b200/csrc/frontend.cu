@@ -324,6 +324,9 @@ extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, in
   NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: problem too large for one launch");
   const size_t smem = sizeof(float) * kWarpSmemFloats * kWarpsPerCta;
   NVSE_CUDA_CHECK(cudaFuncSetAttribute(mel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // algorithmic bytes: waveform in + log-mel out
+  ProfScope prof("mel_frontend", 1, fe->n_mels, 0.0, 4.0 * (double)B * (double)T + 4.0 * (double)B * fe->n_mels * (double)p.F,
+                 as_stream(stream));
   mel_frontend_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, as_stream(stream)>>>(p);
   NVSE_LAUNCH_CHECK("mel_frontend_kernel");
   return NVSE_OK;

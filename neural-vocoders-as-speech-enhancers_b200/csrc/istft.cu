@@ -101,6 +101,7 @@ int launch_istft(const float* z, float* out, int64_t B, int64_t Tp, int hop, cud
   const size_t smem = sizeof(float) * (3 * NFFT + (size_t)max_frames * (NFFT + 1));
   NVSE_CUDA_CHECK(cudaFuncSetAttribute(istft_head_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((Tp - 1 + kGroupsPerCta - 1) / kGroupsPerCta), (unsigned)B);
+  ProfScope prof("istft_head", NFFT + 2, 1, 0.0, 4.0 * (double)B * ((double)Tp * (NFFT + 2) + (double)(Tp - 1) * hop), st);
   istft_head_kernel<NFFT><<<grid, kGroupsPerCta, smem, st>>>(z, out, Tp, hop);
   NVSE_LAUNCH_CHECK("istft_head_kernel");
   return NVSE_OK;

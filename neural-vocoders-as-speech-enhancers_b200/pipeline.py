@@ -1,0 +1,49 @@
+"""Batched wav -> mel -> generator -> wav, the loop body of the reference's inference script
+(infers/inference_hifigan.py:67-95: ``x = get_mel(wav); y = generator(x)``) for a whole list of
+equal-length utterances, from HOST buffers to HOST buffers.
+
+The reference loops one utterance at a time on one device; here a shard of utterances is pushed
+through in micro-batches: pinned host -> device copy, fused front-end kernel, generator kernels,
+device -> pinned host copy, all stream-ordered with no synchronisation inside the loop."""
+from __future__ import annotations
+
+import torch
+
+from .dataset import mel_spectrogram
+
+
+class Vocoder:
+    def __init__(self, generator, h, micro_batch=32, device=None):
+        self.generator = generator
+        self.h = h
+        self.micro_batch = int(micro_batch)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def mel(self, wav_dev):
+        h = self.h
+        return mel_spectrogram(wav_dev, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax)
+
+    @torch.no_grad()
+    def run_device(self, wav_dev, out_dev=None):
+        """Device-resident variant: wav_dev [U, T] on the GPU -> [U, T_out] on the GPU."""
+        outs = []
+        for s in range(0, wav_dev.shape[0], self.micro_batch):
+            y = self.generator(self.mel(wav_dev[s:s + self.micro_batch]))
+            if out_dev is not None:
+                out_dev[s:s + y.shape[0]].copy_(y)
+            else:
+                outs.append(y)
+        return out_dev if out_dev is not None else torch.cat(outs, 0)
+
+    @torch.no_grad()
+    def run_host(self, wav_host, out_host=None):
+        """wav_host: [U, T] float32 CPU tensor (pinned for async copies).  Returns (and fills, if
+        given) a CPU tensor [U, T_out].  The caller synchronises the current stream."""
+        dev = self.device
+        for s in range(0, wav_host.shape[0], self.micro_batch):
+            chunk = wav_host[s:s + self.micro_batch].to(dev, non_blocking=True)
+            y = self.generator(self.mel(chunk))
+            if out_host is None:
+                out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=torch.float32, pin_memory=True)
+            out_host[s:s + y.shape[0]].copy_(y, non_blocking=True)
+        return out_host
