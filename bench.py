@@ -170,7 +170,9 @@ def main():
     gen = pkg.HiFiGAN(h)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state(cfg, 1234, "init").items()})
     gen = gen.to(dev).eval()
-    gen.remove_weight_norm()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the reference's "Removing weight norm..." print (hifigan.py:127)
+        gen.remove_weight_norm()
     gen.precision = args.precision
     voc = pkg.Vocoder(gen, h, micro_batch=args.micro_batch, device=dev)
 

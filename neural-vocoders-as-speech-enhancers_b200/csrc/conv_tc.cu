@@ -15,9 +15,12 @@
 // TMEM with tcgen05.ld and apply bias / residual / MRF scale+accumulate (fp32 output) or
 // bias + leaky_relu + bf16 pack (the intermediate of a ResBlock pair).
 //
-// Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane quarter each), warp 4 weight
-// producer, warp 5 TMEM allocator + MMA issuer.  All six warps stage activations first.
+// Warp roles (320 threads): warps 0-7 epilogue (two per TMEM lane quarter, interleaved over the
+// 16-column chunks), warp 8 weight producer, warp 9 TMEM allocator + MMA issuer.  All ten warps
+// stage activations first; the epilogue warps also prefetch their residual / accumulate rows into
+// L2 before staging so that the loads of the epilogue do not pay HBM latency.
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <cstdlib>
 
@@ -25,135 +28,36 @@ namespace nvse {
 
 namespace {
 
-constexpr int kThreads = 192;
+using namespace tc;
+
+constexpr int kEpiWarps = 8;                     // two per TMEM lane quarter, splitting the column chunks
+constexpr int kThreads = (kEpiWarps + 2) * 32;   // + weight producer + MMA issuer
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
-constexpr long long kTimeoutCycles = 400000000LL;  // ~0.2 s: no legitimate wait is within 1000x of this
-
-__device__ unsigned int g_tc_abort = 0;
-
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long start = clock64();
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xffu) == 0) {
-      if (clock64() - start > kTimeoutCycles || *(volatile unsigned int*)&g_tc_abort) {
-        atomicExch(&g_tc_abort, 1u);
-        return false;
-      }
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> lane base+i)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B (rows 16 B apart).
-//   lbo = byte distance between the two core matrices along K of one K=16 MMA
-//   sbo = byte distance between consecutive 8-row groups along M / N
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float lrelu(float v, float s) { return v >= 0.0f ? v : v * s; }
-// the two bf16 halves of a packed word, widened back to fp32 (exact)
-__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+constexpr int kMaxPhases = 8;
 
 struct KernelArgs {
   ConvTcArgs a;
-  int min_off;     // smallest tap offset
-  int rows;        // staged rows = 128 + (max_off - min_off)
-  int rows_pad;    // rows rounded up to 8m+1 (conflict-free staging stores)
+  int nphase;                      // output phases sharing one staged activation tile (ConvTranspose1d); 1 for Conv1d
+  ConvTaps ptaps[kMaxPhases];      // tap list of each phase
+  int pout_add[kMaxPhases];        // output row = out_mul * t + pout_add[phase]
+  int ntile;       // 128-row M tiles per CTA: every weight stage feeds ntile MMAs (weight reuse from smem)
+  int min_off;     // smallest tap offset over all phases
+  int rows;        // staged rows = 128 * ntile + (max_off - min_off)
+  int rows_pad;    // rows rounded up to an odd count (conflict-free staging stores)
   int stages;      // weight ring depth
   int kc;          // channels per weight stage (min(Cin, 64))
 };
 
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const KernelArgs k) {
+constexpr int kStageUnroll = 4;  // independent 32-byte loads in flight per thread while staging
+
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ KernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  if (*(volatile unsigned int*)&g_tc_abort) return;  // a previous launch tripped a wait timeout
   const ConvTcArgs& a = k.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t b = blockIdx.y;
-  const int t0 = blockIdx.x * kTileM;
+  const int ntile = k.ntile;
+  const int t0 = blockIdx.x * kTileM * ntile;
   const int Cin = a.Cin, Cout = a.Cout;
   const int nchunk = Cin >> 3;
   const uint32_t act_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;  // one bf16 plane
@@ -162,9 +66,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const KernelArgs k) {
   uint8_t* act = smem_raw;
   uint8_t* wst = smem_raw + (split ? 2u : 1u) * act_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)k.stages * stage_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages), bar_accum = smem_u32(bars + 2 * kMaxStages);
-  const uint32_t tmem_cols = Cout < 32 ? 32u : (uint32_t)Cout;  // power of two >= 32 by construction
+  // barriers: full[kMaxStages], empty[kMaxStages], accum_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
+  const uint32_t bar_accum = smem_u32(bars + 2 * kMaxStages), bar_tfree = smem_u32(bars + 2 * kMaxStages + 2);
+  const int nbuf = k.nphase > 1 ? 2 : 1;  // TMEM accumulator double-buffering across phases
+  const uint32_t tmem_cols = (uint32_t)(Cout * nbuf * ntile) < 32u ? 32u : (uint32_t)(Cout * nbuf * ntile);  // power of two by construction
 
   if (tid == 0) {
     for (int s = 0; s < k.stages; ++s) {
@@ -172,9 +79,30 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const KernelArgs k) {
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_accum, 1);
+    mbar_init(bar_accum + 8, 1);
+    mbar_init(bar_tfree, kEpiWarps);
+    mbar_init(bar_tfree + 8, kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  if (warp == kEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+
+  // ---- epilogue warps: pull the rows they will read in the epilogue (residual, accumulate target)
+  //      into L2 now; staging + MMAs give the prefetch time to land ------------------------------
+  if (warp < kEpiWarps && !a.out_bf16 && (a.residual || a.accumulate)) {
+    const int q = warp & 3, half = warp >> 2;
+    for (int ph = 0; ph < k.nphase; ++ph)
+      for (int j = 0; j < ntile; ++j) {
+        const int t = t0 + j * kTileM + q * 32 + lane;
+        const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph];
+        if (t < a.Trows && orow < a.Tout) {
+          const int64_t base = b * a.y_bstride + orow * Cout;
+          for (int c = half * 32; c < Cout; c += 64) {  // one 128-byte line per 32 fp32 channels
+            if (a.residual) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residual + base + c));
+            if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float*>(a.y) + base + c));
+          }
+        }
+      }
+  }
 
   // ---- stage the activation tile (all warps): lrelu + bf16 + K-major core-matrix layout ------
   {
@@ -182,38 +110,61 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const KernelArgs k) {
     const int cshift = 31 - __clz(nchunk);
     if (a.in_bf16) {
       const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a.x) + b * a.x_bstride;
-      for (int e = tid; e < items; e += kThreads) {
-        const int chunk = e & (nchunk - 1), r = e >> cshift;
-        const int t = t0 + k.min_off + r;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && t < a.Tin) v = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)t * Cin + chunk * 8));
-        *reinterpret_cast<uint4*>(act + ((size_t)chunk * k.rows_pad + r) * 16) = v;
+      for (int e0 = tid; e0 < items; e0 += kThreads * kStageUnroll) {
+        uint4 v[kStageUnroll];
+        int dst[kStageUnroll];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+          const int e = e0 + u * kThreads;
+          const int chunk = e & (nchunk - 1), r = e >> cshift;
+          const int t = t0 + k.min_off + r;
+          dst[u] = e < items ? (chunk * k.rows_pad + r) * 16 : -1;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (e < items && t >= 0 && t < a.Tin) v[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)t * Cin + chunk * 8));
+        }
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u)
+          if (dst[u] >= 0) *reinterpret_cast<uint4*>(act + dst[u]) = v[u];
       }
     } else {
       const float* xb = reinterpret_cast<const float*>(a.x) + b * a.x_bstride;
       const float s = a.in_slope;
-      for (int e = tid; e < items; e += kThreads) {
-        const int chunk = e & (nchunk - 1), r = e >> cshift;
-        const int t = t0 + k.min_off + r;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && t < a.Tin) {
-          const float4* src = reinterpret_cast<const float4*>(xb + (int64_t)t * Cin + chunk * 8);
-          const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-          const float f[8] = {lrelu(f0.x, s), lrelu(f0.y, s), lrelu(f0.z, s), lrelu(f0.w, s),
-                              lrelu(f1.x, s), lrelu(f1.y, s), lrelu(f1.z, s), lrelu(f1.w, s)};
+      for (int e0 = tid; e0 < items; e0 += kThreads * kStageUnroll) {
+        float4 f0[kStageUnroll], f1[kStageUnroll];
+        int dst[kStageUnroll];
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+          const int e = e0 + u * kThreads;
+          const int chunk = e & (nchunk - 1), r = e >> cshift;
+          const int t = t0 + k.min_off + r;
+          dst[u] = e < items ? (chunk * k.rows_pad + r) * 16 : -1;
+          f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < items && t >= 0 && t < a.Tin) {
+            const float4* src = reinterpret_cast<const float4*>(xb + (int64_t)t * Cin + chunk * 8);
+            f0[u] = __ldg(src);
+            f1[u] = __ldg(src + 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kStageUnroll; ++u) {
+          if (dst[u] < 0) continue;
+          const float f[8] = {lrelu(f0[u].x, s), lrelu(f0[u].y, s), lrelu(f0[u].z, s), lrelu(f0[u].w, s),
+                              lrelu(f1[u].x, s), lrelu(f1[u].y, s), lrelu(f1[u].z, s), lrelu(f1[u].w, s)};
+          uint4 v;
           v.x = pack_bf16(f[0], f[1]);
           v.y = pack_bf16(f[2], f[3]);
           v.z = pack_bf16(f[4], f[5]);
           v.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(act + dst[u]) = v;
           if (split) {  // residual of the first rounding, itself rounded to bf16: ~16 mantissa bits in total
+            uint4 lo;
             lo.x = pack_bf16(f[0] - bf16_lo(v.x), f[1] - bf16_hi(v.x));
             lo.y = pack_bf16(f[2] - bf16_lo(v.y), f[3] - bf16_hi(v.y));
             lo.z = pack_bf16(f[4] - bf16_lo(v.z), f[5] - bf16_hi(v.z));
             lo.w = pack_bf16(f[6] - bf16_lo(v.w), f[7] - bf16_hi(v.w));
+            *reinterpret_cast<uint4*>(act + act_bytes + dst[u]) = lo;
           }
         }
-        *reinterpret_cast<uint4*>(act + ((size_t)chunk * k.rows_pad + r) * 16) = v;
-        if (split) *reinterpret_cast<uint4*>(act + act_bytes + ((size_t)chunk * k.rows_pad + r) * 16) = lo;
       }
     }
   }
@@ -222,113 +173,142 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const KernelArgs k) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
   const int nkc = Cin / k.kc;
-  const int n_iters = a.taps.ntaps * nkc;
 
-  if (warp == 4) {
-    // ===== weight producer: one bulk copy per (tap, K chunk) stage =====
+  if (warp == kEpiWarps) {
+    // ===== weight producer: one bulk copy per (phase, tap, K chunk) stage =====
     if (lane == 0) {
       int it = 0;
-      for (int tap = 0; tap < a.taps.ntaps; ++tap) {
-        const __nv_bfloat16* wsrc = a.wimg + (size_t)a.taps.widx[tap] * nkc * (stage_bytes / 2);
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % k.stages;
-          const uint32_t par = ((it / k.stages) & 1) ^ 1;
-          if (!mbar_wait(bar_empty + 8 * s, par)) goto done;
-          mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
-          bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wsrc + (size_t)kc * (stage_bytes / 2), stage_bytes,
-                        bar_full + 8 * s);
+      for (int ph = 0; ph < k.nphase; ++ph) {
+        const ConvTaps& tp = k.ptaps[ph];
+        for (int tap = 0; tap < tp.ntaps; ++tap) {
+          const __nv_bfloat16* wsrc = a.wimg + (size_t)tp.widx[tap] * nkc * (stage_bytes / 2);
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % k.stages;
+            const uint32_t par = ((it / k.stages) & 1) ^ 1;
+            if (!mbar_wait(bar_empty + 8 * s, par)) goto done;
+            mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wsrc + (size_t)kc * (stage_bytes / 2), stage_bytes,
+                          bar_full + 8 * s);
+          }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // ===== MMA issuer: a single thread drives the tensor core =====
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t act_base = smem_u32(act);
       const uint32_t a_lbo = (uint32_t)k.rows_pad * 16u, b_lbo = (uint32_t)Cout * 16u, sbo = 128u;
       int it = 0;
-      for (int tap = 0; tap < a.taps.ntaps; ++tap) {
-        const uint32_t row_shift = (uint32_t)(a.taps.off[tap] - k.min_off);
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % k.stages;
-          const uint32_t par = (it / k.stages) & 1;
-          if (!mbar_wait(bar_full + 8 * s, par)) goto done;
+      for (int ph = 0; ph < k.nphase; ++ph) {
+        const ConvTaps& tp = k.ptaps[ph];
+        const int buf = ph & 1;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ntile * Cout);
+        if (ph >= 2) {  // the epilogue must have drained this accumulator (phase ph - 2)
+          if (!mbar_wait(bar_tfree + 8 * buf, ((ph >> 1) - 1) & 1)) goto done;
           tc_fence_after();
-          const uint32_t w_base = smem_u32(wst + (size_t)s * stage_bytes);
-          for (int kk = 0; kk < k.kc / 16; ++kk) {
-            const uint32_t a_addr = act_base + ((uint32_t)(kc * (k.kc / 8) + 2 * kk) * k.rows_pad + row_shift) * 16u;
-            const uint32_t b_addr = w_base + (uint32_t)(2 * kk) * b_lbo;
-            const uint64_t bd = umma_desc(b_addr, b_lbo, sbo);
-            tc_mma_bf16(tmem_base, umma_desc(a_addr, a_lbo, sbo), bd, idesc, (it | kk) != 0 ? 1u : 0u);
-            if (split) tc_mma_bf16(tmem_base, umma_desc(a_addr + act_bytes, a_lbo, sbo), bd, idesc, 1u);
-          }
-          tc_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
         }
+        bool first = true;
+        for (int tap = 0; tap < tp.ntaps; ++tap) {
+          const uint32_t row_shift = (uint32_t)(tp.off[tap] - k.min_off);
+          for (int kc = 0; kc < nkc; ++kc, ++it) {
+            const int s = it % k.stages;
+            const uint32_t par = (it / k.stages) & 1;
+            if (!mbar_wait(bar_full + 8 * s, par)) goto done;
+            tc_fence_after();
+            const uint32_t w_base = smem_u32(wst + (size_t)s * stage_bytes);
+            for (int kk = 0; kk < k.kc / 16; ++kk) {
+              const uint32_t a_addr = act_base + ((uint32_t)(kc * (k.kc / 8) + 2 * kk) * k.rows_pad + row_shift) * 16u;
+              const uint32_t b_addr = w_base + (uint32_t)(2 * kk) * b_lbo;
+              const uint64_t bd = umma_desc(b_addr, b_lbo, sbo);
+              for (int j = 0; j < ntile; ++j) {  // the same weight stage feeds every M tile of this CTA
+                const uint32_t aj = a_addr + (uint32_t)j * (kTileM * 16u);
+                tc_mma_bf16(d_tmem + (uint32_t)(j * Cout), umma_desc(aj, a_lbo, sbo), bd, idesc, first ? 0u : 1u);
+                if (split) tc_mma_bf16(d_tmem + (uint32_t)(j * Cout), umma_desc(aj + act_bytes, a_lbo, sbo), bd, idesc, 1u);
+              }
+              first = false;
+            }
+            tc_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
+          }
+        }
+        tc_commit(bar_accum + 8 * buf);  // accumulator of this phase complete -> epilogue
       }
-      tc_commit(bar_accum);  // accumulator complete -> epilogue
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> global =====
-    const bool ok = mbar_wait(bar_accum, 0);
-    tc_fence_after();
-    if (ok) {
-      const int row = warp * 32 + lane;
-      const int t = t0 + row;
-      const int64_t orow = (int64_t)a.out_mul * t + a.out_add;
+    const int quarter = warp & 3, chalf = warp >> 2;  // TMEM lane quarter; which 16-column chunks (even / odd)
+    const int row = quarter * 32 + lane;
+    for (int ph = 0; ph < k.nphase; ++ph) {
+      const int buf = ph & 1;
+      if (!mbar_wait(bar_accum + 8 * buf, (ph >> 1) & 1)) break;
+      tc_fence_after();
+     for (int j = 0; j < ntile; ++j) {
+      const int t = t0 + j * kTileM + row;
+      const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph];
       const bool valid = t < a.Trows && orow < a.Tout;
-      for (int c0 = 0; c0 < Cout; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!valid) continue;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * ntile + j) * Cout);
+      for (int c0 = chalf * 16; c0 < Cout; c0 += 16 * (kEpiWarps / 4)) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_addr + (uint32_t)c0, v);
         if (a.out_bf16) {
-          __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(a.y) + b * a.y_bstride + orow * Cout + c0;
+          float bq[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q);
+          tmem_ld_wait();
+          if (valid) {
+            __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(a.y) + b * a.y_bstride + orow * Cout + c0;
+            uint4 o[2];
+            uint32_t* op = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int c = q * 8 + j * 2;
-              const float f0 = lrelu(__uint_as_float(v[c]) + __ldg(a.bias + c0 + c), a.out_slope);
-              const float f1 = lrelu(__uint_as_float(v[c + 1]) + __ldg(a.bias + c0 + c + 1), a.out_slope);
-              op[j] = pack_bf16(f0, f1);
-            }
-            *reinterpret_cast<uint4*>(yr + q * 8) = o;
+            for (int j = 0; j < 8; ++j)
+              op[j] = pack_bf16(lrelu(__uint_as_float(v[2 * j]) + bq[2 * j], a.out_slope),
+                                lrelu(__uint_as_float(v[2 * j + 1]) + bq[2 * j + 1], a.out_slope));
+            *reinterpret_cast<uint4*>(yr) = o[0];
+            *reinterpret_cast<uint4*>(yr + 8) = o[1];
           }
         } else {
+          // issue every global load of this chunk before waiting on TMEM (latency overlap)
+          float4 bq[4], rq[4], yq[4];
           float* yr = reinterpret_cast<float*>(a.y) + b * a.y_bstride + orow * Cout + c0;
           const float* rr = a.residual ? a.residual + b * a.y_bstride + orow * Cout + c0 : nullptr;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + q * 4));
-            float4 o = make_float4(__uint_as_float(v[q * 4 + 0]) + bq.x, __uint_as_float(v[q * 4 + 1]) + bq.y,
-                                   __uint_as_float(v[q * 4 + 2]) + bq.z, __uint_as_float(v[q * 4 + 3]) + bq.w);
-            if (a.out_slope != 1.0f) {
-              o.x = lrelu(o.x, a.out_slope); o.y = lrelu(o.y, a.out_slope);
-              o.z = lrelu(o.z, a.out_slope); o.w = lrelu(o.w, a.out_slope);
+          for (int q = 0; q < 4; ++q) {
+            bq[q] = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q);
+            rq[q] = (valid && rr) ? *reinterpret_cast<const float4*>(rr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yq[q] = (valid && a.accumulate) ? *reinterpret_cast<const float4*>(yr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 o = make_float4(__uint_as_float(v[q * 4 + 0]) + bq[q].x, __uint_as_float(v[q * 4 + 1]) + bq[q].y,
+                                     __uint_as_float(v[q * 4 + 2]) + bq[q].z, __uint_as_float(v[q * 4 + 3]) + bq[q].w);
+              if (a.out_slope != 1.0f) {
+                o.x = lrelu(o.x, a.out_slope); o.y = lrelu(o.y, a.out_slope);
+                o.z = lrelu(o.z, a.out_slope); o.w = lrelu(o.w, a.out_slope);
+              }
+              o.x = (o.x + rq[q].x) * a.out_scale + yq[q].x;
+              o.y = (o.y + rq[q].y) * a.out_scale + yq[q].y;
+              o.z = (o.z + rq[q].z) * a.out_scale + yq[q].z;
+              o.w = (o.w + rq[q].w) * a.out_scale + yq[q].w;
+              *reinterpret_cast<float4*>(yr + 4 * q) = o;
             }
-            if (rr) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rr + q * 4);
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            o.x *= a.out_scale; o.y *= a.out_scale; o.z *= a.out_scale; o.w *= a.out_scale;
-            if (a.accumulate) {
-              const float4 y4 = *reinterpret_cast<const float4*>(yr + q * 4);
-              o.x += y4.x; o.y += y4.y; o.z += y4.z; o.w += y4.w;
-            }
-            *reinterpret_cast<float4*>(yr + q * 4) = o;
           }
         }
+      }
+     }
+      if (nbuf > 1) {  // hand the accumulator back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfree + 8 * buf);
       }
     }
   }
 done:
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // fp32 [j][ci][co] -> bf16 [j][ci/KC][(ci%KC)/8][co][ci%8]
@@ -353,66 +333,96 @@ int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int C
   return NVSE_OK;
 }
 
-static constexpr size_t kSmemBudget = 200 * 1024;
-static constexpr size_t kSmemTail = sizeof(uint64_t) * (2 * kMaxStages + 1) + 16;
+static constexpr size_t kSmemBudget = 224 * 1024;  // of the 227 KB a CTA may opt in to
+static constexpr size_t kSmemTail = sizeof(uint64_t) * (2 * kMaxStages + 4) + 16;
 
+static size_t tc_smem_bytes_rows(int Cin, int Cout, int rows, bool split, int stages) {
+  const int rows_pad = rows | 1;
+  const size_t plane = ((size_t)(Cin / 8) * rows_pad * 16 + 127) & ~(size_t)127;
+  return (split ? 2 : 1) * plane + (size_t)stages * tc_kchunk(Cin) * Cout * 2 + kSmemTail;
+}
 size_t tc_smem_bytes(int Cin, int Cout, int tap_span, bool split, int stages) {
   const int rows = kTileM + tap_span;
-  const int rows_pad = ((rows + 6) / 8) * 8 + 1;
+  const int rows_pad = rows | 1;
   const size_t plane = ((size_t)(Cin / 8) * rows_pad * 16 + 127) & ~(size_t)127;
   return (split ? 2 : 1) * plane + (size_t)stages * tc_kchunk(Cin) * Cout * 2 + kSmemTail;
 }
 bool tc_split_fits(int Cin, int Cout, int tap_span) { return tc_smem_bytes(Cin, Cout, tap_span, true, 2) <= kSmemBudget; }
 
-int launch_conv_tc(const ConvTcArgs& a, int64_t B, cudaStream_t st) {
+// `a.taps` / `a.out_add` describe phase 0; `extra` adds phases 1.. (ConvTranspose1d) that share the staged tile.
+int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const int* phase_out_add, int nphase, int64_t B,
+                          cudaStream_t st) {
   NVSE_REQUIRE(tc_supported(a.Cin, a.Cout), NVSE_ERR_UNSUPPORTED, "tensor-core conv: Cin=%d / Cout=%d unsupported", a.Cin, a.Cout);
-  NVSE_REQUIRE(a.taps.ntaps >= 1 && a.taps.ntaps <= kMaxTaps, NVSE_ERR_INVALID, "tensor-core conv: bad tap count");
+  NVSE_REQUIRE(nphase >= 1 && nphase <= kMaxPhases, NVSE_ERR_INVALID, "tensor-core conv: %d phases per launch", nphase);
   NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "tensor-core conv: batch %lld exceeds 65535 per launch", (long long)B);
   NVSE_REQUIRE(!(a.out_bf16 && (a.residual || a.accumulate)), NVSE_ERR_INVALID, "tensor-core conv: bf16 output takes no residual");
+  NVSE_REQUIRE(!(a.split_act && a.in_bf16), NVSE_ERR_INVALID, "tensor-core conv: split activations need fp32 input");
   if (B == 0 || a.Trows <= 0) return NVSE_OK;
   KernelArgs k;
   k.a = a;
-  int mn = a.taps.off[0], mx = a.taps.off[0];
-  for (int i = 1; i < a.taps.ntaps; ++i) {
-    mn = std::min(mn, a.taps.off[i]);
-    mx = std::max(mx, a.taps.off[i]);
+  k.nphase = nphase;
+  int mn = phase_taps[0].off[0], mx = mn, total_taps = 0;
+  for (int p = 0; p < nphase; ++p) {
+    NVSE_REQUIRE(phase_taps[p].ntaps >= 1 && phase_taps[p].ntaps <= kMaxTaps, NVSE_ERR_INVALID, "tensor-core conv: bad tap count");
+    k.ptaps[p] = phase_taps[p];
+    k.pout_add[p] = phase_out_add[p];
+    total_taps += phase_taps[p].ntaps;
+    for (int i = 0; i < phase_taps[p].ntaps; ++i) {
+      mn = std::min(mn, phase_taps[p].off[i]);
+      mx = std::max(mx, phase_taps[p].off[i]);
+    }
   }
   k.min_off = mn;
-  k.rows = kTileM + (mx - mn);
-  k.rows_pad = ((k.rows + 6) / 8) * 8 + 1;  // smallest 8m+1 >= rows
+  // M tiles per CTA: weight bytes streamed per FLOP fall as 1/ntile (L2 -> smem weight traffic is what
+  // bounds the 128-row tile at C >= 128), and per-CTA fixed costs are amortised for the small-C layers.
+  const int nbuf = nphase > 1 ? 2 : 1;
+  int ntile = 1;
+  {
+    static const int forced = [] { const char* e = std::getenv("NVSE_TC_NTILE"); return e ? std::atoi(e) : 0; }();
+    const int want = forced > 0 ? forced : (a.Cout >= 256 ? 2 : (a.Cout >= 128 ? 2 : 4));
+    const int64_t tiles_needed = ((int64_t)a.Trows + kTileM - 1) / kTileM;
+    while (ntile * 2 <= want && a.Cout * nbuf * ntile * 2 <= 512 && ntile * 2 <= tiles_needed &&
+           tc_smem_bytes_rows(a.Cin, a.Cout, kTileM * ntile * 2 + (mx - mn), a.split_act != 0, 2) <= kSmemBudget)
+      ntile *= 2;
+  }
+  k.ntile = ntile;
+  k.rows = kTileM * ntile + (mx - mn);
+  k.rows_pad = k.rows | 1;  // odd row pitch (in 16-byte units): the 8 lanes of a store phase hit 8 distinct bank groups
   k.kc = tc_kchunk(a.Cin);
-  NVSE_REQUIRE(!(a.split_act && a.in_bf16), NVSE_ERR_INVALID, "tensor-core conv: split activations need fp32 input");
   const size_t act_bytes = (a.split_act ? 2 : 1) * (((size_t)(a.Cin / 8) * k.rows_pad * 16 + 127) & ~(size_t)127);
   const size_t stage_bytes = (size_t)k.kc * a.Cout * 2;
   const size_t tail = kSmemTail, budget = kSmemBudget;
   NVSE_REQUIRE(act_bytes + 2 * stage_bytes + tail <= budget, NVSE_ERR_UNSUPPORTED,
                "tensor-core conv: tile needs %zu B of shared memory", act_bytes + 2 * stage_bytes + tail);
-  const int n_iters = a.taps.ntaps * (a.Cin / k.kc);
+  const int n_iters = total_taps * (a.Cin / k.kc);
   int stages = (int)std::min<size_t>((budget - act_bytes - tail) / stage_bytes, (size_t)4);
   stages = std::max(2, std::min(stages, std::max(2, n_iters)));
-  // prefer two CTAs per SM (one CTA's staging / epilogue overlaps the other's MMAs)
-  while (stages > 2 && act_bytes + stages * stage_bytes + tail > 110 * 1024 &&
-         act_bytes + 2 * stage_bytes + tail <= 110 * 1024) --stages;
+  // more resident CTAs per SM beat a deeper weight ring: one CTA's staging / epilogue overlaps another's MMAs
+  while (stages > 2 && act_bytes + stages * stage_bytes + tail > 56 * 1024) --stages;
   k.stages = stages;
   const size_t smem = act_bytes + stages * stage_bytes + tail;
-  NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 1024)));
-  dim3 grid((unsigned)((a.Trows + kTileM - 1) / kTileM), (unsigned)B);
+  NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+  dim3 grid((unsigned)((a.Trows + kTileM * ntile - 1) / (kTileM * ntile)), (unsigned)B);
   const double rows = (double)B * a.Trows;
-  ProfScope prof("conv_tc", a.Cin, a.Cout, 2.0 * rows * a.Cin * a.Cout * a.taps.ntaps,
-                 rows * (a.Cin * (a.in_bf16 ? 2.0 : 4.0) + a.Cout * (a.out_bf16 ? 2.0 : 4.0) * (a.accumulate ? 2.0 : 1.0) +
-                         (a.residual ? 4.0 * a.Cout : 0.0)),
+  ProfScope prof("conv_tc", a.Cin, a.Cout, 2.0 * rows * a.Cin * a.Cout * total_taps,
+                 rows * (a.Cin * (a.in_bf16 ? 2.0 : 4.0) +
+                         nphase * (a.Cout * (a.out_bf16 ? 2.0 : 4.0) * (a.accumulate ? 2.0 : 1.0) + (a.residual ? 4.0 * a.Cout : 0.0))),
                  st);
   conv_tc_kernel<<<grid, kThreads, smem, st>>>(k);
   NVSE_LAUNCH_CHECK("conv_tc_kernel");
   return NVSE_OK;
 }
 
+int launch_conv_tc(const ConvTcArgs& a, int64_t B, cudaStream_t st) {
+  return launch_conv_tc_phases(a, &a.taps, &a.out_add, 1, B, st);
+}
+
 int tc_abort_status(bool reset, unsigned int* flag) {
   unsigned int v = 0;
-  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, g_tc_abort, sizeof(v)));
+  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));
   if (reset && v) {
     const unsigned int z = 0;
-    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(g_tc_abort, &z, sizeof(z)));
+    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));
   }
   *flag = v;
   return NVSE_OK;

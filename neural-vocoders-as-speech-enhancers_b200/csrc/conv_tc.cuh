@@ -41,6 +41,11 @@ size_t tc_smem_bytes(int Cin, int Cout, int tap_span, bool split, int stages);
 bool tc_split_fits(int Cin, int Cout, int tap_span);
 
 int launch_conv_tc(const ConvTcArgs& a, int64_t B, cudaStream_t st);
+// Several output phases (ConvTranspose1d polyphase branches) computed from ONE staged activation tile;
+// a.taps / a.out_add are ignored, phase p uses phase_taps[p] and output rows out_mul * t + phase_out_add[p].
+constexpr int kTcMaxPhases = 8;
+int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const int* phase_out_add, int nphase, int64_t B,
+                          cudaStream_t st);
 // fp32 [k][Cin][Cout] (Layer::w layout) -> bf16 tensor-core image
 int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int k, cudaStream_t st);
 

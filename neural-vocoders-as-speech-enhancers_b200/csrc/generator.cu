@@ -96,33 +96,44 @@ static int run_conv(const Layer& L, bool tc, const ConvIO& io, int64_t B, int64_
   return launch_conv_f32(a, B, st);
 }
 
-// ConvTranspose1d as `stride` polyphase tap-list convolutions.
+// ConvTranspose1d as `stride` polyphase tap-list convolutions.  On the tensor-core
+// path up to 8 phases share one launch: the activation tile is staged once and the phases ping-pong
+// between two TMEM accumulators.
 static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
                               cudaStream_t st) {
   const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
-  for (int r = 0; r < L.stride && r < Tout; ++r) {
-    ConvTaps taps;
-    const int n = conv_transpose_phase_taps(L.k, L.stride, L.padding, r, &taps);
-    NVSE_REQUIRE(n > 0, NVSE_ERR_UNSUPPORTED, "ConvTranspose1d %s: unsupported k/stride", L.name.c_str());
-    const int trows = (int)((Tout - r + L.stride - 1) / L.stride);
-    if (tc && L.w_bf16) {
+  const int nph = (int)std::min<int64_t>(L.stride, Tout);
+  if (tc && L.w_bf16) {
+    for (int r0 = 0; r0 < nph; r0 += kTcMaxPhases) {
+      const int n = std::min(kTcMaxPhases, nph - r0);
+      ConvTaps taps[kTcMaxPhases];
+      int out_add[kTcMaxPhases];
+      for (int p = 0; p < n; ++p) {
+        NVSE_REQUIRE(conv_transpose_phase_taps(L.k, L.stride, L.padding, r0 + p, &taps[p]) > 0, NVSE_ERR_UNSUPPORTED,
+                     "ConvTranspose1d %s: unsupported k/stride", L.name.c_str());
+        out_add[p] = r0 + p;
+      }
       ConvTcArgs a{};
       a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout;
       a.wimg = reinterpret_cast<const __nv_bfloat16*>(L.w_bf16); a.bias = L.bias;
       a.y = y; a.y_bstride = Tout * L.Cout; a.Tout = (int)Tout;
-      a.taps = taps; a.out_mul = L.stride; a.out_add = r; a.Trows = trows;
+      a.out_mul = L.stride; a.Trows = (int)((Tout - r0 + L.stride - 1) / L.stride);
       a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
       a.split_act = L.tc_split;
-      if (int rc = launch_conv_tc(a, B, st)) return rc;
-    } else {
-      ConvF32Args a{};
-      a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin;
-      a.w = L.w; a.bias = L.bias;
-      a.y = y; a.y_bstride = Tout * L.Cout; a.Tout = (int)Tout; a.Cout = L.Cout;
-      a.taps = taps; a.out_mul = L.stride; a.out_add = r; a.Trows = trows;
-      a.in_slope = in_slope; a.out_scale = 1.0f;
-      if (int rc = launch_conv_f32(a, B, st)) return rc;
+      if (int rc = launch_conv_tc_phases(a, taps, out_add, n, B, st)) return rc;
     }
+    return NVSE_OK;
+  }
+  for (int r = 0; r < nph; ++r) {
+    ConvF32Args a{};
+    a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin;
+    a.w = L.w; a.bias = L.bias;
+    a.y = y; a.y_bstride = Tout * L.Cout; a.Tout = (int)Tout; a.Cout = L.Cout;
+    NVSE_REQUIRE(conv_transpose_phase_taps(L.k, L.stride, L.padding, r, &a.taps) > 0, NVSE_ERR_UNSUPPORTED,
+                 "ConvTranspose1d %s: unsupported k/stride", L.name.c_str());
+    a.out_mul = L.stride; a.out_add = r; a.Trows = (int)((Tout - r + L.stride - 1) / L.stride);
+    a.in_slope = in_slope; a.out_scale = 1.0f;
+    if (int rc = launch_conv_f32(a, B, st)) return rc;
   }
   return NVSE_OK;
 }
@@ -206,7 +217,7 @@ int finalize_bf16(nvse_generator* g, cudaStream_t st) {
     // upsamplers: 3 % of the FLOPs; the <= 32-channel MRF stage: HBM-bound anyway) activations are
     // fed as hi + lo bf16 pairs (tools/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
     if (L.transposed) {
-      L.tc_split = tc_split_fits(L.Cin, L.Cout, (L.k + L.stride - 1) / L.stride - 1);
+      L.tc_split = tc_split_fits(L.Cin, L.Cout, (L.k + L.stride - 1) / L.stride);  // all phases share one tile
     } else {
       L.tc_split = L.Cout <= 32 && tc_split_fits(L.Cin, L.Cout, (L.k - 1) * L.dilation);
     }

@@ -55,16 +55,23 @@ extern "C" int nvse_conv_transpose1d_bf16(const float* x, const float* w, const 
   NVSE_CUDA_CHECK(img.alloc(sizeof(__nv_bfloat16) * (size_t)Cin * Cout * k));
   if (int rc = launch_repack_weight(w, (float*)wk.p, Cin, Cout, k, true, st)) return rc;
   if (int rc = launch_pack_weight_tc((const float*)wk.p, (__nv_bfloat16*)img.p, Cin, Cout, k, st)) return rc;
-  for (int r = 0; r < stride && r < Tout; ++r) {
+  const int nph = (int)std::min<int64_t>(stride, Tout);
+  for (int r0 = 0; r0 < nph; r0 += kTcMaxPhases) {
+    const int n = std::min(kTcMaxPhases, nph - r0);
+    ConvTaps taps[kTcMaxPhases];
+    int out_add[kTcMaxPhases];
+    for (int p = 0; p < n; ++p) {
+      NVSE_REQUIRE(conv_transpose_phase_taps(k, stride, padding, r0 + p, &taps[p]) > 0, NVSE_ERR_UNSUPPORTED,
+                   "nvse_conv_transpose1d_bf16: k < stride is not supported");
+      out_add[p] = r0 + p;
+    }
     ConvTcArgs a{};
     a.x = x; a.x_bstride = T * Cin; a.Tin = (int)T; a.Cin = Cin; a.Cout = Cout;
     a.wimg = (const __nv_bfloat16*)img.p; a.bias = bias;
     a.y = y; a.y_bstride = Tout * Cout; a.Tout = (int)Tout;
-    const int n = conv_transpose_phase_taps(k, stride, padding, r, &a.taps);
-    NVSE_REQUIRE(n > 0, NVSE_ERR_UNSUPPORTED, "nvse_conv_transpose1d_bf16: k < stride is not supported");
-    a.out_mul = stride; a.out_add = r; a.Trows = (int)((Tout - r + stride - 1) / stride);
+    a.out_mul = stride; a.Trows = (int)((Tout - r0 + stride - 1) / stride);
     a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
-    if (int rc = launch_conv_tc(a, B, st)) return rc;
+    if (int rc = launch_conv_tc_phases(a, taps, out_add, n, B, st)) return rc;
   }
   return NVSE_OK;
 }
