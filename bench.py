@@ -232,7 +232,7 @@ def main():
         return
 
     pk = peaks()
-    tc = [k for k in prof if k["kernel"].startswith("conv_tc")]
+    tc = [k for k in prof if k["kernel"].startswith(("conv_tc", "resblock_tc"))]
     tc_ms, tc_flops, tc_n = sum(k["ms"] for k in tc), sum(k["flops"] for k in tc), sum(k["launches"] for k in tc)
     all_ms = sum(k["ms"] for k in prof)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
@@ -249,7 +249,7 @@ def main():
         "e2e": {"value": e2e, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(U * T * 4), "d2h_bytes_per_step": int(U * t_out * 4),
                 "ms_per_step": ms_e2e / args.steps, "api": "Vocoder.run_host: pinned host wav -> mel_spectrogram -> HiFiGAN -> pinned host wav"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all MRF + upsampling layers)",
+        "roofline": {"bound": "tensor", "kernel": "resblock_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs: fused MRF ResBlocks + upsamplers)",
                      "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
                      "launches": tc_n, "avg_launch_ms": tc_ms / tc_n if tc_n else None, "share_of_step": tc_ms / all_ms if all_ms else None,

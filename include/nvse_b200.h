@@ -156,6 +156,18 @@ NVSE_API int nvse_conv1d_bf16(const float* x, const float* w, const float* bias,
                      int64_t B, int64_t T, int Cin, int Cout, int k, int dilation,
                      float in_slope, float out_scale, int accumulate, void* stream);
 
+/* One fused launch of a ResBlock1 chain (hifigan.py:43-50) on the tcgen05 path:
+ *   for m in 0..npairs-1:  xt = conv1d(lrelu(x, 0.1), w1[m], dilation[m]) + b1[m]
+ *                          xt = conv1d(lrelu(xt, 0.1), w2[m], 1) + b2[m];   x = xt + x
+ *   y = [accumulate ? y : 0] + out_scale * x
+ * w1, b1, w2, b2: HOST arrays of npairs DEVICE pointers, each weight [C, C, k] (PyTorch Conv1d
+ * layout), each bias [C].  bf16 operands, fp32 accumulate, fp32 residual stream kept in tensor
+ * memory.  Returns NVSE_ERR_UNSUPPORTED for shapes the fused kernel does not take (the generator
+ * then falls back to per-layer launches): C in {32, 64, 128, 256}, k odd <= 15, npairs <= 3. */
+NVSE_API int nvse_resblock1_bf16(const float* x, const float* const* w1, const float* const* b1,
+                        const float* const* w2, const float* const* b2, const int* dilations, int npairs,
+                        float* y, int64_t B, int64_t T, int C, int k, float out_scale, int accumulate, void* stream);
+
 /* y = conv_transpose1d(lrelu(x, in_slope), w, stride, padding) + bias;  w: [Cin, Cout, k]
  * (hifigan.py:93-96,111-112).  T_out = (T-1)*stride - 2*padding + k. */
 NVSE_API int nvse_conv_transpose1d_f32(const float* x, const float* w, const float* bias, float* y,
@@ -174,6 +186,12 @@ NVSE_API int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t 
  * tripped timeout sets a device flag and later tensor-core launches return without computing.
  * *flag = 1 if it is set; reset != 0 clears it.  Synchronises the device. */
 NVSE_API int nvse_tc_abort_status(int reset, int* flag);
+
+/* Debug hook of tools/rb_trace.py: with NVSE_RB_TRACE set in the environment the fused ResBlock kernel
+ * records clock64() stamps of one CTA's phase boundaries (slots 0..62: MMA warp, 63: cycles spent
+ * waiting for weight stages, 64..127: epilogue warp 0); this copies them to the host.  Returns -1
+ * when tracing is off. */
+NVSE_API int nvse_debug_rb_trace(long long* out128);
 
 #ifdef __cplusplus
 }

@@ -61,10 +61,13 @@ PROTOTYPES = {
     "nvse_transpose_btc_to_bct_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "nvse_conv1d_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _f, _f, _i, _vp]),
     "nvse_conv1d_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _f, _f, _i, _vp]),
+    "nvse_resblock1_bf16": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                 C.POINTER(_i), _i, _vp, _i64, _i64, _i, _i, _f, _i, _vp]),
     "nvse_conv_transpose1d_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_conv_transpose1d_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_istft_head_f32": (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp]),
     "nvse_tc_abort_status": (_i, [_i, C.POINTER(_i)]),
+    "nvse_debug_rb_trace": (_i, [C.POINTER(C.c_longlong)]),
 }
 
 _lib = None

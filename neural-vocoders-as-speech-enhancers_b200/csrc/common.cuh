@@ -53,6 +53,16 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// "T32" activation layout of the tensor-core path: fp32 [T, C] stored as [T/32][C/4][32][4], i.e.
+// 32-row blocks in which the 4-channel groups of consecutive rows are contiguous.  The tensor-core
+// kernels move activations with one thread per row (a TMEM lane is a row): in this layout a warp's
+// 16-byte accesses to 32 consecutive rows form ONE 512-byte segment, where channels-last scatters
+// them over 32 cache lines.  Rows are padded to a multiple of 32 per utterance.
+__host__ __device__ inline int64_t t32_off(int64_t t, int c, int C) {
+  return ((t >> 5) * (C >> 2) + (c >> 2)) * 128 + (t & 31) * 4 + (c & 3);
+}
+inline int64_t t32_rows(int64_t T) { return (T + 31) / 32 * 32; }
+
 constexpr int kMaxTaps = 16;
 
 // One "tap-list" convolution over channels-last activations.  A plain dilated Conv1d is a

@@ -137,12 +137,14 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
   for (int ci0 = 0; ci0 < a.Cin; ci0 += THIN_CK) {
     const int ck = min(THIN_CK, a.Cin - ci0);
     for (int e = tid; e < nrows * THIN_CK; e += THIN_ROWS) {
-      const int r = e / THIN_CK, c = e % THIN_CK;
+      // channels-last: lanes run along the channels of a row; T32: along (4 channels, consecutive rows)
+      const int r = a.x_t32 ? (e >> 2) % nrows : e / THIN_CK;
+      const int c = a.x_t32 ? ((e & 3) | (((e >> 2) / nrows) << 2)) : e % THIN_CK;
       const int vrow = t0 + min_off + r;  // row in the (virtually reflection-padded) input
       float v = 0.0f;
       if (c < ck && vrow >= 0 && vrow < a.Tin) {
         const int arow = vrow < a.reflect_left ? a.reflect_left - vrow : vrow - a.reflect_left;
-        v = lrelu(xb[(int64_t)arow * a.Cin + ci0 + c], a.in_slope);
+        v = lrelu(xb[a.x_t32 ? t32_off(arow, ci0 + c, a.Cin) : (int64_t)arow * a.Cin + ci0 + c], a.in_slope);
       }
       xs[r * THIN_XSTRIDE + c] = v;
     }
@@ -227,6 +229,7 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
   ProfScope prof("conv_f32", a.Cin, a.Cout, 2.0 * prows * a.Cin * a.Cout * a.taps.ntaps,
                  prows * 4.0 * (a.Cin + a.Cout * (a.accumulate ? 2.0 : 1.0) + (a.residual ? a.Cout : 0.0)), st);
   const bool thin = a.Cout < 32 || a.reflect_left || (a.Cin % BK != 0 && a.Cout <= 32);
+  NVSE_REQUIRE(!a.x_t32 || (thin && a.Cin % 4 == 0), NVSE_ERR_UNSUPPORTED, "fp32 conv: T32 input is only read by the thin kernel");
   if (thin) {
     NVSE_REQUIRE(a.Cout <= 32, NVSE_ERR_UNSUPPORTED, "thin conv: Cout=%d > 32", a.Cout);
     NVSE_REQUIRE(max_off - min_off <= THIN_MAX_SPAN, NVSE_ERR_UNSUPPORTED, "thin conv: tap span %d too wide", max_off - min_off);

@@ -26,6 +26,7 @@ struct ConvF32Args {
   float out_scale;       // y = [accumulate ? y : 0] + out_scale * (conv + bias + residual)
   int accumulate;
   int out_act;           // 0 none, 1 tanh
+  int x_t32;             // x is in the T32 layout (thin kernel only: conv_post of the tensor-core path)
   int reflect_left;      // x is viewed through ReflectionPad1d((reflect_left, 0)) (istftnet.py:296,312)
 };
 

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 
   // ---- epilogue warps: pull the rows they will read in the epilogue (residual, accumulate target)
   //      into L2 now; staging + MMAs give the prefetch time to land ------------------------------
-  if (warp < kEpiWarps && !a.out_bf16 && (a.residual || a.accumulate)) {
+  if (warp < kEpiWarps && !a.out_bf16 && !a.y_t32 && (a.residual || a.accumulate)) {
     const int q = warp & 3, half = warp >> 2;
     for (int ph = 0; ph < k.nphase; ++ph)
       for (int j = 0; j < ntile; ++j) {
@@ -135,14 +135,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
 #pragma unroll
         for (int u = 0; u < kStageUnroll; ++u) {
           const int e = e0 + u * kThreads;
-          const int chunk = e & (nchunk - 1), r = e >> cshift;
+          // channels-last: consecutive lanes take consecutive 8-channel chunks of a row; T32: consecutive rows of a chunk
+          const int chunk = a.x_t32 ? e / k.rows : e & (nchunk - 1), r = a.x_t32 ? e - chunk * k.rows : e >> cshift;
           const int t = t0 + k.min_off + r;
           dst[u] = e < items ? (chunk * k.rows_pad + r) * 16 : -1;
           f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (e < items && t >= 0 && t < a.Tin) {
-            const float4* src = reinterpret_cast<const float4*>(xb + (int64_t)t * Cin + chunk * 8);
+            const float4* src = reinterpret_cast<const float4*>(xb + (a.x_t32 ? t32_off(t, chunk * 8, Cin) : (int64_t)t * Cin + chunk * 8));
             f0[u] = __ldg(src);
-            f1[u] = __ldg(src + 1);
+            f1[u] = __ldg(src + (a.x_t32 ? 32 : 1));
           }
         }
 #pragma unroll
@@ -270,13 +271,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
         } else {
           // issue every global load of this chunk before waiting on TMEM (latency overlap)
           float4 bq[4], rq[4], yq[4];
-          float* yr = reinterpret_cast<float*>(a.y) + b * a.y_bstride + orow * Cout + c0;
-          const float* rr = a.residual ? a.residual + b * a.y_bstride + orow * Cout + c0 : nullptr;
+          const int64_t yoff = b * a.y_bstride + (a.y_t32 ? t32_off(orow, c0, Cout) : orow * Cout + c0);
+          const int qs = a.y_t32 ? 128 : 4;  // floats between consecutive 4-channel groups of a row
+          float* yr = reinterpret_cast<float*>(a.y) + yoff;
+          const float* rr = a.residual ? a.residual + yoff : nullptr;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             bq[q] = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q);
-            rq[q] = (valid && rr) ? *reinterpret_cast<const float4*>(rr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            yq[q] = (valid && a.accumulate) ? *reinterpret_cast<const float4*>(yr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rq[q] = (valid && rr) ? *reinterpret_cast<const float4*>(rr + qs * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            yq[q] = (valid && a.accumulate) ? *reinterpret_cast<const float4*>(yr + qs * q) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           tmem_ld_wait();
           if (valid) {
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
               o.y = (o.y + rq[q].y) * a.out_scale + yq[q].y;
               o.z = (o.z + rq[q].z) * a.out_scale + yq[q].z;
               o.w = (o.w + rq[q].w) * a.out_scale + yq[q].w;
-              *reinterpret_cast<float4*>(yr + 4 * q) = o;
+              *reinterpret_cast<float4*>(yr + qs * q) = o;
             }
           }
         }
@@ -357,6 +360,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "tensor-core conv: batch %lld exceeds 65535 per launch", (long long)B);
   NVSE_REQUIRE(!(a.out_bf16 && (a.residual || a.accumulate)), NVSE_ERR_INVALID, "tensor-core conv: bf16 output takes no residual");
   NVSE_REQUIRE(!(a.split_act && a.in_bf16), NVSE_ERR_INVALID, "tensor-core conv: split activations need fp32 input");
+  NVSE_REQUIRE(!(a.x_t32 && a.in_bf16) && !(a.y_t32 && a.out_bf16), NVSE_ERR_INVALID, "tensor-core conv: the T32 layout is fp32 only");
   if (B == 0 || a.Trows <= 0) return NVSE_OK;
   KernelArgs k;
   k.a = a;

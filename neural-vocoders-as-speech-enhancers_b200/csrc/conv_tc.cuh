@@ -22,6 +22,7 @@ struct ConvTcArgs {
   int Tin;
   int Cin, Cout;
   int in_bf16;
+  int x_t32;           // fp32 x is in the T32 layout (common.cuh); x_bstride then counts padded rows
   const __nv_bfloat16* wimg;
   const float* bias;
   const float* residual;  // fp32, same shape as y (fp32 output only; added after the out_slope activation)
@@ -29,6 +30,7 @@ struct ConvTcArgs {
   int64_t y_bstride;
   int Tout;
   int out_bf16;           // y = bf16(lrelu(conv + bias, out_slope))
+  int y_t32;              // fp32 y (and residual) are in the T32 layout
   ConvTaps taps;
   int out_mul, out_add, Trows;
   float in_slope, out_slope, out_scale;

@@ -4,7 +4,9 @@
 // workspace (four ping-pong activation buffers).
 #include "generator.cuh"
 #include "conv_tc.cuh"
+#include "resblock_tc.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace nvse {
@@ -55,7 +57,7 @@ static int64_t max_activation_elems(const nvse_generator* g, int64_t F) {
   for (int i = 0; i < c.num_upsamples; ++i) {
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
     T = (T - 1) * u - 2 * ((k - u) / 2) + k;
-    m = std::max<int64_t>(m, T * (c.initial_channel >> (i + 1)));
+    m = std::max<int64_t>(m, t32_rows(T) * (c.initial_channel >> (i + 1)));  // T32 pads rows to a multiple of 32
   }
   if (c.kind == NVSE_GEN_ISTFTNET) m = std::max<int64_t>(m, (T + 1) * (c.istft_n_fft + 2));
   return m;
@@ -100,7 +102,7 @@ static int run_conv(const Layer& L, bool tc, const ConvIO& io, int64_t B, int64_
 // path up to 8 phases share one launch: the activation tile is staged once and the phases ping-pong
 // between two TMEM accumulators.
 static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool x_t32 = false, bool y_t32 = false) {
   const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
   const int nph = (int)std::min<int64_t>(L.stride, Tout);
   if (tc && L.w_bf16) {
@@ -114,9 +116,10 @@ static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B
         out_add[p] = r0 + p;
       }
       ConvTcArgs a{};
-      a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout;
+      a.x = x; a.x_bstride = (x_t32 ? t32_rows(Tin) : Tin) * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout;
       a.wimg = reinterpret_cast<const __nv_bfloat16*>(L.w_bf16); a.bias = L.bias;
-      a.y = y; a.y_bstride = Tout * L.Cout; a.Tout = (int)Tout;
+      a.y = y; a.y_bstride = (y_t32 ? t32_rows(Tout) : Tout) * L.Cout; a.Tout = (int)Tout;
+      a.x_t32 = x_t32; a.y_t32 = y_t32;
       a.out_mul = L.stride; a.Trows = (int)((Tout - r0 + L.stride - 1) / L.stride);
       a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
       a.split_act = L.tc_split;
@@ -124,6 +127,7 @@ static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B
     }
     return NVSE_OK;
   }
+  NVSE_REQUIRE(!x_t32 && !y_t32, NVSE_ERR_STATE, "ConvTranspose1d %s: the T32 layout needs the tensor-core path", L.name.c_str());
   for (int r = 0; r < nph; ++r) {
     ConvF32Args a{};
     a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin;
@@ -156,16 +160,62 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
     const ConvIO io{bufR, false, nullptr, bufA, false, 1.0f, 1.0f, 1.0f, 0};
     if (int rc = run_conv(g->layer("conv_pre"), false, io, B, F, st)) return rc;
   }
+  // Fused tensor-core plan: every ResBlock1 as one launch (or one launch per pair, whichever the cost
+  // model of resblock_tc.cu prefers).  When every stage can be fused the activations between the
+  // kernels are kept in the T32 layout (common.cuh); otherwise the per-layer channels-last path runs.
+  static const bool fuse_env = [] { const char* e = std::getenv("NVSE_RB_FUSE"); return !(e && e[0] == '0'); }();
+  std::vector<int> per_launch((size_t)c.num_upsamples * c.num_kernels, 0);
+  bool t32 = tc && fuse_env && c.resblock_type == 1;
+  for (int i = 0; i < c.num_upsamples && t32; ++i) {
+    t32 = g->layer("ups." + std::to_string(i)).w_bf16 != nullptr;
+    for (int j = 0; j < c.num_kernels && t32; ++j) {
+      const std::string p = "resblocks." + std::to_string(i * c.num_kernels + j);
+      const int nd = c.num_dilations[j];
+      const Layer& l0 = g->layer(p + ".convs1.0");
+      for (int m = 0; m < nd && t32; ++m)
+        t32 = g->layer(p + ".convs1." + std::to_string(m)).w_bf16 && g->layer(p + ".convs2." + std::to_string(m)).w_bf16;
+      if (!t32) break;
+      const int* dil = c.resblock_dilations[j];
+      double whole = nd <= kRbMaxPairs ? rb_cost_per_row(l0.Cin, l0.k, dil, nd) : -1.0, single = 0.0;
+      for (int m = 0; m < nd; ++m) {
+        const double v = rb_cost_per_row(l0.Cin, l0.k, dil + m, 1);
+        single = (v < 0.0 || single < 0.0) ? -1.0 : single + v;
+      }
+      if (whole < 0.0 && single < 0.0) t32 = false;
+      per_launch[(size_t)i * c.num_kernels + j] = (single < 0.0 || (whole >= 0.0 && whole <= single)) ? nd : 1;
+    }
+  }
   int64_t T = F;
   for (int i = 0; i < c.num_upsamples; ++i) {
     const Layer& up = g->layer("ups." + std::to_string(i));
-    if (int rc = run_conv_transpose(up, tc, bufA, B, T, bufU, slope, st)) return rc;  // hifigan.py:111-112
+    if (int rc = run_conv_transpose(up, tc, bufA, B, T, bufU, slope, st, t32 && i > 0, t32)) return rc;  // hifigan.py:111-112
     T = (T - 1) * up.stride - 2 * up.padding + up.k;
     const float inv = 1.0f / (float)c.num_kernels;  // hifigan.py:119
     for (int j = 0; j < c.num_kernels; ++j) {
       const std::string p = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
       const float* src = bufU;
+      if (t32) {
+        const int per = per_launch[(size_t)i * c.num_kernels + j];
+        const Layer& l0 = g->layer(p + ".convs1.0");
+        for (int m0 = 0; m0 < nd; m0 += per) {
+          const bool last = (m0 + per == nd);
+          float* dst = last ? bufA : (src == bufR ? bufT : bufR);
+          ResblockTcArgs ra{};
+          ra.x = src; ra.y = dst; ra.T = (int)T; ra.C = l0.Cin; ra.k = l0.k; ra.npairs = per;
+          ra.t32 = 1; ra.bstride = t32_rows(T) * l0.Cin;
+          ra.slope = slope; ra.out_scale = last ? inv : 1.0f; ra.accumulate = last && j > 0;
+          for (int q = 0; q < per; ++q) {
+            const Layer& c1 = g->layer(p + ".convs1." + std::to_string(m0 + q));
+            const Layer& c2 = g->layer(p + ".convs2." + std::to_string(m0 + q));
+            ra.pair[q] = RbPair{reinterpret_cast<const __nv_bfloat16*>(c1.w_bf16), reinterpret_cast<const __nv_bfloat16*>(c2.w_bf16),
+                                c1.bias, c2.bias, c1.dilation};
+          }
+          if (int rc = launch_resblock_tc(ra, B, st)) return rc;
+          src = dst;
+        }
+        continue;
+      }
       for (int m = 0; m < nd; ++m) {
         const bool last = (m == nd - 1);
         float* dst = last ? bufA : (c.resblock_type == 1 ? bufR : (src == bufR ? bufT : bufR));
@@ -192,7 +242,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   }
   const Layer& post = g->layer("conv_post");
   ConvF32Args a{};
-  a.x = bufA; a.x_bstride = T * post.Cin; a.Cin = post.Cin;
+  a.x = bufA; a.x_bstride = (t32 ? t32_rows(T) : T) * post.Cin; a.Cin = post.Cin; a.x_t32 = t32;
   a.w = post.w; a.bias = post.bias; a.Cout = post.Cout;
   conv1d_taps(post.k, 1, &a.taps);
   a.out_mul = 1; a.out_add = 0; a.in_slope = 0.01f; a.out_scale = 1.0f;  // F.leaky_relu default slope, hifigan.py:120

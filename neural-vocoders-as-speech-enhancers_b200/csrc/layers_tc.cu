@@ -1,8 +1,11 @@
 // Layer-level C ABI entry points of the tensor-core path (test convenience: they pack the
 // weights on the fly, which the generator handle does once at load time).
+#include <cstdlib>
+
 #include "conv_f32.cuh"
 #include "conv_tc.cuh"
 #include "generator.cuh"
+#include "resblock_tc.cuh"
 
 using namespace nvse;
 
@@ -76,10 +79,42 @@ extern "C" int nvse_conv_transpose1d_bf16(const float* x, const float* w, const 
   return NVSE_OK;
 }
 
+extern "C" int nvse_resblock1_bf16(const float* x, const float* const* w1, const float* const* b1, const float* const* w2,
+                                   const float* const* b2, const int* dilations, int npairs, float* y, int64_t B, int64_t T,
+                                   int C, int k, float out_scale, int accumulate, void* stream) {
+  NVSE_REQUIRE(x && w1 && b1 && w2 && b2 && dilations && y, NVSE_ERR_INVALID, "nvse_resblock1_bf16: null argument");
+  NVSE_REQUIRE(B >= 0 && T >= 0 && T <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_resblock1_bf16: bad shape");
+  NVSE_REQUIRE(npairs >= 1 && npairs <= kRbMaxPairs, NVSE_ERR_UNSUPPORTED, "nvse_resblock1_bf16: %d pairs (1..%d)", npairs, kRbMaxPairs);
+  NVSE_REQUIRE(rb_supported(C, k, dilations, npairs), NVSE_ERR_UNSUPPORTED, "nvse_resblock1_bf16: C=%d k=%d unsupported", C, k);
+  cudaStream_t st = as_stream(stream);
+  const size_t wn = (size_t)C * C * k;
+  Scratch wk(st), img(st);
+  NVSE_CUDA_CHECK(wk.alloc(sizeof(float) * wn));
+  NVSE_CUDA_CHECK(img.alloc(sizeof(__nv_bfloat16) * wn * 2 * npairs));
+  ResblockTcArgs a{};
+  a.x = x; a.y = y; a.T = (int)T; a.C = C; a.k = k; a.npairs = npairs;
+  a.slope = 0.1f; a.out_scale = out_scale; a.accumulate = accumulate;
+  // timing experiments only (tools/rb_bench.py): read x / y as T32 buffers; needs T % 32 == 0
+  static const bool bench_t32 = std::getenv("NVSE_RB_T32") != nullptr;
+  a.t32 = bench_t32 && (T % 32 == 0);
+  for (int m = 0; m < npairs; ++m) {
+    NVSE_REQUIRE(w1[m] && w2[m] && b1[m] && b2[m], NVSE_ERR_INVALID, "nvse_resblock1_bf16: null tensor in pair %d", m);
+    __nv_bfloat16* i1 = (__nv_bfloat16*)img.p + (size_t)(2 * m) * wn;
+    __nv_bfloat16* i2 = i1 + wn;
+    if (int rc = launch_repack_weight(w1[m], (float*)wk.p, C, C, k, false, st)) return rc;
+    if (int rc = launch_pack_weight_tc((const float*)wk.p, i1, C, C, k, st)) return rc;
+    if (int rc = launch_repack_weight(w2[m], (float*)wk.p, C, C, k, false, st)) return rc;
+    if (int rc = launch_pack_weight_tc((const float*)wk.p, i2, C, C, k, st)) return rc;
+    a.pair[m] = RbPair{i1, i2, b1[m], b2[m], dilations[m]};
+  }
+  return launch_resblock_tc(a, B, st);
+}
+
 extern "C" int nvse_tc_abort_status(int reset, int* flag) {
   NVSE_REQUIRE(flag, NVSE_ERR_INVALID, "nvse_tc_abort_status: null argument");
-  unsigned int v = 0;
+  unsigned int v = 0, v2 = 0;
   if (int rc = tc_abort_status(reset != 0, &v)) return rc;
-  *flag = (int)v;
+  if (int rc = rb_abort_status(reset != 0, &v2)) return rc;
+  *flag = (int)(v | v2);
   return NVSE_OK;
 }

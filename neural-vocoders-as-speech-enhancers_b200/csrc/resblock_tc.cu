@@ -1,0 +1,505 @@
+// Fused ResBlock1 chain on the 5th-gen tensor cores (sm_100a): Models/hifigan.py:43-50,
+//
+//   for m in pairs:  xt = c1_m(lrelu(x));  xt = c2_m(lrelu(xt));  x = xt + x
+//
+// as ONE kernel per (utterance, time tile).  A CTA pushes R = 128 * ntile rows through the whole
+// chain ("overlapped tiling": every conv is evaluated on all R rows, rows closer to the tile edge
+// than the receptive field go stale and only the central R - 2 * halo rows are written), so the
+// residual stream and every intermediate stay on chip:
+//
+//   * X, the fp32 residual stream, lives in TENSOR MEMORY (ntile * C columns).  c2's MMAs are
+//     issued with accumulate = 1 straight onto X, i.e. the tensor core performs the "+ x".  The
+//     c2 biases are never added to X: X_true = X + cb_m with cb_m = b2_0 + .. + b2_m per channel,
+//     which the epilogues add on the fly.
+//   * ACC, the accumulator of c1, is a second TMEM region of the same size.
+//   * OP, the bf16 operand buffer in shared memory, canonical no-swizzle K-major UMMA layout
+//     [ci/8][row][ci%8] with P zero rows on either side.  A conv tap is a row shift of the A
+//     descriptor's start address.  The epilogues overwrite OP in place:
+//        load:  OP = bf16(lrelu(x))          epi1:  OP = bf16(lrelu(ACC + b1))
+//        epi2:  OP = bf16(lrelu(X + cb_m))   (rows outside [0, T) forced to 0 = "same" padding)
+//   * weights stream through an mbarrier ring of (tap, 64-channel K chunk) stages, one
+//     cp.async.bulk per stage, each stage feeding the MMAs of all ntile tiles.
+//
+// Warp roles (320 threads): warps 0-7 load/epilogue (TMEM lane quarter = warp & 3, the two warps of
+// a quarter split the 16-column chunks), warp 8 weight producer, warp 9 TMEM allocator + MMA issuer.
+#include "resblock_tc.cuh"
+
+#include <cstdlib>
+
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace nvse {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kWorkWarps = 8;
+constexpr int kThreads = (kWorkWarps + 2) * 32;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kNumBars = 2 * kMaxStages + 4;
+
+struct RbKernelArgs {
+  ResblockTcArgs a;
+  int ntile;     // 128-row tiles per CTA
+  int halo;      // rows of context the chain consumes on each side
+  int V;         // 128 * ntile - 2 * halo: output rows one CTA produces
+  int P;         // zero rows on each side of the operand buffer (largest conv padding)
+  int rows_pad;  // operand buffer rows per 8-channel chunk (P + R + P)
+  int stages, kc;
+  long long* trace;  // debug: clock64 stamps of one CTA's phase boundaries (NVSE_RB_TRACE), else null
+};
+
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  // every lane polls (try_wait suspends in hardware); a timeout in any lane is seen by all
+  const bool ok = mbar_wait(bar, parity);
+  return __all_sync(0xffffffffu, ok);
+}
+
+// 16 activated values of one row -> two 16-byte core-matrix rows of the operand buffer
+__device__ __forceinline__ void store_operand(uint8_t* op, int rows_pad, int brow, int c0, const float (&f)[16], float slope,
+                                              bool keep) {
+  uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+  if (keep) {
+    v0.x = pack_bf16(lrelu(f[0], slope), lrelu(f[1], slope));
+    v0.y = pack_bf16(lrelu(f[2], slope), lrelu(f[3], slope));
+    v0.z = pack_bf16(lrelu(f[4], slope), lrelu(f[5], slope));
+    v0.w = pack_bf16(lrelu(f[6], slope), lrelu(f[7], slope));
+    v1.x = pack_bf16(lrelu(f[8], slope), lrelu(f[9], slope));
+    v1.y = pack_bf16(lrelu(f[10], slope), lrelu(f[11], slope));
+    v1.z = pack_bf16(lrelu(f[12], slope), lrelu(f[13], slope));
+    v1.w = pack_bf16(lrelu(f[14], slope), lrelu(f[15], slope));
+  }
+  const int chunk = c0 >> 3;
+  *reinterpret_cast<uint4*>(op + ((size_t)chunk * rows_pad + brow) * 16) = v0;
+  *reinterpret_cast<uint4*>(op + ((size_t)(chunk + 1) * rows_pad + brow) * 16) = v1;
+}
+
+// C and the tile count are compile-time: the MMA issue loop must unroll completely -- a tcgen05.mma issued
+// from a loop with run-time trip counts costs 60-200 cycles of issue (tools/probe/mma_probe3.cu), more
+// than the MMA itself takes on the tensor core.
+template <int C, int NT>
+__global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resblock_tc_kernel(const __grid_constant__ RbKernelArgs k) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const ResblockTcArgs& a = k.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int n = NT, R = n * kTileM, nchunk = C >> 3, KC = C < 64 ? C : 64;
+  const int npairs = a.npairs;
+  const int64_t b = blockIdx.y;
+  const int64_t bstride = a.bstride;
+  const int ws4 = a.t32 ? 32 : 1;  // float4 stride between the 4-channel groups of one row
+  const int t_in0 = (int)blockIdx.x * k.V - k.halo;  // time index of tile row 0
+  const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
+  constexpr uint32_t stage_bytes = (uint32_t)KC * C * 2u;
+  uint8_t* op = smem_raw;
+  uint8_t* wst = smem_raw + op_bytes;
+  float* bsm = reinterpret_cast<float*>(wst + (size_t)k.stages * stage_bytes);  // b1[m][C] then cb[m][C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 2 * kRbMaxPairs * C);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
+  const uint32_t bar_op = smem_u32(bars + 2 * kMaxStages), bar_acc = bar_op + 8, bar_h = bar_op + 16, bar_x = bar_op + 24;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * n * C)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < k.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_op, kWorkWarps);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_h, kWorkWarps);
+    mbar_init(bar_x, 1);
+    fence_barrier_init();
+  }
+  if (warp == kWorkWarps + 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  // zero rows on both sides of every chunk of the operand buffer (never written again)
+  {
+    const int zr = 2 * k.P;
+    for (int e = tid; e < nchunk * zr; e += kThreads) {
+      const int chunk = e / zr, i = e - chunk * zr;
+      const int row = i < k.P ? i : R + i;  // [0, P) and [P + R, 2P + R)
+      *reinterpret_cast<uint4*>(op + ((size_t)chunk * k.rows_pad + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int e = tid; e < npairs * C; e += kThreads) {
+      const int m = e / C, c = e - m * C;
+      bsm[e] = __ldg(a.pair[m].b1 + c);
+      float cb = 0.f;
+      for (int i = 0; i <= m; ++i) cb += __ldg(a.pair[i].b2 + c);
+      bsm[kRbMaxPairs * C + e] = cb;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_x = tmem_base, tmem_acc = tmem_base + (uint32_t)(n * C);
+  constexpr int nkc = C / KC;
+  const bool tracing = k.trace != nullptr && blockIdx.x == 3 && blockIdx.y == gridDim.y / 2 && lane == 0;  // a CTA of a middle wave
+  int tr_i = 0;
+#define RB_STAMP(role) do { if (tracing) k.trace[(role) * 64 + tr_i++] = clock64(); } while (0)
+
+  if (warp == kWorkWarps) {
+    // ===== weight producer: one bulk copy per (conv, tap, K chunk) stage =====
+    if (lane == 0) {
+      const uint32_t nstage = (uint32_t)k.stages;
+      uint32_t s = 0, ph = 1;
+      for (int m = 0; m < npairs; ++m)
+        for (int half = 0; half < 2; ++half) {
+          const __nv_bfloat16* wimg = half ? a.pair[m].w2 : a.pair[m].w1;
+          for (int st = 0; st < a.k * nkc; ++st) {
+            if (!mbar_wait(bar_empty + 8 * s, ph)) goto done;
+            mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
+            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (stage_bytes / 2), stage_bytes,
+                          bar_full + 8 * s);
+            if (++s == nstage) { s = 0; ph ^= 1u; }
+          }
+        }
+    }
+  } else if (warp == kWorkWarps + 1) {
+    // ===== MMA issuer: ONE elected thread runs the whole loop.  Everything on its path between two
+    // MMAs is a handful of instructions (no divisions, no votes): the tensor-core queue is only a few
+    // MMAs deep, so issue-side latency beyond ~100 cycles per stage shows up as tensor idle time. =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      // descriptor low words advance in 16-byte units: one operand-buffer row = 1, one weight row = 1
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(op), (uint32_t)k.rows_pad * 16u);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(wst), (uint32_t)C * 16u);
+      const uint32_t hi = umma_desc_hi(128u);
+      constexpr uint32_t stage_units = stage_bytes >> 4;
+      constexpr int kkn = KC >> 4;
+      const uint32_t nstage = (uint32_t)k.stages;
+      uint32_t s = 0, ph = 0;  // ring slot and its phase parity
+      long long tr_wait = 0;
+      for (int m = 0; m < npairs; ++m)
+        for (int half = 0; half < 2; ++half) {
+          RB_STAMP(0);
+          if (!mbar_wait(half ? bar_h : bar_op, m & 1)) goto mma_exit;
+          tc_fence_after();
+          RB_STAMP(0);
+          const int d = half ? 1 : a.pair[m].dil;
+          const uint32_t d_tmem = half ? tmem_x : tmem_acc;
+          uint32_t acc = half ? 1u : 0u;  // c1 starts a fresh accumulator, c2 accumulates onto X
+          uint32_t a_tap = a_lo0 + (uint32_t)(k.P - (a.k - 1) / 2 * d);
+          for (int tap = 0; tap < a.k; ++tap, a_tap += (uint32_t)d) {
+#pragma unroll
+            for (int kc = 0; kc < nkc; ++kc) {
+              const long long tw0 = tracing ? clock64() : 0;
+              if (!mbar_wait(bar_full + 8 * s, ph)) goto mma_exit;
+              if (tracing) tr_wait += clock64() - tw0;
+              tc_fence_after();
+              uint32_t a_lo = a_tap + (uint32_t)(kc * (KC >> 3)) * (uint32_t)k.rows_pad;
+              uint32_t b_lo = b_lo0 + s * stage_units;
+#pragma unroll
+              for (int kk = 0; kk < kkn; ++kk) {
+#pragma unroll
+                for (int j = 0; j < n; ++j)
+                  tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, acc);
+                acc = 1u;
+                a_lo += 2u * (uint32_t)k.rows_pad;
+                b_lo += 2u * (uint32_t)C;
+              }
+              tc_commit(bar_empty + 8 * s);
+              if (++s == nstage) { s = 0; ph ^= 1u; }
+            }
+          }
+          tc_commit(half ? bar_x : bar_acc);
+        }
+      if (tracing) k.trace[63] = tr_wait;
+    mma_exit:;
+    }
+    __syncwarp();
+  } else {
+    // ===== load / epilogue warps =====
+    const int q = warp & 3, h = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const float slope = a.slope;
+#define RB_WSTAMP() do { if (warp == 0) RB_STAMP(1); } while (0)
+    RB_WSTAMP();
+    // Work items of this warp: (tile j, 16-column chunk c0).  Global loads are issued U items ahead of
+    // their use: the load and the final phase are pure memory latency otherwise.
+    constexpr int CPW = C / 32;          // chunks per warp and tile
+    constexpr int IT = n * CPW;          // items per warp
+    constexpr int UMAX = (2 * NT * C <= 256) ? 2 : 4;  // two resident CTAs: half the registers each
+    constexpr int U = IT < UMAX ? IT : UMAX;           // items in flight (U * 64 bytes per thread)
+    if (a.accumulate) {
+      // the rows of y the final phase will read: pull them into L2 while the chain runs
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
+        if (r >= k.halo && r < R - k.halo && t < a.T)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + b * bstride + (a.t32 ? t32_off(t, ((i % CPW) * 2 + h) * 16, C) : (int64_t)t * C + ((i % CPW) * 2 + h) * 16)));
+      }
+    }
+    // load: x -> X (TMEM, fp32) and OP = bf16(lrelu(x))
+#pragma unroll
+    for (int i0 = 0; i0 < IT; i0 += U) {
+      float4 v[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16;
+        const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
+        const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+        const bool inb = t >= 0 && t < a.T;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v[u][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16, jt = i / CPW;
+        const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
+        float f[16];
+        uint32_t bits[16];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          f[4 * w] = v[u][w].x; f[4 * w + 1] = v[u][w].y; f[4 * w + 2] = v[u][w].z; f[4 * w + 3] = v[u][w].w;
+        }
+#pragma unroll
+        for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
+        tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
+        store_operand(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+      }
+    }
+    tmem_st_wait();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_op);
+    RB_WSTAMP();
+
+    for (int m = 0; m < npairs; ++m) {
+      // epi1: OP = bf16(lrelu(ACC + b1_m)), zero outside the sequence
+      if (!mbar_wait_warp(bar_acc, m & 1)) break;
+      tc_fence_after();
+      RB_WSTAMP();
+      const float* b1 = bsm + m * C;
+      for (int j = 0; j < n; ++j) {
+        const int r = j * kTileM + q * 32 + lane;
+        const int t = t_in0 + r;
+        const bool inb = t >= 0 && t < a.T;
+        for (int c0 = h * 16; c0 < C; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_acc + lane_sel + (uint32_t)(j * C + c0), v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 bq = *reinterpret_cast<const float4*>(b1 + c0 + 4 * u);
+            f[4 * u] = __uint_as_float(v[4 * u]) + bq.x;
+            f[4 * u + 1] = __uint_as_float(v[4 * u + 1]) + bq.y;
+            f[4 * u + 2] = __uint_as_float(v[4 * u + 2]) + bq.z;
+            f[4 * u + 3] = __uint_as_float(v[4 * u + 3]) + bq.w;
+          }
+          store_operand(op, k.rows_pad, k.P + r, c0, f, slope, inb);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_h);
+      RB_WSTAMP();
+
+      if (!mbar_wait_warp(bar_x, m & 1)) break;
+      tc_fence_after();
+      RB_WSTAMP();
+      const float* cb = bsm + (kRbMaxPairs + m) * C;
+      if (m + 1 < npairs) {
+        // epi2: OP = bf16(lrelu(X + cb_m)): the input of the next pair
+        for (int j = 0; j < n; ++j) {
+          const int r = j * kTileM + q * 32 + lane;
+          const int t = t_in0 + r;
+          const bool inb = t >= 0 && t < a.T;
+          for (int c0 = h * 16; c0 < C; c0 += 32) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(j * C + c0), v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 bq = *reinterpret_cast<const float4*>(cb + c0 + 4 * u);
+              f[4 * u] = __uint_as_float(v[4 * u]) + bq.x;
+              f[4 * u + 1] = __uint_as_float(v[4 * u + 1]) + bq.y;
+              f[4 * u + 2] = __uint_as_float(v[4 * u + 2]) + bq.z;
+              f[4 * u + 3] = __uint_as_float(v[4 * u + 3]) + bq.w;
+            }
+            store_operand(op, k.rows_pad, k.P + r, c0, f, slope, inb);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_op);
+        RB_WSTAMP();
+      } else {
+        // final: y = [y +] out_scale * (X + cb_last) for the central V rows
+#pragma unroll
+        for (int i0 = 0; i0 < IT; i0 += U) {
+          float4 yq[U][4];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16;
+            const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
+            const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+            const float4* src = reinterpret_cast<const float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+#pragma unroll
+            for (int w = 0; w < 4; ++w) yq[u][w] = (valid && a.accumulate) ? src[w * ws4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16, jt = i / CPW;
+            const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
+            const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), v);
+            tmem_ld_wait();
+            if (valid) {
+              float4* dst = reinterpret_cast<float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const float4 bq = *reinterpret_cast<const float4*>(cb + c0 + 4 * w);
+                float4 o;
+                o.x = (__uint_as_float(v[4 * w]) + bq.x) * a.out_scale + yq[u][w].x;
+                o.y = (__uint_as_float(v[4 * w + 1]) + bq.y) * a.out_scale + yq[u][w].y;
+                o.z = (__uint_as_float(v[4 * w + 2]) + bq.z) * a.out_scale + yq[u][w].z;
+                o.w = (__uint_as_float(v[4 * w + 3]) + bq.w) * a.out_scale + yq[u][w].w;
+                dst[w * ws4] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+done:
+  if (warp == 0) RB_STAMP(1);
+  if (warp == kWorkWarps + 1) RB_STAMP(0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+constexpr size_t kSmemBudget = 224 * 1024;
+
+struct RbPlan {
+  int ntile, halo, V, P, rows_pad, stages, kc;
+  size_t smem;
+};
+
+// ntile: as many 128-row tiles as tensor memory (X + ACC = 2 * ntile * C columns <= 512) and shared memory allow
+bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
+  if (!(C == 32 || C == 64 || C == 128 || C == 256)) return false;
+  if (k < 1 || !(k & 1) || k > kMaxTaps || npairs < 1 || npairs > kRbMaxPairs) return false;
+  int halo = 0, P = (k - 1) / 2;
+  for (int m = 0; m < npairs; ++m) {
+    if (dil[m] < 1) return false;
+    halo += (k - 1) / 2 * dil[m] + (k - 1) / 2;
+    P = std::max(P, (k - 1) / 2 * dil[m]);
+  }
+  static const int forced = [] { const char* e = std::getenv("NVSE_RB_NTILE"); return e ? std::atoi(e) : 0; }();
+  int ntile = std::min(C <= 64 ? 4 : 8, 256 / C);
+  if (forced > 0) ntile = std::min(forced, 256 / C);
+  const int kc = tc_kchunk(C);
+  const size_t stage_bytes = (size_t)kc * C * 2;
+  const size_t tail = sizeof(float) * 2 * kRbMaxPairs * C + sizeof(uint64_t) * kNumBars + 16;
+  const int min_tile = C == 32 ? 4 : (C == 64 ? 2 : 1);  // instantiated kernels: see RB_LAUNCH
+  for (; ntile >= min_tile; ntile >>= 1) {
+    const int R = kTileM * ntile;
+    const int rows_pad = R + 2 * P;
+    const size_t opb = ((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127;
+    if (R - 2 * halo < 32) return false;  // not enough useful rows per tile: per-layer kernels do better
+    if (opb + 2 * stage_bytes + tail > kSmemBudget) continue;
+    int stages = (int)std::min<size_t>((kSmemBudget - opb - tail) / stage_bytes, (size_t)kMaxStages);
+    // keep two CTAs per SM resident when tensor memory allows it (2 * ntile * C <= 256 columns)
+    if (2 * ntile * C <= 256)
+      while (stages > 2 && opb + stages * stage_bytes + tail > 110 * 1024) --stages;
+    p->ntile = ntile; p->halo = halo; p->V = R - 2 * halo; p->P = P; p->rows_pad = rows_pad;
+    p->stages = stages; p->kc = kc;
+    p->smem = opb + stages * stage_bytes + tail;
+    return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+static long long* trace_buffer() {
+  static long long* buf = [] {
+    long long* ptr = nullptr;
+    if (std::getenv("NVSE_RB_TRACE")) {
+      cudaMalloc(&ptr, 128 * sizeof(long long));
+      cudaMemset(ptr, 0, 128 * sizeof(long long));
+    }
+    return ptr;
+  }();
+  return buf;
+}
+
+bool rb_supported(int C, int k, const int* dil, int npairs) {
+  RbPlan p;
+  return make_plan(C, k, dil, npairs, &p);
+}
+
+// Per-CTA cycle model fitted to the phase traces of tools/rb_trace.py (profiles/): load + final phases,
+// 2 * npairs MMA phases at the tensor-core/shared-memory floor, 2 * npairs - 1 epilogues.
+double rb_cost_per_row(int C, int k, const int* dil, int npairs) {
+  RbPlan p;
+  if (!make_plan(C, k, dil, npairs, &p)) return -1.0;
+  const double mma = std::max(C / 2.0, 32.0 + C / 4.0) * 1.12;
+  const double conv = (double)p.ntile * k * (C / 16) * mma;
+  const double epi = 600.0 + 7.5 * p.ntile * C;
+  const double io = 5000.0 + 110.0 * C * p.ntile / (C == 128 ? 2.0 : (C == 256 ? 1.0 : 4.0));
+  return (io + 2.0 * npairs * conv + (2.0 * npairs - 1.0) * epi) / p.V;
+}
+
+int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
+  NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "fused resblock: batch %lld exceeds 65535 per launch", (long long)B);
+  if (B == 0 || a.T <= 0) return NVSE_OK;
+  int dil[kRbMaxPairs] = {1, 1, 1};
+  for (int m = 0; m < a.npairs && m < kRbMaxPairs; ++m) dil[m] = a.pair[m].dil;
+  RbPlan p;
+  NVSE_REQUIRE(make_plan(a.C, a.k, dil, a.npairs, &p), NVSE_ERR_UNSUPPORTED, "fused resblock: C=%d k=%d unsupported", a.C, a.k);
+  RbKernelArgs k;
+  k.a = a;
+  if (k.a.bstride == 0) k.a.bstride = (a.t32 ? t32_rows(a.T) : (int64_t)a.T) * a.C;
+  k.trace = nullptr;
+  k.trace = trace_buffer();
+  k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
+  dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
+  const double rows = (double)B * a.T;
+  ProfScope prof("resblock_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0 * a.npairs,
+                 rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
+#define RB_LAUNCH(CC, NN)                                                                                                   \
+  if (a.C == CC && p.ntile == NN) {                                                                                         \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_tc_kernel<CC, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    resblock_tc_kernel<CC, NN><<<grid, kThreads, p.smem, st>>>(k);                                                          \
+  } else
+  RB_LAUNCH(32, 4) RB_LAUNCH(32, 8) RB_LAUNCH(64, 4) RB_LAUNCH(64, 2) RB_LAUNCH(128, 2) RB_LAUNCH(128, 1) RB_LAUNCH(256, 1)
+  return fail(NVSE_ERR_UNSUPPORTED, "fused resblock: no kernel for C=%d with %d tiles", a.C, p.ntile);
+#undef RB_LAUNCH
+  NVSE_LAUNCH_CHECK("resblock_tc_kernel");
+  return NVSE_OK;
+}
+
+long long* rb_trace_buffer() { return trace_buffer(); }
+
+int rb_abort_status(bool reset, unsigned int* flag) {
+  unsigned int v = 0;
+  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));
+  if (reset && v) {
+    const unsigned int z = 0;
+    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));
+  }
+  *flag = v;
+  return NVSE_OK;
+}
+
+}  // namespace nvse
+
+// debug (tools/rb_trace.py): copy the 2 x 64 phase stamps of the traced CTA to the host
+extern "C" int nvse_debug_rb_trace(long long* out128) {
+  if (!nvse::rb_trace_buffer() || !out128) return -1;
+  return cudaMemcpy(out128, nvse::rb_trace_buffer(), 128 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+

@@ -8,7 +8,8 @@ namespace nvse {
 namespace tc {
 
 constexpr long long kTimeoutCycles = 400000000LL;  // ~0.2 s: no legitimate wait is within 1000x of this
-// set when a bounded wait times out; one copy per translation unit (only conv_tc.cu includes this header)
+// set when a bounded wait times out; one copy per translation unit that includes this header
+// (conv_tc.cu, resblock_tc.cu); nvse_tc_abort_status reports the OR of the copies
 static __device__ unsigned int g_tc_abort = 0;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -131,6 +132,50 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+
+// One lane of the (converged) warp; the rest of the warp runs the same uniform code so that the
+// descriptors live in uniform registers and an MMA issue is a couple of instructions.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor halves: lo = (addr >> 4) | (lbo >> 4) << 16  (both 14-bit fields), hi = (sbo >> 4) | version bit 46
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: thread i writes 16 consecutive fp32 columns of lane base+i
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace nvse

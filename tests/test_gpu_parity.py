@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 import synth
 from oracle import np_oracle
-from util import build_generator, conv1d_cl, conv_transpose1d_cl, lib_mod, pkg, report, stream_ptr
+from util import build_generator, conv1d_cl, conv_transpose1d_cl, lib_mod, pkg, report, resblock1_cl, stream_ptr
 
 pytestmark = pytest.mark.gpu
 A = synth.HIFIGAN_V1
@@ -149,6 +149,45 @@ def test_conv1d_tensor_core_matches_torch_on_bf16_operands(cin, cout, k, d, T, B
     assert torch.allclose(out, conv, atol=3e-5, rtol=1e-5), float((out - conv).abs().max())
     out2 = conv1d_cl(x, w, b, d, in_slope=0.1, residual_bct=res, out_scale=1.0 / 3, y0_bct=y0, tc=True)
     assert torch.allclose(out2, y0 + (conv + res) / 3, atol=3e-5, rtol=1e-5)
+
+
+RB_CASES = [  # (C, k, dilations, T, B): every MRF class of HiFi-GAN V1; T spans several CTA tiles, ragged ends, tiny T
+    (32, 3, (1, 3, 5), 1300, 2), (32, 7, (1, 3, 5), 1000, 1), (32, 11, (1, 3, 5), 1000, 2), (32, 11, (1, 3, 5), 7, 1),
+    (64, 3, (1, 3, 5), 700, 1), (64, 7, (1, 3, 5), 1500, 1), (64, 11, (1, 3, 5), 900, 2), (64, 11, (1, 3, 5), 393, 1),
+    (128, 3, (1,), 600, 2), (128, 7, (3,), 255, 1), (128, 11, (5,), 1000, 1), (128, 11, (1, 3, 5), 400, 1),
+    (256, 3, (5,), 300, 1), (256, 11, (3,), 130, 2), (32, 3, (1, 1), 50, 1), (64, 5, (2,), 2000, 1),
+]
+
+
+@pytest.mark.parametrize("C_,k,dils,T,B", RB_CASES)
+def test_fused_resblock1_tensor_core_matches_torch_on_bf16_operands(C_, k, dils, T, B):
+    """The fused chain rounds exactly where this reference does (conv operands to bf16, fp32
+    accumulate, fp32 residual stream); what differs is fp32 summation order, which can flip an
+    occasional bf16 rounding of an intermediate -- hence a loose max-abs and a tight mean."""
+    n = len(dils)
+    x = _rand((B, C_, T), 41)
+    w1 = [_rand((C_, C_, k), 42 + m, 1.0 / np.sqrt(C_ * k)) for m in range(n)]
+    w2 = [_rand((C_, C_, k), 52 + m, 1.0 / np.sqrt(C_ * k)) for m in range(n)]
+    b1 = [_rand((C_,), 62 + m, 0.3) for m in range(n)]
+    b2 = [_rand((C_,), 72 + m, 0.3) for m in range(n)]
+    ref, ref32 = x, x
+    for m, d in enumerate(dils):
+        h = F.conv1d(_bf(F.leaky_relu(ref, 0.1)), _bf(w1[m]), b1[m], dilation=d, padding=(k - 1) * d // 2)
+        ref = F.conv1d(_bf(F.leaky_relu(h, 0.1)), _bf(w2[m]), b2[m], padding=(k - 1) // 2) + ref
+        h = F.conv1d(F.leaky_relu(ref32, 0.1), w1[m], b1[m], dilation=d, padding=(k - 1) * d // 2)
+        ref32 = F.conv1d(F.leaky_relu(h, 0.1), w2[m], b2[m], padding=(k - 1) // 2) + ref32
+    out = resblock1_cl(x, w1, b1, w2, b2, dils)
+    assert not lib_mod.tc_abort_status()
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs()
+    # a flipped rounding is one bf16 ulp of one operand and spreads through the later convs (the same
+    # reference evaluated by torch on CPU and on GPU differs by as much): bound it by a fraction of
+    # what bf16 rounding itself costs against the unrounded fp32 chain
+    budget = float((ref - ref32).abs().mean())
+    assert float(err.max()) <= 2e-2 and float(err.mean()) <= 0.5 * budget + 1e-5, (float(err.max()), float(err.mean()), budget)
+    y0 = _rand((B, C_, T), 99)
+    out2 = resblock1_cl(x, w1, b1, w2, b2, dils, out_scale=1.0 / 3, y0_bct=y0)
+    assert torch.allclose(out2, y0 + out / 3, atol=1e-5, rtol=1e-5)
 
 
 @pytest.mark.parametrize("cin,cout,k,u,T,B", [(512, 256, 16, 8, 9, 2), (256, 128, 16, 8, 140, 1), (128, 64, 4, 2, 130, 2),

@@ -54,6 +54,27 @@ def conv_transpose1d_cl(x_bct, w, b, stride, padding, in_slope=1.0, tc=False):
     return y.transpose(1, 2).contiguous()
 
 
+def resblock1_cl(x_bct, w1, b1, w2, b2, dilations, out_scale=1.0, y0_bct=None):
+    """Run nvse_resblock1_bf16 (fused ResBlock1 chain) on a [B, C, T] tensor; returns [B, C, T]."""
+    import torch
+    lib = lib_mod.load()
+    x = x_bct.transpose(1, 2).contiguous()
+    B, T, Cc = x.shape
+    k = w1[0].shape[2]
+    n = len(dilations)
+    if y0_bct is not None:
+        y, acc = y0_bct.transpose(1, 2).contiguous().clone(), 1
+    else:
+        y, acc = torch.full((B, T, Cc), float("nan"), dtype=torch.float32, device=x.device), 0
+    keep = [[t.contiguous() for t in ts] for ts in (w1, b1, w2, b2)]
+    arrs = [(C.c_void_p * n)(*[t.data_ptr() for t in ts]) for ts in keep]
+    dil = (C.c_int * n)(*dilations)
+    lib_mod.check(lib.nvse_resblock1_bf16(lib_mod.ptr(x), arrs[0], arrs[1], arrs[2], arrs[3], dil, n, lib_mod.ptr(y),
+                                          B, T, Cc, k, out_scale, acc, stream_ptr()))
+    torch.cuda.synchronize()
+    return y.transpose(1, 2).contiguous()
+
+
 def report(line):
     """Print a measurement and, on the GPU box, also append it to gpurun_out/parity_report.txt."""
     print(line)
