@@ -205,6 +205,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
           ra.x = src; ra.y = dst; ra.T = (int)T; ra.C = l0.Cin; ra.k = l0.k; ra.npairs = per;
           ra.t32 = 1; ra.bstride = t32_rows(T) * l0.Cin;
           ra.slope = slope; ra.out_scale = last ? inv : 1.0f; ra.accumulate = last && j > 0;
+          ra.split_h = l0.Cin <= 32;  // the c1 -> c2 intermediate as hi + lo bf16 planes (see finalize_bf16)
           for (int q = 0; q < per; ++q) {
             const Layer& c1 = g->layer(p + ".convs1." + std::to_string(m0 + q));
             const Layer& c2 = g->layer(p + ".convs2." + std::to_string(m0 + q));

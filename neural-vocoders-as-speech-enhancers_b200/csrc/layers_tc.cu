@@ -97,6 +97,8 @@ extern "C" int nvse_resblock1_bf16(const float* x, const float* const* w1, const
   // timing experiments only (tools/rb_bench.py): read x / y as T32 buffers; needs T % 32 == 0
   static const bool bench_t32 = std::getenv("NVSE_RB_T32") != nullptr;
   a.t32 = bench_t32 && (T % 32 == 0);
+  static const bool bench_split = std::getenv("NVSE_RB_SPLIT") != nullptr;  // experiments: hi + lo intermediate at C = 32
+  a.split_h = bench_split && C == 32;
   for (int m = 0; m < npairs; ++m) {
     NVSE_REQUIRE(w1[m] && w2[m] && b1[m] && b2[m], NVSE_ERR_INVALID, "nvse_resblock1_bf16: null tensor in pair %d", m);
     __nv_bfloat16* i1 = (__nv_bfloat16*)img.p + (size_t)(2 * m) * wn;

@@ -49,6 +49,7 @@ struct RbKernelArgs {
   int P;         // zero rows on each side of the operand buffer (largest conv padding)
   int rows_pad;  // operand buffer rows per 8-channel chunk (P + R + P)
   int stages, kc;
+  int sm_count;
   long long* trace;  // debug: clock64 stamps of one CTA's phase boundaries (NVSE_RB_TRACE), else null
 };
 
@@ -58,29 +59,31 @@ __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity) {
   return __all_sync(0xffffffffu, ok);
 }
 
-// 16 activated values of one row -> two 16-byte core-matrix rows of the operand buffer
-__device__ __forceinline__ void store_operand(uint8_t* op, int rows_pad, int brow, int c0, const float (&f)[16], float slope,
-                                              bool keep) {
-  uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-  if (keep) {
-    v0.x = pack_bf16(lrelu(f[0], slope), lrelu(f[1], slope));
-    v0.y = pack_bf16(lrelu(f[2], slope), lrelu(f[3], slope));
-    v0.z = pack_bf16(lrelu(f[4], slope), lrelu(f[5], slope));
-    v0.w = pack_bf16(lrelu(f[6], slope), lrelu(f[7], slope));
-    v1.x = pack_bf16(lrelu(f[8], slope), lrelu(f[9], slope));
-    v1.y = pack_bf16(lrelu(f[10], slope), lrelu(f[11], slope));
-    v1.z = pack_bf16(lrelu(f[12], slope), lrelu(f[13], slope));
-    v1.w = pack_bf16(lrelu(f[14], slope), lrelu(f[15], slope));
+// 16 activated values of one row -> two 16-byte core-matrix rows of the operand buffer; with LO also the
+// bf16-rounded residual of the first rounding into the second plane (hi + lo carries ~16 mantissa bits)
+template <bool LO>
+__device__ __forceinline__ void store_operand(uint8_t* op, uint32_t lo_plane, int rows_pad, int brow, int c0, const float (&f)[16],
+                                              float slope, bool keep) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a0 = keep ? lrelu(f[2 * i], slope) : 0.f, a1 = keep ? lrelu(f[2 * i + 1], slope) : 0.f;
+    hi[i] = pack_bf16(a0, a1);
+    if (LO) lo[i] = pack_bf16(a0 - bf16_lo(hi[i]), a1 - bf16_hi(hi[i]));
   }
-  const int chunk = c0 >> 3;
-  *reinterpret_cast<uint4*>(op + ((size_t)chunk * rows_pad + brow) * 16) = v0;
-  *reinterpret_cast<uint4*>(op + ((size_t)(chunk + 1) * rows_pad + brow) * 16) = v1;
+  const size_t o0 = ((size_t)(c0 >> 3) * rows_pad + brow) * 16, o1 = o0 + (size_t)rows_pad * 16;
+  *reinterpret_cast<uint4*>(op + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(op + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (LO) {
+    *reinterpret_cast<uint4*>(op + lo_plane + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(op + lo_plane + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
 }
 
 // C and the tile count are compile-time: the MMA issue loop must unroll completely -- a tcgen05.mma issued
 // from a loop with run-time trip counts costs 60-200 cycles of issue (tools/probe/mma_probe3.cu), more
 // than the MMA itself takes on the tensor core.
-template <int C, int NT>
+template <int C, int NT, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resblock_tc_kernel(const __grid_constant__ RbKernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const ResblockTcArgs& a = k.a;
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   const int t_in0 = (int)blockIdx.x * k.V - k.halo;  // time index of tile row 0
   const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
   constexpr uint32_t stage_bytes = (uint32_t)KC * C * 2u;
-  uint8_t* op = smem_raw;
-  uint8_t* wst = smem_raw + op_bytes;
+  uint8_t* op = smem_raw;  // hi plane, then (SPLIT) the lo plane of the c1 -> c2 intermediate
+  uint8_t* wst = smem_raw + (SPLIT ? 2u : 1u) * op_bytes;
   float* bsm = reinterpret_cast<float*>(wst + (size_t)k.stages * stage_bytes);  // b1[m][C] then cb[m][C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 2 * kRbMaxPairs * C);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
@@ -195,8 +198,10 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
 #pragma unroll
               for (int kk = 0; kk < kkn; ++kk) {
 #pragma unroll
-                for (int j = 0; j < n; ++j)
+                for (int j = 0; j < n; ++j) {
                   tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, acc);
+                  if (SPLIT && half) tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (op_bytes >> 4) + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, 1u);
+                }
                 acc = 1u;
                 a_lo += 2u * (uint32_t)k.rows_pad;
                 b_lo += 2u * (uint32_t)C;
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
 #pragma unroll
         for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
         tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
-        store_operand(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+        store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
       }
     }
     tmem_st_wait();
@@ -268,6 +273,25 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_op);
     RB_WSTAMP();
+    // While the tensor core works on the first conv: pull the x tile of the CTA that will be scheduled one
+    // wave from now into L2 (blocks are dispatched in linear order), so that its load phase hits L2.
+    if (a.t32) {
+      const unsigned resident = (unsigned)k.sm_count * ((2 * NT * C <= 256) ? 2u : 1u);
+      const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + resident;
+      const unsigned nb = lin / gridDim.x, nx = lin - nb * gridDim.x;
+      if (nb < gridDim.y && (lane & 7) == 0) {
+        const int nt0 = (int)nx * k.V - k.halo;
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+          const int c0 = ((i % CPW) * 2 + h) * 16, t = nt0 + (i / CPW) * kTileM + q * 32 + lane;
+          if (t >= 0 && t < a.T) {
+            const float* src = a.x + (int64_t)nb * bstride + t32_off(t, c0, C);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + w * 128));
+          }
+        }
+      }
+    }
 
     for (int m = 0; m < npairs; ++m) {
       // epi1: OP = bf16(lrelu(ACC + b1_m)), zero outside the sequence
@@ -292,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
             f[4 * u + 2] = __uint_as_float(v[4 * u + 2]) + bq.z;
             f[4 * u + 3] = __uint_as_float(v[4 * u + 3]) + bq.w;
           }
-          store_operand(op, k.rows_pad, k.P + r, c0, f, slope, inb);
+          store_operand<SPLIT>(op, op_bytes, k.rows_pad, k.P + r, c0, f, slope, inb);
         }
       }
       fence_proxy_async_smem();
@@ -324,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
               f[4 * u + 2] = __uint_as_float(v[4 * u + 2]) + bq.z;
               f[4 * u + 3] = __uint_as_float(v[4 * u + 3]) + bq.w;
             }
-            store_operand(op, k.rows_pad, k.P + r, c0, f, slope, inb);
+            store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, inb);
           }
         }
         fence_proxy_async_smem();
@@ -388,7 +412,8 @@ struct RbPlan {
 };
 
 // ntile: as many 128-row tiles as tensor memory (X + ACC = 2 * ntile * C columns <= 512) and shared memory allow
-bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
+bool make_plan(int C, int k, const int* dil, int npairs, bool split, RbPlan* p) {
+  if (split && C != 32) return false;
   if (!(C == 32 || C == 64 || C == 128 || C == 256)) return false;
   if (k < 1 || !(k & 1) || k > kMaxTaps || npairs < 1 || npairs > kRbMaxPairs) return false;
   int halo = 0, P = (k - 1) / 2;
@@ -407,7 +432,7 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
   for (; ntile >= min_tile; ntile >>= 1) {
     const int R = kTileM * ntile;
     const int rows_pad = R + 2 * P;
-    const size_t opb = ((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127;
+    const size_t opb = (split ? 2 : 1) * (((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127);
     if (R - 2 * halo < 32) return false;  // not enough useful rows per tile: per-layer kernels do better
     if (opb + 2 * stage_bytes + tail > kSmemBudget) continue;
     int stages = (int)std::min<size_t>((kSmemBudget - opb - tail) / stage_bytes, (size_t)kMaxStages);
@@ -438,14 +463,14 @@ static long long* trace_buffer() {
 
 bool rb_supported(int C, int k, const int* dil, int npairs) {
   RbPlan p;
-  return make_plan(C, k, dil, npairs, &p);
+  return make_plan(C, k, dil, npairs, false, &p);
 }
 
 // Per-CTA cycle model fitted to the phase traces of tools/rb_trace.py (profiles/): load + final phases,
 // 2 * npairs MMA phases at the tensor-core/shared-memory floor, 2 * npairs - 1 epilogues.
 double rb_cost_per_row(int C, int k, const int* dil, int npairs) {
   RbPlan p;
-  if (!make_plan(C, k, dil, npairs, &p)) return -1.0;
+  if (!make_plan(C, k, dil, npairs, false, &p)) return -1.0;
   const double mma = std::max(C / 2.0, 32.0 + C / 4.0) * 1.12;
   const double conv = (double)p.ntile * k * (C / 16) * mma;
   const double epi = 600.0 + 7.5 * p.ntile * C;
@@ -459,23 +484,26 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   int dil[kRbMaxPairs] = {1, 1, 1};
   for (int m = 0; m < a.npairs && m < kRbMaxPairs; ++m) dil[m] = a.pair[m].dil;
   RbPlan p;
-  NVSE_REQUIRE(make_plan(a.C, a.k, dil, a.npairs, &p), NVSE_ERR_UNSUPPORTED, "fused resblock: C=%d k=%d unsupported", a.C, a.k);
+  NVSE_REQUIRE(make_plan(a.C, a.k, dil, a.npairs, a.split_h != 0, &p), NVSE_ERR_UNSUPPORTED, "fused resblock: C=%d k=%d unsupported", a.C, a.k);
   RbKernelArgs k;
   k.a = a;
   if (k.a.bstride == 0) k.a.bstride = (a.t32 ? t32_rows(a.T) : (int64_t)a.T) * a.C;
   k.trace = nullptr;
   k.trace = trace_buffer();
+  static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+  k.sm_count = sm_count;
   k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
   dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
   const double rows = (double)B * a.T;
   ProfScope prof("resblock_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0 * a.npairs,
                  rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
-#define RB_LAUNCH(CC, NN)                                                                                                   \
-  if (a.C == CC && p.ntile == NN) {                                                                                         \
-    NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_tc_kernel<CC, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
-    resblock_tc_kernel<CC, NN><<<grid, kThreads, p.smem, st>>>(k);                                                          \
+#define RB_LAUNCH(CC, NN, SP)                                                                                               \
+  if (a.C == CC && p.ntile == NN && (a.split_h != 0) == SP) {                                                               \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_tc_kernel<CC, NN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    resblock_tc_kernel<CC, NN, SP><<<grid, kThreads, p.smem, st>>>(k);                                                      \
   } else
-  RB_LAUNCH(32, 4) RB_LAUNCH(32, 8) RB_LAUNCH(64, 4) RB_LAUNCH(64, 2) RB_LAUNCH(128, 2) RB_LAUNCH(128, 1) RB_LAUNCH(256, 1)
+  RB_LAUNCH(32, 4, false) RB_LAUNCH(32, 4, true) RB_LAUNCH(32, 8, false) RB_LAUNCH(32, 8, true) RB_LAUNCH(64, 4, false)
+  RB_LAUNCH(64, 2, false) RB_LAUNCH(128, 2, false) RB_LAUNCH(128, 1, false) RB_LAUNCH(256, 1, false)
   return fail(NVSE_ERR_UNSUPPORTED, "fused resblock: no kernel for C=%d with %d tiles", a.C, p.ntile);
 #undef RB_LAUNCH
   NVSE_LAUNCH_CHECK("resblock_tc_kernel");

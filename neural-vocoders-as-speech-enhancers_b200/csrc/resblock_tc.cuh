@@ -28,6 +28,8 @@ struct ResblockTcArgs {
   float slope;       // leaky_relu slope in front of every conv (LRELU_SLOPE, hifigan.py:7)
   float out_scale;
   int accumulate;
+  int split_h;       // feed c2 its input as hi + lo bf16 planes (two MMAs per step): where the rounding of the
+                     // c1 -> c2 intermediate costs the most SNR (tools/bf16_budget.py); C = 32 only
 };
 
 // true when the fused kernel handles this shape (otherwise the caller uses the per-layer kernels)
