@@ -185,6 +185,58 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// conv_post of the tensor-core path (HiFi-GAN: Cin -> 1 channel, hifigan.py:120-122): the input is the
+// T32-layout MRF output.  Memory-bound: one pass over x with fully coalesced 16-byte loads into a
+// padded shared tile (row pitch Cin + 4 floats: conflict-free 128-bit stores and loads with one thread
+// per row), then one output sample per thread.
+// ------------------------------------------------------------------------------------------
+constexpr int POST_ROWS = 256;
+
+__global__ void __launch_bounds__(POST_ROWS) conv_post1_t32_kernel(const ConvF32Args a, int min_off, int span) {
+  extern __shared__ __align__(16) float sm[];
+  const int pitch = a.Cin + 4, c4n = a.Cin >> 2, nrows = POST_ROWS + span;
+  float* xs = sm;                   // [nrows][pitch]
+  float* ws = sm + nrows * pitch;   // [ntaps][Cin]
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.y;
+  const int t0 = blockIdx.x * POST_ROWS;
+  const float* __restrict__ xb = a.x + b * a.x_bstride;
+  for (int e = tid; e < a.taps.ntaps * a.Cin; e += POST_ROWS) {
+    const int tap = e / a.Cin, c = e - tap * a.Cin;
+    ws[e] = a.w[(int64_t)a.taps.widx[tap] * a.Cin + c];
+  }
+  for (int c4 = 0; c4 < c4n; ++c4)
+    for (int r = tid; r < nrows; r += POST_ROWS) {
+      const int t = t0 + min_off + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= 0 && t < a.Tin) {
+        v = __ldg(reinterpret_cast<const float4*>(xb + t32_off(t, 4 * c4, a.Cin)));
+        v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope); v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope);
+      }
+      *reinterpret_cast<float4*>(xs + r * pitch + 4 * c4) = v;
+    }
+  __syncthreads();
+  const int t = t0 + tid;
+  if (t >= a.Trows) return;
+  float acc = a.bias ? a.bias[0] : 0.0f;
+  for (int tap = 0; tap < a.taps.ntaps; ++tap) {
+    const float4* xr = reinterpret_cast<const float4*>(xs + (tid + a.taps.off[tap] - min_off) * pitch);
+    const float4* wr = reinterpret_cast<const float4*>(ws + tap * a.Cin);
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll 8
+    for (int c4 = 0; c4 < c4n; ++c4) {
+      const float4 xv = xr[c4], wv = wr[c4];
+      p0 = fmaf(xv.x, wv.x, p0); p1 = fmaf(xv.y, wv.y, p1); p2 = fmaf(xv.z, wv.z, p2); p3 = fmaf(xv.w, wv.w, p3);
+    }
+    acc += (p0 + p1) + (p2 + p3);
+  }
+  acc *= a.out_scale;
+  float* yr = a.y + b * a.y_bstride + t;
+  if (a.accumulate) acc += *yr;
+  *yr = a.out_act == 1 ? tanhf(acc) : acc;
+}
+
 // [Cout, Cin, k] (Conv1d) or [Cin, Cout, k] (ConvTranspose1d) -> [k][Cin][Cout]
 __global__ void __launch_bounds__(256) repack_weight_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                              int Cin, int Cout, int k, int transposed) {
@@ -234,6 +286,14 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
     NVSE_REQUIRE(a.Cout <= 32, NVSE_ERR_UNSUPPORTED, "thin conv: Cout=%d > 32", a.Cout);
     NVSE_REQUIRE(max_off - min_off <= THIN_MAX_SPAN, NVSE_ERR_UNSUPPORTED, "thin conv: tap span %d too wide", max_off - min_off);
     const int span = max_off - min_off;
+    if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && a.out_mul == 1 && a.out_add == 0 && a.Cin <= 128) {
+      const size_t smem = sizeof(float) * ((size_t)(POST_ROWS + span) * (a.Cin + 4) + (size_t)a.taps.ntaps * a.Cin);
+      NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_post1_t32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((unsigned)((a.Trows + POST_ROWS - 1) / POST_ROWS), (unsigned)B);
+      conv_post1_t32_kernel<<<grid, POST_ROWS, smem, st>>>(a, min_off, span);
+      NVSE_LAUNCH_CHECK("conv_post1_t32_kernel");
+      return NVSE_OK;
+    }
     if (a.Cout == 1) return launch_thin<1>(a, B, min_off, span, st);
     if (a.Cout <= 4) return launch_thin<4>(a, B, min_off, span, st);
     if (a.Cout <= 8) return launch_thin<8>(a, B, min_off, span, st);

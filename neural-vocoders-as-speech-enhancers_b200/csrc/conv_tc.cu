@@ -51,18 +51,22 @@ struct KernelArgs {
 
 constexpr int kStageUnroll = 4;  // independent 32-byte loads in flight per thread while staging
 
+// KK (16-channel MMA steps per weight stage), the tile count and the split flag are compile-time so that the
+// MMA issue loop unrolls completely (an MMA issued from a loop with run-time trip counts costs more issue
+// cycles than the tensor core needs to execute it: tools/probe/mma_probe3.cu).
+template <int KK, int NT, bool SPLIT>
 __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ KernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const ConvTcArgs& a = k.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t b = blockIdx.y;
-  const int ntile = k.ntile;
+  constexpr int ntile = NT;
   const int t0 = blockIdx.x * kTileM * ntile;
   const int Cin = a.Cin, Cout = a.Cout;
   const int nchunk = Cin >> 3;
   const uint32_t act_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;  // one bf16 plane
   const uint32_t stage_bytes = (uint32_t)k.kc * Cout * 2u;
-  const int split = a.split_act;  // activations as hi + lo bf16 planes (two MMAs per K step)
+  constexpr bool split = SPLIT;  // activations as hi + lo bf16 planes (two MMAs per K step)
   uint8_t* act = smem_raw;
   uint8_t* wst = smem_raw + (split ? 2u : 1u) * act_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)k.stages * stage_bytes);
@@ -196,46 +200,50 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
       }
     }
   } else if (warp == kEpiWarps + 1) {
-    // ===== MMA issuer: a single thread drives the tensor core =====
-    if (lane == 0) {
+    // ===== MMA issuer: one elected thread, a few instructions between consecutive MMAs =====
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t act_base = smem_u32(act);
-      const uint32_t a_lbo = (uint32_t)k.rows_pad * 16u, b_lbo = (uint32_t)Cout * 16u, sbo = 128u;
-      int it = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(act), (uint32_t)k.rows_pad * 16u);  // advances in rows (16-byte units)
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(wst), (uint32_t)Cout * 16u);
+      const uint32_t hi = umma_desc_hi(128u);
+      const uint32_t stage_units = stage_bytes >> 4, nstage = (uint32_t)k.stages, lo_plane = act_bytes >> 4;
+      const uint32_t kc_rows = (uint32_t)(KK * 2) * (uint32_t)k.rows_pad;
+      uint32_t s = 0, par = 0;
       for (int ph = 0; ph < k.nphase; ++ph) {
         const ConvTaps& tp = k.ptaps[ph];
         const int buf = ph & 1;
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ntile * Cout);
         if (ph >= 2) {  // the epilogue must have drained this accumulator (phase ph - 2)
-          if (!mbar_wait(bar_tfree + 8 * buf, ((ph >> 1) - 1) & 1)) goto done;
+          if (!mbar_wait(bar_tfree + 8 * buf, ((ph >> 1) - 1) & 1)) goto mma_exit;
           tc_fence_after();
         }
-        bool first = true;
+        uint32_t acc = 0u;
         for (int tap = 0; tap < tp.ntaps; ++tap) {
-          const uint32_t row_shift = (uint32_t)(tp.off[tap] - k.min_off);
-          for (int kc = 0; kc < nkc; ++kc, ++it) {
-            const int s = it % k.stages;
-            const uint32_t par = (it / k.stages) & 1;
-            if (!mbar_wait(bar_full + 8 * s, par)) goto done;
+          uint32_t a_kc = a_lo0 + (uint32_t)(tp.off[tap] - k.min_off);
+          for (int kc = 0; kc < nkc; ++kc, a_kc += kc_rows) {
+            if (!mbar_wait(bar_full + 8 * s, par)) goto mma_exit;
             tc_fence_after();
-            const uint32_t w_base = smem_u32(wst + (size_t)s * stage_bytes);
-            for (int kk = 0; kk < k.kc / 16; ++kk) {
-              const uint32_t a_addr = act_base + ((uint32_t)(kc * (k.kc / 8) + 2 * kk) * k.rows_pad + row_shift) * 16u;
-              const uint32_t b_addr = w_base + (uint32_t)(2 * kk) * b_lbo;
-              const uint64_t bd = umma_desc(b_addr, b_lbo, sbo);
-              for (int j = 0; j < ntile; ++j) {  // the same weight stage feeds every M tile of this CTA
-                const uint32_t aj = a_addr + (uint32_t)j * (kTileM * 16u);
-                tc_mma_bf16(d_tmem + (uint32_t)(j * Cout), umma_desc(aj, a_lbo, sbo), bd, idesc, first ? 0u : 1u);
-                if (split) tc_mma_bf16(d_tmem + (uint32_t)(j * Cout), umma_desc(aj + act_bytes, a_lbo, sbo), bd, idesc, 1u);
+            uint32_t a_lo = a_kc, b_lo = b_lo0 + s * stage_units;
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+#pragma unroll
+              for (int j = 0; j < NT; ++j) {  // the same weight stage feeds every M tile of this CTA
+                tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * Cout), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, acc);
+                if (SPLIT) tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * Cout), a_lo + lo_plane + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, 1u);
               }
-              first = false;
+              acc = 1u;
+              a_lo += 2u * (uint32_t)k.rows_pad;
+              b_lo += 2u * (uint32_t)Cout;
             }
             tc_commit(bar_empty + 8 * s);  // stage reusable once these MMAs have read it
+            if (++s == nstage) { s = 0; par ^= 1u; }
           }
         }
         tc_commit(bar_accum + 8 * buf);  // accumulator of this phase complete -> epilogue
       }
+    mma_exit:;
     }
+    __syncwarp();
   } else {
     // ===== epilogue warps: TMEM -> registers -> global =====
     const int quarter = warp & 3, chalf = warp >> 2;  // TMEM lane quarter; which 16-column chunks (even / odd)
@@ -405,14 +413,22 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   while (stages > 2 && act_bytes + stages * stage_bytes + tail > 56 * 1024) --stages;
   k.stages = stages;
   const size_t smem = act_bytes + stages * stage_bytes + tail;
-  NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
   dim3 grid((unsigned)((a.Trows + kTileM * ntile - 1) / (kTileM * ntile)), (unsigned)B);
   const double rows = (double)B * a.Trows;
   ProfScope prof("conv_tc", a.Cin, a.Cout, 2.0 * rows * a.Cin * a.Cout * total_taps,
                  rows * (a.Cin * (a.in_bf16 ? 2.0 : 4.0) +
                          nphase * (a.Cout * (a.out_bf16 ? 2.0 : 4.0) * (a.accumulate ? 2.0 : 1.0) + (a.residual ? 4.0 * a.Cout : 0.0))),
                  st);
-  conv_tc_kernel<<<grid, kThreads, smem, st>>>(k);
+  const bool sp = a.split_act != 0;
+#define TC_LAUNCH(KKV, NTV, SPV)                                                                                          \
+  if (k.kc == 16 * KKV && ntile == NTV && sp == SPV) {                                                                    \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<KKV, NTV, SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
+    conv_tc_kernel<KKV, NTV, SPV><<<grid, kThreads, smem, st>>>(k);                                                       \
+  } else
+  TC_LAUNCH(2, 1, false) TC_LAUNCH(2, 2, false) TC_LAUNCH(2, 4, false) TC_LAUNCH(4, 1, false) TC_LAUNCH(4, 2, false) TC_LAUNCH(4, 4, false)
+  TC_LAUNCH(2, 1, true) TC_LAUNCH(2, 2, true) TC_LAUNCH(2, 4, true) TC_LAUNCH(4, 1, true) TC_LAUNCH(4, 2, true) TC_LAUNCH(4, 4, true)
+  return fail(NVSE_ERR_UNSUPPORTED, "tensor-core conv: no kernel for kc=%d ntile=%d", k.kc, ntile);
+#undef TC_LAUNCH
   NVSE_LAUNCH_CHECK("conv_tc_kernel");
   return NVSE_OK;
 }
