@@ -61,7 +61,7 @@ struct ProfScope {
 __host__ __device__ inline int64_t t32_off(int64_t t, int c, int C) {
   return ((t >> 5) * (C >> 2) + (c >> 2)) * 128 + (t & 31) * 4 + (c & 3);
 }
-inline int64_t t32_rows(int64_t T) { return (T + 31) / 32 * 32; }
+__host__ __device__ inline int64_t t32_rows(int64_t T) { return (T + 31) / 32 * 32; }
 
 constexpr int kMaxTaps = 16;
 

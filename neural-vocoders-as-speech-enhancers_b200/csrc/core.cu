@@ -1,6 +1,7 @@
 // Error plumbing, launch accounting and the small layout / weight-norm kernels.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -119,6 +120,29 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 }
 
 }  // namespace
+
+namespace {
+// channels-last [B, T, C] <-> T32 (common.cuh); element-wise gather, used by tests / the layer-level entry points
+__global__ void __launch_bounds__(256) relayout_t32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int C,
+                                                           int to_t32) {
+  const int64_t b = blockIdx.y, n = T * C, tstride = t32_rows(T) * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = e / C;
+    const int c = (int)(e - t * C);
+    if (to_t32) y[b * tstride + t32_off(t, c, C)] = x[b * n + e];
+    else y[b * n + e] = x[b * tstride + t32_off(t, c, C)];
+  }
+}
+}  // namespace
+
+int launch_relayout_t32(const float* x, float* y, int64_t B, int64_t T, int C, bool to_t32, cudaStream_t st) {
+  if (B == 0 || T == 0) return NVSE_OK;
+  NVSE_REQUIRE(B <= 65535 && C % 4 == 0, NVSE_ERR_INVALID, "relayout: bad shape");
+  dim3 grid((unsigned)std::min<int64_t>((T * C + 255) / 256, 8192), (unsigned)B);
+  relayout_t32_kernel<<<grid, 256, 0, st>>>(x, y, T, C, to_t32 ? 1 : 0);
+  NVSE_LAUNCH_CHECK("relayout_t32_kernel");
+  return NVSE_OK;
+}
 
 int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st) {
   if (B == 0 || R == 0 || C == 0) return NVSE_OK;

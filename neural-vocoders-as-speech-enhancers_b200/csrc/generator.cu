@@ -212,7 +212,12 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
             ra.pair[q] = RbPair{reinterpret_cast<const __nv_bfloat16*>(c1.w_bf16), reinterpret_cast<const __nv_bfloat16*>(c2.w_bf16),
                                 c1.bias, c2.bias, c1.dilation};
           }
-          if (int rc = launch_resblock_tc(ra, B, st)) return rc;
+          static const bool pairpipe = [] { const char* e = std::getenv("NVSE_PAIRPIPE"); return !(e && e[0] == '0'); }();
+          if (pairpipe && per == 1 && !ra.split_h && pair_supported(ra.C, ra.k, ra.pair[0].dil)) {
+            if (int rc = launch_pair_tc(ra, B, st)) return rc;
+          } else if (int rc = launch_resblock_tc(ra, B, st)) {
+            return rc;
+          }
           src = dst;
         }
         continue;

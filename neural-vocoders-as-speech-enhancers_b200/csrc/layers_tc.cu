@@ -94,11 +94,27 @@ extern "C" int nvse_resblock1_bf16(const float* x, const float* const* w1, const
   ResblockTcArgs a{};
   a.x = x; a.y = y; a.T = (int)T; a.C = C; a.k = k; a.npairs = npairs;
   a.slope = 0.1f; a.out_scale = out_scale; a.accumulate = accumulate;
-  // timing experiments only (tools/rb_bench.py): read x / y as T32 buffers; needs T % 32 == 0
-  static const bool bench_t32 = std::getenv("NVSE_RB_T32") != nullptr;
-  a.t32 = bench_t32 && (T % 32 == 0);
+  // NVSE_RB_T32 (timing, tools/rb_bench.py): treat x / y as T32 buffers as they are (needs T % 32 == 0).
+  // NVSE_RB_LAYER_T32 (tests): convert x (and y when accumulating) to T32 scratch copies, run the T32
+  // kernels the generator runs -- including the pipelined pair kernel where it applies -- and convert back.
+  const bool bench_t32 = std::getenv("NVSE_RB_T32") != nullptr && (T % 32 == 0);
+  const bool layer_t32 = !bench_t32 && std::getenv("NVSE_RB_LAYER_T32") != nullptr;
+  const char* pp = std::getenv("NVSE_PAIRPIPE");
+  const bool pairpipe = !(pp && pp[0] == '0');
+  a.t32 = bench_t32 || layer_t32;
   static const bool bench_split = std::getenv("NVSE_RB_SPLIT") != nullptr;  // experiments: hi + lo intermediate at C = 32
   a.split_h = bench_split && C == 32;
+  Scratch xt(st), yt(st);
+  if (layer_t32) {
+    const size_t bytes = sizeof(float) * (size_t)B * t32_rows(T) * C;
+    NVSE_CUDA_CHECK(xt.alloc(bytes));
+    NVSE_CUDA_CHECK(yt.alloc(bytes));
+    if (int rc = launch_relayout_t32(x, (float*)xt.p, B, T, C, true, st)) return rc;
+    if (accumulate)
+      if (int rc = launch_relayout_t32(y, (float*)yt.p, B, T, C, true, st)) return rc;
+    a.x = (const float*)xt.p;
+    a.y = (float*)yt.p;
+  }
   for (int m = 0; m < npairs; ++m) {
     NVSE_REQUIRE(w1[m] && w2[m] && b1[m] && b2[m], NVSE_ERR_INVALID, "nvse_resblock1_bf16: null tensor in pair %d", m);
     __nv_bfloat16* i1 = (__nv_bfloat16*)img.p + (size_t)(2 * m) * wn;
@@ -109,7 +125,12 @@ extern "C" int nvse_resblock1_bf16(const float* x, const float* const* w1, const
     if (int rc = launch_pack_weight_tc((const float*)wk.p, i2, C, C, k, st)) return rc;
     a.pair[m] = RbPair{i1, i2, b1[m], b2[m], dilations[m]};
   }
-  return launch_resblock_tc(a, B, st);
+  int rc;
+  if (a.t32 && pairpipe && npairs == 1 && !a.split_h && pair_supported(C, k, dilations[0])) rc = launch_pair_tc(a, B, st);
+  else rc = launch_resblock_tc(a, B, st);
+  if (rc) return rc;
+  if (layer_t32) return launch_relayout_t32((const float*)yt.p, y, B, T, C, false, st);
+  return NVSE_OK;
 }
 
 extern "C" int nvse_tc_abort_status(int reset, int* flag) {
@@ -117,6 +138,8 @@ extern "C" int nvse_tc_abort_status(int reset, int* flag) {
   unsigned int v = 0, v2 = 0;
   if (int rc = tc_abort_status(reset != 0, &v)) return rc;
   if (int rc = rb_abort_status(reset != 0, &v2)) return rc;
-  *flag = (int)(v | v2);
+  unsigned int v3 = 0;
+  if (int rc = pair_abort_status(reset != 0, &v3)) return rc;
+  *flag = (int)(v | v2 | v3);
   return NVSE_OK;
 }

@@ -299,24 +299,27 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
       tc_fence_after();
       RB_WSTAMP();
       const float* b1 = bsm + m * C;
-      for (int j = 0; j < n; ++j) {
-        const int r = j * kTileM + q * 32 + lane;
-        const int t = t_in0 + r;
-        const bool inb = t >= 0 && t < a.T;
-        for (int c0 = h * 16; c0 < C; c0 += 32) {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem_acc + lane_sel + (uint32_t)(j * C + c0), v);
+      {
+        // TMEM loads run one item ahead of the conversion (tcgen05.wait::ld covers every load in flight)
+        uint32_t v[2][16];
+        tmem_ld_32x16(tmem_acc + lane_sel + (uint32_t)(h * 16), v[0]);
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+          const int c0 = ((i % CPW) * 2 + h) * 16, jt = i / CPW;
+          const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
           tmem_ld_wait();
+          if (i + 1 < IT)
+            tmem_ld_32x16(tmem_acc + lane_sel + (uint32_t)(((i + 1) / CPW) * C + (((i + 1) % CPW) * 2 + h) * 16), v[(i + 1) & 1]);
           float f[16];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float4 bq = *reinterpret_cast<const float4*>(b1 + c0 + 4 * u);
-            f[4 * u] = __uint_as_float(v[4 * u]) + bq.x;
-            f[4 * u + 1] = __uint_as_float(v[4 * u + 1]) + bq.y;
-            f[4 * u + 2] = __uint_as_float(v[4 * u + 2]) + bq.z;
-            f[4 * u + 3] = __uint_as_float(v[4 * u + 3]) + bq.w;
+            f[4 * u] = __uint_as_float(v[i & 1][4 * u]) + bq.x;
+            f[4 * u + 1] = __uint_as_float(v[i & 1][4 * u + 1]) + bq.y;
+            f[4 * u + 2] = __uint_as_float(v[i & 1][4 * u + 2]) + bq.z;
+            f[4 * u + 3] = __uint_as_float(v[i & 1][4 * u + 3]) + bq.w;
           }
-          store_operand<SPLIT>(op, op_bytes, k.rows_pad, k.P + r, c0, f, slope, inb);
+          store_operand<SPLIT>(op, op_bytes, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
         }
       }
       fence_proxy_async_smem();
@@ -331,24 +334,26 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
       const float* cb = bsm + (kRbMaxPairs + m) * C;
       if (m + 1 < npairs) {
         // epi2: OP = bf16(lrelu(X + cb_m)): the input of the next pair
-        for (int j = 0; j < n; ++j) {
-          const int r = j * kTileM + q * 32 + lane;
-          const int t = t_in0 + r;
-          const bool inb = t >= 0 && t < a.T;
-          for (int c0 = h * 16; c0 < C; c0 += 32) {
-            uint32_t v[16];
-            tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(j * C + c0), v);
+        {
+          uint32_t v[2][16];
+          tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(h * 16), v[0]);
+#pragma unroll
+          for (int i = 0; i < IT; ++i) {
+            const int c0 = ((i % CPW) * 2 + h) * 16, jt = i / CPW;
+            const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
             tmem_ld_wait();
+            if (i + 1 < IT)
+              tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(((i + 1) / CPW) * C + (((i + 1) % CPW) * 2 + h) * 16), v[(i + 1) & 1]);
             float f[16];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 bq = *reinterpret_cast<const float4*>(cb + c0 + 4 * u);
-              f[4 * u] = __uint_as_float(v[4 * u]) + bq.x;
-              f[4 * u + 1] = __uint_as_float(v[4 * u + 1]) + bq.y;
-              f[4 * u + 2] = __uint_as_float(v[4 * u + 2]) + bq.z;
-              f[4 * u + 3] = __uint_as_float(v[4 * u + 3]) + bq.w;
+              f[4 * u] = __uint_as_float(v[i & 1][4 * u]) + bq.x;
+              f[4 * u + 1] = __uint_as_float(v[i & 1][4 * u + 1]) + bq.y;
+              f[4 * u + 2] = __uint_as_float(v[i & 1][4 * u + 2]) + bq.z;
+              f[4 * u + 3] = __uint_as_float(v[i & 1][4 * u + 3]) + bq.w;
             }
-            store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, inb);
+            store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
           }
         }
         fence_proxy_async_smem();
@@ -424,6 +429,9 @@ bool make_plan(int C, int k, const int* dil, int npairs, bool split, RbPlan* p) 
   }
   static const int forced = [] { const char* e = std::getenv("NVSE_RB_NTILE"); return e ? std::atoi(e) : 0; }();
   int ntile = std::min(C <= 64 ? 4 : 8, 256 / C);
+  // C = 128, whole k = 3 ResBlock: one tile per CTA lets two CTAs share an SM (TMEM 256 columns each), and
+  // the overlap of one CTA's load / final phases with the other's MMAs outweighs the larger halo share
+  if (C == 128 && npairs > 1 && k <= 3) ntile = 1;
   if (forced > 0) ntile = std::min(forced, 256 / C);
   const int kc = tc_kchunk(C);
   const size_t stage_bytes = (size_t)kc * C * 2;

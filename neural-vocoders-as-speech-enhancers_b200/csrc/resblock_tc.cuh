@@ -39,5 +39,11 @@ bool rb_supported(int C, int k, const int* dil, int npairs);
 double rb_cost_per_row(int C, int k, const int* dil, int npairs);
 int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st);
 int rb_abort_status(bool reset, unsigned int* flag);
+long long* rb_trace_buffer();  // debug stamps (NVSE_RB_TRACE), null when off
+
+// pair_tc.cu: persistent, software-pipelined single pair (C = 128), T32 layout only
+bool pair_supported(int C, int k, int dil);
+int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st);
+int pair_abort_status(bool reset, unsigned int* flag);
 
 }  // namespace nvse

@@ -190,6 +190,44 @@ def test_fused_resblock1_tensor_core_matches_torch_on_bf16_operands(C_, k, dils,
     assert torch.allclose(out2, y0 + out / 3, atol=1e-5, rtol=1e-5)
 
 
+RB_T32_CASES = [  # the T32-layout kernels the generator launches: pipelined pair kernel (C = 128) and the chain kernel
+    (128, 3, (1,), 1000, 2), (128, 7, (3,), 700, 1), (128, 11, (5,), 1500, 2), (128, 11, (1,), 255, 1), (128, 3, (5,), 31, 1),
+    (128, 7, (1,), 5000, 3), (128, 7, (3,), 55168, 2), (64, 7, (1, 3, 5), 1000, 1), (32, 11, (1, 3, 5), 900, 2), (256, 7, (3,), 300, 1),
+]
+
+
+@pytest.mark.parametrize("pairpipe", ["1", "0"])
+@pytest.mark.parametrize("C_,k,dils,T,B", RB_T32_CASES)
+def test_fused_resblock1_t32_layout_kernels(monkeypatch, C_, k, dils, T, B, pairpipe):
+    """Same reference as above, through the T32 activation layout (and, for single C = 128 pairs, the
+    persistent software-pipelined pair kernel): NVSE_RB_LAYER_T32 makes the layer entry convert to T32."""
+    if pairpipe == "0" and not (C_ == 128 and len(dils) == 1):
+        pytest.skip("only C = 128 single pairs have two kernels")
+    monkeypatch.setenv("NVSE_RB_LAYER_T32", "1")
+    monkeypatch.setenv("NVSE_PAIRPIPE", pairpipe)
+    n = len(dils)
+    x = _rand((B, C_, T), 141)
+    w1 = [_rand((C_, C_, k), 142 + m, 1.0 / np.sqrt(C_ * k)) for m in range(n)]
+    w2 = [_rand((C_, C_, k), 152 + m, 1.0 / np.sqrt(C_ * k)) for m in range(n)]
+    b1 = [_rand((C_,), 162 + m, 0.3) for m in range(n)]
+    b2 = [_rand((C_,), 172 + m, 0.3) for m in range(n)]
+    ref, ref32 = x, x
+    for m, d in enumerate(dils):
+        h = F.conv1d(_bf(F.leaky_relu(ref, 0.1)), _bf(w1[m]), b1[m], dilation=d, padding=(k - 1) * d // 2)
+        ref = F.conv1d(_bf(F.leaky_relu(h, 0.1)), _bf(w2[m]), b2[m], padding=(k - 1) // 2) + ref
+        h = F.conv1d(F.leaky_relu(ref32, 0.1), w1[m], b1[m], dilation=d, padding=(k - 1) * d // 2)
+        ref32 = F.conv1d(F.leaky_relu(h, 0.1), w2[m], b2[m], padding=(k - 1) // 2) + ref32
+    out = resblock1_cl(x, w1, b1, w2, b2, dils)
+    assert not lib_mod.tc_abort_status()
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs()
+    budget = float((ref - ref32).abs().mean())
+    assert float(err.max()) <= 2e-2 and float(err.mean()) <= 0.5 * budget + 1e-5, (float(err.max()), float(err.mean()), budget)
+    y0 = _rand((B, C_, T), 199)
+    out2 = resblock1_cl(x, w1, b1, w2, b2, dils, out_scale=1.0 / 3, y0_bct=y0)
+    assert torch.allclose(out2, y0 + out / 3, atol=1e-5, rtol=1e-5)
+
+
 @pytest.mark.parametrize("cin,cout,k,u,T,B", [(512, 256, 16, 8, 9, 2), (256, 128, 16, 8, 140, 1), (128, 64, 4, 2, 130, 2),
                                              (64, 32, 4, 2, 257, 1), (64, 32, 16, 8, 1, 1)])
 def test_conv_transpose1d_tensor_core_matches_torch_on_bf16_operands(cin, cout, k, u, T, B):

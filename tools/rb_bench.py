@@ -37,7 +37,7 @@ for _ in range(iters):
     run()
 torch.cuda.synchronize()
 for p in lib_mod.profile_end():
-    if p["kernel"].startswith("resblock_tc"):
+    if p["kernel"].startswith(("resblock_tc", "pair_tc")):
         ms = p["ms"] / p["launches"]
         print(f"C={Cc} k={k} T={T} B={B} pairs={npairs}: {ms:.3f} ms  {p['flops'] / p['launches'] / ms / 1e9:.0f} TFLOP/s (algorithmic)  "
               f"{p['bytes'] / p['launches'] / ms / 1e6:.0f} GB/s  aborted={lib_mod.tc_abort_status()}")
