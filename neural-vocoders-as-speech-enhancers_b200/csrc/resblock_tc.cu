@@ -50,6 +50,7 @@ struct RbKernelArgs {
   int rows_pad;  // operand buffer rows per 8-channel chunk (P + R + P)
   int stages, kc;
   int sm_count;
+  int dbg;  // experiments (NVSE_RB_DBG bitmask): 1 = the weight producer starts after the load phase
   long long* trace;  // debug: clock64 stamps of one CTA's phase boundaries (NVSE_RB_TRACE), else null
 };
 
@@ -149,13 +150,15 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     if (lane == 0) {
       const uint32_t nstage = (uint32_t)k.stages;
       uint32_t s = 0, ph = 1;
+      if ((k.dbg & 1) && !mbar_wait(bar_op, 0)) goto done;
       for (int m = 0; m < npairs; ++m)
         for (int half = 0; half < 2; ++half) {
           const __nv_bfloat16* wimg = half ? a.pair[m].w2 : a.pair[m].w1;
           for (int st = 0; st < a.k * nkc; ++st) {
             if (!mbar_wait(bar_empty + 8 * s, ph)) goto done;
-            mbar_arrive_expect_tx(bar_full + 8 * s, stage_bytes);
-            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (stage_bytes / 2), stage_bytes,
+            const uint32_t cp_bytes = (k.dbg & 2) ? stage_bytes / 4 : stage_bytes;  // dbg 2: timing experiment, wrong results
+            mbar_arrive_expect_tx(bar_full + 8 * s, cp_bytes);
+            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (stage_bytes / 2), cp_bytes,
                           bar_full + 8 * s);
             if (++s == nstage) { s = 0; ph ^= 1u; }
           }
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
         const bool inb = t >= 0 && t < a.T;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) v[u][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < 4; ++w) v[u][w] = (inb && !(k.dbg & 16)) ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -263,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         }
 #pragma unroll
         for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
-        tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
-        store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+        if (!(k.dbg & 4)) tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
+        if (!(k.dbg & 8)) store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
       }
     }
     tmem_st_wait();
@@ -432,6 +435,7 @@ bool make_plan(int C, int k, const int* dil, int npairs, bool split, RbPlan* p) 
   // C = 128, whole k = 3 ResBlock: one tile per CTA lets two CTAs share an SM (TMEM 256 columns each), and
   // the overlap of one CTA's load / final phases with the other's MMAs outweighs the larger halo share
   if (C == 128 && npairs > 1 && k <= 3) ntile = 1;
+  if (C == 64 && k <= 3) ntile = 2;  // same trade at C = 64: 1.37 -> 1.13 ms for the k = 3 ResBlock of stage 3
   if (forced > 0) ntile = std::min(forced, 256 / C);
   const int kc = tc_kchunk(C);
   const size_t stage_bytes = (size_t)kc * C * 2;
@@ -443,7 +447,12 @@ bool make_plan(int C, int k, const int* dil, int npairs, bool split, RbPlan* p) 
     const size_t opb = (split ? 2 : 1) * (((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127);
     if (R - 2 * halo < 32) return false;  // not enough useful rows per tile: per-layer kernels do better
     if (opb + 2 * stage_bytes + tail > kSmemBudget) continue;
-    int stages = (int)std::min<size_t>((kSmemBudget - opb - tail) / stage_bytes, (size_t)kMaxStages);
+    static const int max_stages = [] { const char* e = std::getenv("NVSE_RB_STAGES"); return e ? std::atoi(e) : kMaxStages; }();
+    int stages = (int)std::min<size_t>((kSmemBudget - opb - tail) / stage_bytes, (size_t)std::max(2, std::min(max_stages, kMaxStages)));
+    // A deep ring buys nothing at C >= 128 (a stage is >= 512 tensor-core cycles) while every 16-32 KB of
+    // shared memory it takes is L1 that the load / final phases' global accesses need for misses in flight
+    // (measured: C = 256 pairs 0.47 -> 0.41 ms (k = 3) with 3 stages, C = 128 pairs 0.89 -> 0.78 ms with 4)
+    if (C >= 128) stages = std::min(stages, C == 256 ? 3 : 4);
     // keep two CTAs per SM resident when tensor memory allows it (2 * ntile * C <= 256 columns)
     if (2 * ntile * C <= 256)
       while (stages > 2 && opb + stages * stage_bytes + tail > 110 * 1024) --stages;
@@ -500,6 +509,8 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   k.trace = trace_buffer();
   static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
   k.sm_count = sm_count;
+  static const int dbg = [] { const char* e = std::getenv("NVSE_RB_DBG"); return e ? std::atoi(e) : 0; }();
+  k.dbg = dbg;
   k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
   dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
   const double rows = (double)B * a.T;
