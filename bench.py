@@ -232,7 +232,17 @@ def main():
         return
 
     pk = peaks()
-    tc = [k for k in prof if k["kernel"].startswith(("conv_tc", "resblock_tc"))]
+    # DRAM traffic of the tensor-core kernels from the committed `ncu --set full` capture of one forward
+    # (profiles/r01_ncu_traffic.json: bytes per launch, same shapes as this workload's micro-batch)
+    traffic, traffic_note = None, "no ncu capture for this micro-batch"
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("micro_batch") == args.micro_batch and tj.get("seconds") == args.seconds:
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_note = (f"dram__bytes_read+write per launch, mean over the {tj['launches']} tensor-core launches of one forward "
+                            f"(algorithmic bytes per launch by the same count: {tj['algorithmic_bytes_per_launch']:.3e})")
+    tc = [k for k in prof if k["kernel"].startswith(("conv_tc", "resblock_tc", "pair_tc"))]
     tc_ms, tc_flops, tc_n = sum(k["ms"] for k in tc), sum(k["flops"] for k in tc), sum(k["launches"] for k in tc)
     all_ms = sum(k["ms"] for k in prof)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
@@ -249,9 +259,9 @@ def main():
         "e2e": {"value": e2e, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(U * T * 4), "d2h_bytes_per_step": int(U * t_out * 4),
                 "ms_per_step": ms_e2e / args.steps, "api": "Vocoder.run_host: pinned host wav -> mel_spectrogram -> HiFiGAN -> pinned host wav"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "resblock_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs: fused MRF ResBlocks + upsamplers)",
+        "roofline": {"bound": "tensor", "kernel": "resblock_tc_kernel + pair_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs: fused MRF ResBlocks + upsamplers)",
                      "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", sustained bf16",
+                     "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + ", sustained bf16",
                      "launches": tc_n, "avg_launch_ms": tc_ms / tc_n if tc_n else None, "share_of_step": tc_ms / all_ms if all_ms else None,
                      "timing": "per-launch CUDA events on the launching stream, separate pass of the same K steps"},
         "frontend": {"kernel": "mel_frontend_kernel", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": fe_gbs / pk["hbm_gbs"],

@@ -182,7 +182,16 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
         single = (v < 0.0 || single < 0.0) ? -1.0 : single + v;
       }
       if (whole < 0.0 && single < 0.0) t32 = false;
-      per_launch[(size_t)i * c.num_kernels + j] = (single < 0.0 || (whole >= 0.0 && whole <= single)) ? nd : 1;
+      int per = (single < 0.0 || (whole >= 0.0 && whole <= single)) ? nd : 1;
+      // measured (tools/rb_bench.py, C = 128, 32 x 55168 rows): the pipelined pair kernel beats the whole-block
+      // launch from k = 5 up (k = 7: 3 x 0.86 ms vs 2.9 ms), the two-CTA whole-block launch wins at k = 3
+      static const bool pairpipe_plan = [] { const char* e = std::getenv("NVSE_PAIRPIPE"); return !(e && e[0] == '0'); }();
+      if (pairpipe_plan && single >= 0.0 && l0.k >= 5) {
+        bool all = true;
+        for (int m = 0; m < nd; ++m) all = all && pair_supported(l0.Cin, l0.k, dil[m]);
+        if (all) per = 1;
+      }
+      per_launch[(size_t)i * c.num_kernels + j] = per;
     }
   }
   int64_t T = F;

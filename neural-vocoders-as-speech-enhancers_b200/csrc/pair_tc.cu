@@ -348,7 +348,9 @@ bool make_pair_plan(int C, int k, int dil, PairPlan* p) {
   const size_t stage_bytes = (size_t)64 * C * 2;
   const size_t tail = sizeof(float) * 2 * C + sizeof(uint64_t) * kNumBars + 16;
   if (2 * opb + 2 * stage_bytes + tail > kSmemBudget) return false;
-  p->stages = (int)std::min<size_t>((kSmemBudget - 2 * opb - tail) / stage_bytes, (size_t)kMaxStages);
+  static const int max_stages = [] { const char* e = std::getenv("NVSE_PAIR_STAGES"); return e ? std::atoi(e) : 3; }();
+  // shared memory left unused is L1 for the loaders' and the final phase's global accesses (see resblock_tc.cu)
+  p->stages = (int)std::min<size_t>((kSmemBudget - 2 * opb - tail) / stage_bytes, (size_t)std::max(2, std::min(max_stages, kMaxStages)));
   p->halo = halo; p->V = R - 2 * halo; p->P = P; p->rows_pad = rows_pad;
   p->smem = 2 * opb + p->stages * stage_bytes + tail;
   return true;

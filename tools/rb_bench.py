@@ -27,7 +27,7 @@ dil = (C.c_int * npairs)(*dils)
 
 def run():
     lib_mod.check(lib.nvse_resblock1_bf16(lib_mod.ptr(x), a_w1, a_b1, a_w2, a_b2, dil, npairs, lib_mod.ptr(y), B, T, Cc, k,
-                                          1.0 / 3, 1, stream_ptr()))
+                                          1.0 / 3, int(os.environ.get("RB_ACC", "1")), stream_ptr()))
 
 
 run()
