@@ -19,6 +19,8 @@
 // 16-column chunks), warp 8 weight producer, warp 9 TMEM allocator + MMA issuer.  All ten warps
 // stage activations first; the epilogue warps also prefetch their residual / accumulate rows into
 // L2 before staging so that the loads of the epilogue do not pay HBM latency.
+#include <cuda_fp16.h>
+
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -324,22 +326,23 @@ done:
 
 // fp32 [j][ci][co] -> bf16 [j][ci/KC][(ci%KC)/8][co][ci%8]
 __global__ void __launch_bounds__(256) pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img,
-                                                              int Cin, int Cout, int ktaps, int kc) {
+                                                              int Cin, int Cout, int ktaps, int kc, int as_fp16) {
   const int64_t n = (int64_t)Cin * Cout * ktaps;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int co = e % Cout, ci = (e / Cout) % Cin, j = e / ((int64_t)Cout * Cin);
     const int64_t dst = ((((int64_t)j * (Cin / kc) + ci / kc) * (kc / 8) + (ci % kc) / 8) * Cout + co) * 8 + (ci % 8);
-    img[dst] = __float2bfloat16_rn(w[e]);
+    if (as_fp16) reinterpret_cast<__half*>(img)[dst] = __float2half_rn(w[e]);  // same 16-bit slots, IEEE half
+    else img[dst] = __float2bfloat16_rn(w[e]);
   }
 }
 
 }  // namespace
 
-int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int ktaps, cudaStream_t st) {
+int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int ktaps, cudaStream_t st, bool as_fp16) {
   NVSE_REQUIRE(tc_supported(Cin, Cout), NVSE_ERR_UNSUPPORTED, "tensor-core conv: Cin=%d / Cout=%d unsupported", Cin, Cout);
   const int64_t n = (int64_t)Cin * Cout * ktaps;
   pack_weight_tc_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, st>>>(w_kio, img, Cin, Cout, ktaps,
-                                                                                            tc_kchunk(Cin));
+                                                                                            tc_kchunk(Cin), as_fp16 ? 1 : 0);
   NVSE_LAUNCH_CHECK("pack_weight_tc_kernel");
   return NVSE_OK;
 }

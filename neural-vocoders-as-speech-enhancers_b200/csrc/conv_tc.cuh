@@ -49,6 +49,7 @@ constexpr int kTcMaxPhases = 8;
 int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const int* phase_out_add, int nphase, int64_t B,
                           cudaStream_t st);
 // fp32 [k][Cin][Cout] (Layer::w layout) -> bf16 tensor-core image
-int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int k, cudaStream_t st);
+// as_fp16: IEEE half instead of bf16 in the same image layout (operands of the C = 32 c2 convs, resblock_tc.cu)
+int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int k, cudaStream_t st, bool as_fp16 = false);
 
 }  // namespace nvse

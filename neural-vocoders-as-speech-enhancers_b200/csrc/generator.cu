@@ -214,15 +214,15 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
           ra.x = src; ra.y = dst; ra.T = (int)T; ra.C = l0.Cin; ra.k = l0.k; ra.npairs = per;
           ra.t32 = 1; ra.bstride = t32_rows(T) * l0.Cin;
           ra.slope = slope; ra.out_scale = last ? inv : 1.0f; ra.accumulate = last && j > 0;
-          ra.split_h = l0.Cin <= 32;  // the c1 -> c2 intermediate as hi + lo bf16 planes (see finalize_bf16)
+          ra.h_fp16 = l0.Cin <= 32;  // the c1 -> c2 intermediate and w2 in IEEE half (see finalize_bf16)
           for (int q = 0; q < per; ++q) {
             const Layer& c1 = g->layer(p + ".convs1." + std::to_string(m0 + q));
             const Layer& c2 = g->layer(p + ".convs2." + std::to_string(m0 + q));
-            ra.pair[q] = RbPair{reinterpret_cast<const __nv_bfloat16*>(c1.w_bf16), reinterpret_cast<const __nv_bfloat16*>(c2.w_bf16),
-                                c1.bias, c2.bias, c1.dilation};
+            ra.pair[q] = RbPair{reinterpret_cast<const __nv_bfloat16*>(c1.w_bf16),
+                                reinterpret_cast<const __nv_bfloat16*>(ra.h_fp16 ? c2.w_f16 : c2.w_bf16), c1.bias, c2.bias, c1.dilation};
           }
           static const bool pairpipe = [] { const char* e = std::getenv("NVSE_PAIRPIPE"); return !(e && e[0] == '0'); }();
-          if (pairpipe && per == 1 && !ra.split_h && pair_supported(ra.C, ra.k, ra.pair[0].dil)) {
+          if (pairpipe && per == 1 && !ra.h_fp16 && pair_supported(ra.C, ra.k, ra.pair[0].dil)) {
             if (int rc = launch_pair_tc(ra, B, st)) return rc;
           } else if (int rc = launch_resblock_tc(ra, B, st)) {
             return rc;
@@ -278,6 +278,10 @@ int finalize_bf16(nvse_generator* g, cudaStream_t st) {
     if (!wanted) continue;
     if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
     if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_bf16), L.Cin, L.Cout, L.k, st)) return rc;
+    if (!L.transposed && L.Cout <= 32 && L.name.find(".convs2.") != std::string::npos) {
+      if (!L.w_f16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_f16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
+      if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_f16), L.Cin, L.Cout, L.k, st, true)) return rc;
+    }
     // Where bf16 rounding of the ACTIVATION operand costs the most SNR and the least time (the
     // upsamplers: 3 % of the FLOPs; the <= 32-channel MRF stage: HBM-bound anyway) activations are
     // fed as hi + lo bf16 pairs (tools/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
@@ -336,6 +340,7 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     cudaFree(L.w);
     cudaFree(L.bias);
     cudaFree(L.w_bf16);
+    cudaFree(L.w_f16);
   }
   delete g;
   return NVSE_OK;

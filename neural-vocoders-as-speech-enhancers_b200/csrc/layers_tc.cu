@@ -102,8 +102,8 @@ extern "C" int nvse_resblock1_bf16(const float* x, const float* const* w1, const
   const char* pp = std::getenv("NVSE_PAIRPIPE");
   const bool pairpipe = !(pp && pp[0] == '0');
   a.t32 = bench_t32 || layer_t32;
-  static const bool bench_split = std::getenv("NVSE_RB_SPLIT") != nullptr;  // experiments: hi + lo intermediate at C = 32
-  a.split_h = bench_split && C == 32;
+  const char* h16 = std::getenv("NVSE_RB_H16");  // tests / experiments: IEEE-half c1 -> c2 intermediate (what the generator uses at C <= 32)
+  a.h_fp16 = h16 && h16[0] != '0' && C <= 64;
   Scratch xt(st), yt(st);
   if (layer_t32) {
     const size_t bytes = sizeof(float) * (size_t)B * t32_rows(T) * C;
@@ -122,11 +122,11 @@ extern "C" int nvse_resblock1_bf16(const float* x, const float* const* w1, const
     if (int rc = launch_repack_weight(w1[m], (float*)wk.p, C, C, k, false, st)) return rc;
     if (int rc = launch_pack_weight_tc((const float*)wk.p, i1, C, C, k, st)) return rc;
     if (int rc = launch_repack_weight(w2[m], (float*)wk.p, C, C, k, false, st)) return rc;
-    if (int rc = launch_pack_weight_tc((const float*)wk.p, i2, C, C, k, st)) return rc;
+    if (int rc = launch_pack_weight_tc((const float*)wk.p, i2, C, C, k, st, a.h_fp16 != 0)) return rc;
     a.pair[m] = RbPair{i1, i2, b1[m], b2[m], dilations[m]};
   }
   int rc;
-  if (a.t32 && pairpipe && npairs == 1 && !a.split_h && pair_supported(C, k, dilations[0])) rc = launch_pair_tc(a, B, st);
+  if (a.t32 && pairpipe && npairs == 1 && !a.h_fp16 && pair_supported(C, k, dilations[0])) rc = launch_pair_tc(a, B, st);
   else rc = launch_resblock_tc(a, B, st);
   if (rc) return rc;
   if (layer_t32) return launch_relayout_t32((const float*)yt.p, y, B, T, C, false, st);

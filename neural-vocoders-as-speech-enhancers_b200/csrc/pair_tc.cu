@@ -364,7 +364,7 @@ bool pair_supported(int C, int k, int dil) {
 }
 
 int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
-  NVSE_REQUIRE(a.npairs == 1 && a.t32 && !a.split_h, NVSE_ERR_INVALID, "pipelined pair kernel: one pair, T32 layout, no split");
+  NVSE_REQUIRE(a.npairs == 1 && a.t32 && !a.h_fp16, NVSE_ERR_INVALID, "pipelined pair kernel: one pair, T32 layout, no split");
   if (B == 0 || a.T <= 0) return NVSE_OK;
   PairPlan p;
   NVSE_REQUIRE(make_pair_plan(a.C, a.k, a.pair[0].dil, &p), NVSE_ERR_UNSUPPORTED, "pipelined pair kernel: C=%d k=%d d=%d unsupported", a.C,

@@ -24,6 +24,8 @@
 // a quarter split the 16-column chunks), warp 8 weight producer, warp 9 TMEM allocator + MMA issuer.
 #include "resblock_tc.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "conv_tc.cuh"
@@ -60,31 +62,30 @@ __device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity) {
   return __all_sync(0xffffffffu, ok);
 }
 
-// 16 activated values of one row -> two 16-byte core-matrix rows of the operand buffer; with LO also the
-// bf16-rounded residual of the first rounding into the second plane (hi + lo carries ~16 mantissa bits)
-template <bool LO>
-__device__ __forceinline__ void store_operand(uint8_t* op, uint32_t lo_plane, int rows_pad, int brow, int c0, const float (&f)[16],
-                                              float slope, bool keep) {
-  uint32_t hi[8], lo[8];
+// 16 activated values of one row -> two 16-byte core-matrix rows of the operand buffer, as bf16 or (F16) as IEEE
+// half saturated to the finite range (three more mantissa bits for the c1 -> c2 intermediate of the last stage)
+template <bool F16>
+__device__ __forceinline__ void store_operand(uint8_t* op, int rows_pad, int brow, int c0, const float (&f)[16], float slope, bool keep) {
+  uint32_t hi[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float a0 = keep ? lrelu(f[2 * i], slope) : 0.f, a1 = keep ? lrelu(f[2 * i + 1], slope) : 0.f;
-    hi[i] = pack_bf16(a0, a1);
-    if (LO) lo[i] = pack_bf16(a0 - bf16_lo(hi[i]), a1 - bf16_hi(hi[i]));
+    if (F16) {
+      const __half2 h = __floats2half2_rn(fminf(fmaxf(a0, -65504.f), 65504.f), fminf(fmaxf(a1, -65504.f), 65504.f));
+      hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      hi[i] = pack_bf16(a0, a1);
+    }
   }
   const size_t o0 = ((size_t)(c0 >> 3) * rows_pad + brow) * 16, o1 = o0 + (size_t)rows_pad * 16;
   *reinterpret_cast<uint4*>(op + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(op + o1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  if (LO) {
-    *reinterpret_cast<uint4*>(op + lo_plane + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(op + lo_plane + o1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-  }
 }
 
 // C and the tile count are compile-time: the MMA issue loop must unroll completely -- a tcgen05.mma issued
 // from a loop with run-time trip counts costs 60-200 cycles of issue (tools/probe/mma_probe3.cu), more
 // than the MMA itself takes on the tensor core.
-template <int C, int NT, bool SPLIT>
+template <int C, int NT, bool H16>
 __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resblock_tc_kernel(const __grid_constant__ RbKernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const ResblockTcArgs& a = k.a;
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   const int t_in0 = (int)blockIdx.x * k.V - k.halo;  // time index of tile row 0
   const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
   constexpr uint32_t stage_bytes = (uint32_t)KC * C * 2u;
-  uint8_t* op = smem_raw;  // hi plane, then (SPLIT) the lo plane of the c1 -> c2 intermediate
-  uint8_t* wst = smem_raw + (SPLIT ? 2u : 1u) * op_bytes;
+  uint8_t* op = smem_raw;
+  uint8_t* wst = smem_raw + op_bytes;
   float* bsm = reinterpret_cast<float*>(wst + (size_t)k.stages * stage_bytes);  // b1[m][C] then cb[m][C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 2 * kRbMaxPairs * C);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     // MMAs deep, so issue-side latency beyond ~100 cycles per stage shows up as tensor idle time. =====
     if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      constexpr uint32_t idesc_f16 = idesc & ~((1u << 7) | (1u << 10));  // A and B formats 0 = IEEE half
       // descriptor low words advance in 16-byte units: one operand-buffer row = 1, one weight row = 1
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(op), (uint32_t)k.rows_pad * 16u);
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(wst), (uint32_t)C * 16u);
@@ -201,10 +203,9 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
 #pragma unroll
               for (int kk = 0; kk < kkn; ++kk) {
 #pragma unroll
-                for (int j = 0; j < n; ++j) {
-                  tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, acc);
-                  if (SPLIT && half) tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (op_bytes >> 4) + (uint32_t)(j * kTileM), hi, b_lo, hi, idesc, 1u);
-                }
+                for (int j = 0; j < n; ++j)
+                  tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, (H16 && half) ? idesc_f16 : idesc,
+                                   acc);
                 acc = 1u;
                 a_lo += 2u * (uint32_t)k.rows_pad;
                 b_lo += 2u * (uint32_t)C;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
 #pragma unroll
         for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
         if (!(k.dbg & 4)) tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
-        if (!(k.dbg & 8)) store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+        if (!(k.dbg & 8)) store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
       }
     }
     tmem_st_wait();
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
             f[4 * u + 2] = __uint_as_float(v[i & 1][4 * u + 2]) + bq.z;
             f[4 * u + 3] = __uint_as_float(v[i & 1][4 * u + 3]) + bq.w;
           }
-          store_operand<SPLIT>(op, op_bytes, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+          store_operand<H16>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
         }
       }
       fence_proxy_async_smem();
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
               f[4 * u + 2] = __uint_as_float(v[i & 1][4 * u + 2]) + bq.z;
               f[4 * u + 3] = __uint_as_float(v[i & 1][4 * u + 3]) + bq.w;
             }
-            store_operand<false>(op, 0u, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+            store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
           }
         }
         fence_proxy_async_smem();
@@ -420,8 +421,7 @@ struct RbPlan {
 };
 
 // ntile: as many 128-row tiles as tensor memory (X + ACC = 2 * ntile * C columns <= 512) and shared memory allow
-bool make_plan(int C, int k, const int* dil, int npairs, bool split, RbPlan* p) {
-  if (split && C != 32) return false;
+bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
   if (!(C == 32 || C == 64 || C == 128 || C == 256)) return false;
   if (k < 1 || !(k & 1) || k > kMaxTaps || npairs < 1 || npairs > kRbMaxPairs) return false;
   int halo = 0, P = (k - 1) / 2;
@@ -444,7 +444,7 @@ bool make_plan(int C, int k, const int* dil, int npairs, bool split, RbPlan* p) 
   for (; ntile >= min_tile; ntile >>= 1) {
     const int R = kTileM * ntile;
     const int rows_pad = R + 2 * P;
-    const size_t opb = (split ? 2 : 1) * (((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127);
+    const size_t opb = ((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127;
     if (R - 2 * halo < 32) return false;  // not enough useful rows per tile: per-layer kernels do better
     if (opb + 2 * stage_bytes + tail > kSmemBudget) continue;
     static const int max_stages = [] { const char* e = std::getenv("NVSE_RB_STAGES"); return e ? std::atoi(e) : kMaxStages; }();
@@ -480,14 +480,14 @@ static long long* trace_buffer() {
 
 bool rb_supported(int C, int k, const int* dil, int npairs) {
   RbPlan p;
-  return make_plan(C, k, dil, npairs, false, &p);
+  return make_plan(C, k, dil, npairs, &p);
 }
 
 // Per-CTA cycle model fitted to the phase traces of tools/rb_trace.py (profiles/): load + final phases,
 // 2 * npairs MMA phases at the tensor-core/shared-memory floor, 2 * npairs - 1 epilogues.
 double rb_cost_per_row(int C, int k, const int* dil, int npairs) {
   RbPlan p;
-  if (!make_plan(C, k, dil, npairs, false, &p)) return -1.0;
+  if (!make_plan(C, k, dil, npairs, &p)) return -1.0;
   const double mma = std::max(C / 2.0, 32.0 + C / 4.0) * 1.12;
   const double conv = (double)p.ntile * k * (C / 16) * mma;
   const double epi = 600.0 + 7.5 * p.ntile * C;
@@ -501,7 +501,7 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   int dil[kRbMaxPairs] = {1, 1, 1};
   for (int m = 0; m < a.npairs && m < kRbMaxPairs; ++m) dil[m] = a.pair[m].dil;
   RbPlan p;
-  NVSE_REQUIRE(make_plan(a.C, a.k, dil, a.npairs, a.split_h != 0, &p), NVSE_ERR_UNSUPPORTED, "fused resblock: C=%d k=%d unsupported", a.C, a.k);
+  NVSE_REQUIRE(make_plan(a.C, a.k, dil, a.npairs, &p), NVSE_ERR_UNSUPPORTED, "fused resblock: C=%d k=%d unsupported", a.C, a.k);
   RbKernelArgs k;
   k.a = a;
   if (k.a.bstride == 0) k.a.bstride = (a.t32 ? t32_rows(a.T) : (int64_t)a.T) * a.C;
@@ -517,11 +517,11 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   ProfScope prof("resblock_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0 * a.npairs,
                  rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
 #define RB_LAUNCH(CC, NN, SP)                                                                                               \
-  if (a.C == CC && p.ntile == NN && (a.split_h != 0) == SP) {                                                               \
+  if (a.C == CC && p.ntile == NN && (a.h_fp16 != 0) == SP) {                                                               \
     NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_tc_kernel<CC, NN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
     resblock_tc_kernel<CC, NN, SP><<<grid, kThreads, p.smem, st>>>(k);                                                      \
   } else
-  RB_LAUNCH(32, 4, false) RB_LAUNCH(32, 4, true) RB_LAUNCH(32, 8, false) RB_LAUNCH(32, 8, true) RB_LAUNCH(64, 4, false)
+  RB_LAUNCH(32, 4, false) RB_LAUNCH(32, 4, true) RB_LAUNCH(32, 8, false) RB_LAUNCH(64, 4, false) RB_LAUNCH(64, 4, true)
   RB_LAUNCH(64, 2, false) RB_LAUNCH(128, 2, false) RB_LAUNCH(128, 1, false) RB_LAUNCH(256, 1, false)
   return fail(NVSE_ERR_UNSUPPORTED, "fused resblock: no kernel for C=%d with %d tiles", a.C, p.ntile);
 #undef RB_LAUNCH

@@ -11,7 +11,7 @@ constexpr int kRbMaxPairs = 3;
 
 struct RbPair {
   const __nv_bfloat16* w1;  // tensor-core weight image of convs1[m] (conv_tc.cuh layout), dilation `dil`
-  const __nv_bfloat16* w2;  // image of convs2[m], dilation 1
+  const __nv_bfloat16* w2;  // image of convs2[m], dilation 1 (IEEE half bit patterns when h_fp16)
   const float* b1;          // [C]
   const float* b2;          // [C]
   int dil;
@@ -28,8 +28,8 @@ struct ResblockTcArgs {
   float slope;       // leaky_relu slope in front of every conv (LRELU_SLOPE, hifigan.py:7)
   float out_scale;
   int accumulate;
-  int split_h;       // feed c2 its input as hi + lo bf16 planes (two MMAs per step): where the rounding of the
-                     // c1 -> c2 intermediate costs the most SNR (tools/bf16_budget.py); C = 32 only
+  int h_fp16;        // the c1 -> c2 intermediate and the w2 images are IEEE half instead of bf16 (same range of values,
+                     // three more mantissa bits): where rounding of that intermediate costs the most SNR (tools/bf16_budget.py)
 };
 
 // true when the fused kernel handles this shape (otherwise the caller uses the per-layer kernels)

@@ -228,6 +228,36 @@ def test_fused_resblock1_t32_layout_kernels(monkeypatch, C_, k, dils, T, B, pair
     assert torch.allclose(out2, y0 + out / 3, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("C_,k,dils,T,B", [(32, 3, (1, 3, 5), 1300, 2), (32, 11, (1, 3, 5), 1000, 1), (32, 7, (1, 3, 5), 40, 1),
+                                           (64, 7, (1, 3), 700, 1)])
+def test_fused_resblock1_half_precision_intermediate(monkeypatch, C_, k, dils, T, B):
+    """The variant the generator runs at C <= 32: the c1 -> c2 intermediate and the c2 weights are rounded to IEEE
+    half (fp16 tcgen05 operands) instead of bf16; everything else as above."""
+    monkeypatch.setenv("NVSE_RB_H16", "1")
+    f16 = lambda v: v.to(torch.float16).to(torch.float32)
+    n = len(dils)
+    x = _rand((B, C_, T), 241)
+    w1 = [_rand((C_, C_, k), 242 + m, 1.0 / np.sqrt(C_ * k)) for m in range(n)]
+    w2 = [_rand((C_, C_, k), 252 + m, 1.0 / np.sqrt(C_ * k)) for m in range(n)]
+    b1 = [_rand((C_,), 262 + m, 0.3) for m in range(n)]
+    b2 = [_rand((C_,), 272 + m, 0.3) for m in range(n)]
+    ref, ref32 = x, x
+    for m, d in enumerate(dils):
+        h = F.conv1d(_bf(F.leaky_relu(ref, 0.1)), _bf(w1[m]), b1[m], dilation=d, padding=(k - 1) * d // 2)
+        ref = F.conv1d(f16(F.leaky_relu(h, 0.1)), f16(w2[m]), b2[m], padding=(k - 1) // 2) + ref
+        h = F.conv1d(F.leaky_relu(ref32, 0.1), w1[m], b1[m], dilation=d, padding=(k - 1) * d // 2)
+        ref32 = F.conv1d(F.leaky_relu(h, 0.1), w2[m], b2[m], padding=(k - 1) // 2) + ref32
+    out = resblock1_cl(x, w1, b1, w2, b2, dils)
+    assert not lib_mod.tc_abort_status()
+    err = (out - ref).abs()
+    budget = float((ref - ref32).abs().mean())
+    assert float(err.max()) <= 2e-2 and float(err.mean()) <= 0.5 * budget + 1e-5, (float(err.max()), float(err.mean()), budget)
+    # and it is the more accurate variant: closer to the unrounded chain than the all-bf16 kernel
+    monkeypatch.setenv("NVSE_RB_H16", "0")
+    out_bf = resblock1_cl(x, w1, b1, w2, b2, dils)
+    assert float((out - ref32).abs().mean()) < float((out_bf - ref32).abs().mean())
+
+
 @pytest.mark.parametrize("cin,cout,k,u,T,B", [(512, 256, 16, 8, 9, 2), (256, 128, 16, 8, 140, 1), (128, 64, 4, 2, 130, 2),
                                              (64, 32, 4, 2, 257, 1), (64, 32, 16, 8, 1, 1)])
 def test_conv_transpose1d_tensor_core_matches_torch_on_bf16_operands(cin, cout, k, u, T, B):
