@@ -91,13 +91,14 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   const ResblockTcArgs& a = k.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int n = NT, R = n * kTileM, nchunk = C >> 3, KC = C < 64 ? C : 64;
+  constexpr int TPS = C == 32 ? 4 : (C == 64 ? 2 : 1);  // taps per weight stage (nkc == 1 whenever TPS > 1)
   const int npairs = a.npairs;
   const int64_t b = blockIdx.y;
   const int64_t bstride = a.bstride;
   const int ws4 = a.t32 ? 32 : 1;  // float4 stride between the 4-channel groups of one row
   const int t_in0 = (int)blockIdx.x * k.V - k.halo;  // time index of tile row 0
   const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
-  constexpr uint32_t stage_bytes = (uint32_t)KC * C * 2u;
+  constexpr uint32_t tap_bytes = (uint32_t)KC * C * 2u, stage_bytes = TPS * tap_bytes;
   uint8_t* op = smem_raw;
   uint8_t* wst = smem_raw + op_bytes;
   float* bsm = reinterpret_cast<float*>(wst + (size_t)k.stages * stage_bytes);  // b1[m][C] then cb[m][C]
@@ -155,12 +156,11 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
       for (int m = 0; m < npairs; ++m)
         for (int half = 0; half < 2; ++half) {
           const __nv_bfloat16* wimg = half ? a.pair[m].w2 : a.pair[m].w1;
-          for (int st = 0; st < a.k * nkc; ++st) {
+          for (int st = 0; st < a.k * nkc; st += TPS) {  // a stage = TPS consecutive (tap, K chunk) slices of the image
             if (!mbar_wait(bar_empty + 8 * s, ph)) goto done;
-            const uint32_t cp_bytes = (k.dbg & 2) ? stage_bytes / 4 : stage_bytes;  // dbg 2: timing experiment, wrong results
+            const uint32_t cp_bytes = (uint32_t)min(TPS, a.k * nkc - st) * tap_bytes;
             mbar_arrive_expect_tx(bar_full + 8 * s, cp_bytes);
-            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (stage_bytes / 2), cp_bytes,
-                          bar_full + 8 * s);
+            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (tap_bytes / 2), cp_bytes, bar_full + 8 * s);
             if (++s == nstage) { s = 0; ph ^= 1u; }
           }
         }
@@ -191,28 +191,35 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
           const uint32_t d_tmem = half ? tmem_x : tmem_acc;
           uint32_t acc = half ? 1u : 0u;  // c1 starts a fresh accumulator, c2 accumulates onto X
           uint32_t a_tap = a_lo0 + (uint32_t)(k.P - (a.k - 1) / 2 * d);
-          for (int tap = 0; tap < a.k; ++tap, a_tap += (uint32_t)d) {
+          for (int tap = 0; tap < a.k; tap += TPS) {
 #pragma unroll
-            for (int kc = 0; kc < nkc; ++kc) {
+            for (int kc = 0; kc < (TPS > 1 ? 1 : nkc); ++kc) {
               const long long tw0 = tracing ? clock64() : 0;
               if (!mbar_wait(bar_full + 8 * s, ph)) goto mma_exit;
               if (tracing) tr_wait += clock64() - tw0;
               tc_fence_after();
-              uint32_t a_lo = a_tap + (uint32_t)(kc * (KC >> 3)) * (uint32_t)k.rows_pad;
               uint32_t b_lo = b_lo0 + s * stage_units;
 #pragma unroll
-              for (int kk = 0; kk < kkn; ++kk) {
+              for (int tt = 0; tt < TPS; ++tt) {
+                if (tap + tt < a.k) {
+                  uint32_t a_lo = a_tap + (uint32_t)(kc * (KC >> 3)) * (uint32_t)k.rows_pad;
 #pragma unroll
-                for (int j = 0; j < n; ++j)
-                  tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, (H16 && half) ? idesc_f16 : idesc,
-                                   acc);
-                acc = 1u;
-                a_lo += 2u * (uint32_t)k.rows_pad;
-                b_lo += 2u * (uint32_t)C;
+                  for (int kk = 0; kk < kkn; ++kk) {
+#pragma unroll
+                    for (int j = 0; j < n; ++j)
+                      tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi,
+                                       (H16 && half) ? idesc_f16 : idesc, acc);
+                    acc = 1u;
+                    a_lo += 2u * (uint32_t)k.rows_pad;
+                    b_lo += 2u * (uint32_t)C;
+                  }
+                  if (TPS > 1) a_tap += (uint32_t)d;
+                }
               }
               tc_commit(bar_empty + 8 * s);
               if (++s == nstage) { s = 0; ph ^= 1u; }
             }
+            if (TPS == 1) a_tap += (uint32_t)d;
           }
           tc_commit(half ? bar_x : bar_acc);
         }
@@ -413,10 +420,292 @@ done:
   if (warp == kWorkWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Software-pipelined variant of the chain kernel (C <= 64, NT even): the NT tiles of a CTA are worked on as
+// two halves A and B.  The MMA thread issues conv l on A, then on B, then conv l+1 on A, ...; the epilogue of
+// (l, A) runs while the tensor core works on (l, B), the epilogue of (l, B) while it works on (l+1, A):
+// except for the few rows of B that conv l+1 on A reads across the A/B boundary, the tensor core never waits
+// for an epilogue.  What that takes:
+//   * two operand buffers: the input S_l of conv l lives in OP[l & 1], its epilogue writes S_(l+1) into
+//     OP[(l+1) & 1] -- half A may not overwrite rows conv l still reads for half B;
+//   * one mbarrier per TILE ("S_l of tile j is written"): conv l on a half waits for its own tiles and the
+//     neighbouring tile of the other half; one "accumulator ready" mbarrier per half;
+//   * the weights of every conv stream through the ring twice (once per half): L2 traffic x2, which at
+//     C <= 64 is ~20 B/clk/SM.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPipeBars = 2 * kMaxStages + 8 + 2;
+
+template <int C, int NT, bool H16>
+__global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resblock_pipe_kernel(const __grid_constant__ RbKernelArgs k) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  static_assert(NT % 2 == 0 && NT <= 8, "the tiles are split into two halves");
+  const ResblockTcArgs& a = k.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int n = NT, HN = NT / 2, R = n * kTileM, nchunk = C >> 3, KC = C < 64 ? C : 64;
+  constexpr int nkc = C / KC, kkn = KC >> 4;
+  constexpr int TPS = C == 32 ? 4 : 2;  // taps per weight stage (nkc == 1 at C <= 64)
+  static_assert(nkc == 1, "the pipelined kernel is for C <= 64");
+  const int npairs = a.npairs, L = 2 * npairs;
+  const int64_t b = blockIdx.y;
+  const int64_t bstride = a.bstride;
+  const int ws4 = a.t32 ? 32 : 1;
+  const int t_in0 = (int)blockIdx.x * k.V - k.halo;
+  const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
+  constexpr uint32_t tap_bytes = (uint32_t)KC * C * 2u, stage_bytes = TPS * tap_bytes;
+  uint8_t* op0 = smem_raw;  // OP[0], OP[1]
+  uint8_t* wst = smem_raw + 2 * op_bytes;
+  float* bsm = reinterpret_cast<float*>(wst + (size_t)k.stages * stage_bytes);  // b1[m][C] then cb[m][C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + 2 * kRbMaxPairs * C);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
+  const uint32_t bar_tile = smem_u32(bars + 2 * kMaxStages);  // [NT]  S_l of tile j written   (8 warps)
+  const uint32_t bar_accf = bar_tile + 8 * 8;                 // [2]   accumulator of a half ready (commit)
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * n * C)) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < k.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < n; ++j) mbar_init(bar_tile + 8 * j, kWorkWarps);
+    mbar_init(bar_accf, 1);
+    mbar_init(bar_accf + 8, 1);
+    fence_barrier_init();
+  }
+  if (warp == kWorkWarps + 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+  {
+    const int zr = 2 * k.P;
+    for (int e = tid; e < 2 * nchunk * zr; e += kThreads) {
+      const int bufi = e / (nchunk * zr), e2 = e - bufi * nchunk * zr;
+      const int chunk = e2 / zr, i = e2 - chunk * zr;
+      const int row = i < k.P ? i : R + i;
+      *reinterpret_cast<uint4*>(op0 + (size_t)bufi * op_bytes + ((size_t)chunk * k.rows_pad + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int e = tid; e < npairs * C; e += kThreads) {
+      const int m = e / C, c = e - m * C;
+      bsm[e] = __ldg(a.pair[m].b1 + c);
+      float cb = 0.f;
+      for (int i = 0; i <= m; ++i) cb += __ldg(a.pair[i].b2 + c);
+      bsm[kRbMaxPairs * C + e] = cb;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_x = tmem_base, tmem_acc = tmem_base + (uint32_t)(n * C);
+
+  if (warp == kWorkWarps) {
+    // ===== weight producer: every conv's stages twice (half A, half B) =====
+    if (lane == 0) {
+      const uint32_t nstage = (uint32_t)k.stages;
+      uint32_t s = 0, ph = 1;
+      for (int l = 0; l < L; ++l) {
+        const __nv_bfloat16* wimg = (l & 1) ? a.pair[l >> 1].w2 : a.pair[l >> 1].w1;
+        for (int hf = 0; hf < 2; ++hf)
+          for (int st = 0; st < a.k; st += TPS) {
+            if (!mbar_wait(bar_empty + 8 * s, ph)) goto done;
+            const uint32_t cp_bytes = (uint32_t)min(TPS, a.k - st) * tap_bytes;
+            mbar_arrive_expect_tx(bar_full + 8 * s, cp_bytes);
+            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (tap_bytes / 2), cp_bytes, bar_full + 8 * s);
+            if (++s == nstage) { s = 0; ph ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == kWorkWarps + 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      constexpr uint32_t idesc_f16 = idesc & ~((1u << 7) | (1u << 10));
+      const uint32_t a_lo_even = umma_desc_lo(smem_u32(op0), (uint32_t)k.rows_pad * 16u);
+      const uint32_t a_lo_odd = umma_desc_lo(smem_u32(op0 + op_bytes), (uint32_t)k.rows_pad * 16u);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(wst), (uint32_t)C * 16u);
+      const uint32_t hi = umma_desc_hi(128u);
+      constexpr uint32_t stage_units = stage_bytes >> 4;
+      const uint32_t nstage = (uint32_t)k.stages;
+      uint32_t s = 0, ph = 0;
+      for (int l = 0; l < L; ++l) {
+        const int c2 = l & 1;
+        const int d = c2 ? 1 : a.pair[l >> 1].dil;
+        const uint32_t d_tmem = c2 ? tmem_x : tmem_acc;
+        const uint32_t id = (H16 && c2) ? idesc_f16 : idesc;
+        const uint32_t a_buf = (c2 ? a_lo_odd : a_lo_even) + (uint32_t)(k.P - (a.k - 1) / 2 * d);
+        for (int hf = 0; hf < 2; ++hf) {
+          // S_l of this half's tiles and of the adjacent tile of the other half
+          const int j_lo = hf ? HN - 1 : 0, j_hi = hf ? n - 1 : HN;
+          for (int j = j_lo; j <= j_hi; ++j)
+            if (!mbar_wait(bar_tile + 8 * j, (uint32_t)l & 1u)) goto mma_exit;
+          tc_fence_after();
+          uint32_t acc = c2 ? 1u : 0u;
+          uint32_t a_tap = a_buf + (uint32_t)(hf * HN * kTileM);
+          for (int tap = 0; tap < a.k; tap += TPS) {
+            if (!mbar_wait(bar_full + 8 * s, ph)) goto mma_exit;
+            tc_fence_after();
+            uint32_t b_lo = b_lo0 + s * stage_units;
+#pragma unroll
+            for (int tt = 0; tt < TPS; ++tt) {
+              if (tap + tt < a.k) {
+                uint32_t a_lo = a_tap;
+#pragma unroll
+                for (int kk = 0; kk < kkn; ++kk) {
+#pragma unroll
+                  for (int j = 0; j < HN; ++j)
+                    tc_mma_bf16_lohi(d_tmem + (uint32_t)((hf * HN + j) * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, id, acc);
+                  acc = 1u;
+                  a_lo += 2u * (uint32_t)k.rows_pad;
+                  b_lo += 2u * (uint32_t)C;
+                }
+                a_tap += (uint32_t)d;
+              }
+            }
+            tc_commit(bar_empty + 8 * s);
+            if (++s == nstage) { s = 0; ph ^= 1u; }
+          }
+          tc_commit(bar_accf + 8 * hf);
+        }
+      }
+    mma_exit:;
+    }
+    __syncwarp();
+  } else {
+    // ===== load / epilogue warps =====
+    const int q = warp & 3, h = warp >> 2;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const float slope = a.slope;
+    constexpr int CPW = C / 32;  // 16-column chunks per warp and tile
+    // load, two tiles' worth of global loads in flight, one "tile written" arrival per tile:
+    // x -> X (TMEM, fp32) and S_0 = bf16(lrelu(x)) -> OP[0]
+#pragma unroll
+    for (int jt0 = 0; jt0 < n; jt0 += 2) {
+      float4 v[2][CPW][4];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int t = t_in0 + (jt0 + jj) * kTileM + q * 32 + lane;
+        const bool inb = t >= 0 && t < a.T;
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c0 = (ci * 2 + h) * 16;
+          const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+#pragma unroll
+          for (int w = 0; w < 4; ++w) v[jj][ci][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int jt = jt0 + jj;
+        const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
+        const bool inb = t >= 0 && t < a.T;
+#pragma unroll
+        for (int ci = 0; ci < CPW; ++ci) {
+          const int c0 = (ci * 2 + h) * 16;
+          float f[16];
+          uint32_t bits[16];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            f[4 * w] = v[jj][ci][w].x; f[4 * w + 1] = v[jj][ci][w].y; f[4 * w + 2] = v[jj][ci][w].z; f[4 * w + 3] = v[jj][ci][w].w;
+          }
+#pragma unroll
+          for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
+          tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
+          store_operand<false>(op0, k.rows_pad, k.P + r, c0, f, slope, inb);
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
+      }
+    }
+
+    bool alive = true;
+    for (int l = 0; l < L && alive; ++l) {
+      const int m = l >> 1, c2 = l & 1;
+      const bool last = (l == L - 1);
+      const float* bias = c2 ? bsm + (kRbMaxPairs + m) * C : bsm + m * C;  // cb_m for X, b1_m for ACC
+      const uint32_t src_tmem = c2 ? tmem_x : tmem_acc;
+      uint8_t* dst_op = op0 + (size_t)((l + 1) & 1) * op_bytes;
+      for (int hf = 0; hf < 2 && alive; ++hf) {
+        alive = mbar_wait_warp(bar_accf + 8 * hf, (uint32_t)l & 1u);
+        if (!alive) break;
+        tc_fence_after();
+#pragma unroll
+        for (int jj = 0; jj < HN; ++jj) {
+          const int jt = hf * HN + jj;
+          const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
+          if (!last) {
+            // S_(l+1) = bf16 / half (lrelu(acc + bias)), zero outside the sequence
+            uint32_t v[2][16];
+            tmem_ld_32x16(src_tmem + lane_sel + (uint32_t)(jt * C + h * 16), v[0]);
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) {
+              const int c0 = (ci * 2 + h) * 16;
+              tmem_ld_wait();
+              if (ci + 1 < CPW) tmem_ld_32x16(src_tmem + lane_sel + (uint32_t)(jt * C + ((ci + 1) * 2 + h) * 16), v[(ci + 1) & 1]);
+              float f[16];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * u);
+                f[4 * u] = __uint_as_float(v[ci & 1][4 * u]) + bq.x;
+                f[4 * u + 1] = __uint_as_float(v[ci & 1][4 * u + 1]) + bq.y;
+                f[4 * u + 2] = __uint_as_float(v[ci & 1][4 * u + 2]) + bq.z;
+                f[4 * u + 3] = __uint_as_float(v[ci & 1][4 * u + 3]) + bq.w;
+              }
+              if (c2) store_operand<false>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+              else store_operand<H16>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
+          } else {
+            // final: y = [y +] out_scale * (X + cb_last) for the central V rows
+            const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+            float4 yq[CPW][4];
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) {
+              const int c0 = (ci * 2 + h) * 16;
+              const float4* src = reinterpret_cast<const float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+#pragma unroll
+              for (int w = 0; w < 4; ++w) yq[ci][w] = (valid && a.accumulate) ? src[w * ws4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int ci = 0; ci < CPW; ++ci) {
+              const int c0 = (ci * 2 + h) * 16;
+              uint32_t v[16];
+              tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), v);
+              tmem_ld_wait();
+              if (valid) {
+                float4* dst = reinterpret_cast<float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * w);
+                  float4 o;
+                  o.x = (__uint_as_float(v[4 * w]) + bq.x) * a.out_scale + yq[ci][w].x;
+                  o.y = (__uint_as_float(v[4 * w + 1]) + bq.y) * a.out_scale + yq[ci][w].y;
+                  o.z = (__uint_as_float(v[4 * w + 2]) + bq.z) * a.out_scale + yq[ci][w].z;
+                  o.w = (__uint_as_float(v[4 * w + 3]) + bq.w) * a.out_scale + yq[ci][w].w;
+                  dst[w * ws4] = o;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+done:
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWorkWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 constexpr size_t kSmemBudget = 224 * 1024;
 
 struct RbPlan {
   int ntile, halo, V, P, rows_pad, stages, kc;
+  bool pipe;  // software-pipelined kernel (two operand buffers)
   size_t smem;
 };
 
@@ -438,13 +727,15 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
   if (C == 64 && k <= 3) ntile = 2;  // same trade at C = 64: 1.37 -> 1.13 ms for the k = 3 ResBlock of stage 3
   if (forced > 0) ntile = std::min(forced, 256 / C);
   const int kc = tc_kchunk(C);
-  const size_t stage_bytes = (size_t)kc * C * 2;
-  const size_t tail = sizeof(float) * 2 * kRbMaxPairs * C + sizeof(uint64_t) * kNumBars + 16;
+  const size_t stage_bytes = (size_t)(C == 32 ? 4 : (C == 64 ? 2 : 1)) * kc * C * 2;  // TPS taps per stage, as in the kernels
   const int min_tile = C == 32 ? 4 : (C == 64 ? 2 : 1);  // instantiated kernels: see RB_LAUNCH
   for (; ntile >= min_tile; ntile >>= 1) {
     const int R = kTileM * ntile;
     const int rows_pad = R + 2 * P;
-    const size_t opb = ((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127;
+    static const bool pipe_env = [] { const char* e = std::getenv("NVSE_RB_PIPE"); return !(e && e[0] == '0'); }();
+    const bool pipe = pipe_env && C <= 64 && k >= 5 && ntile == 4;  // measured: -3..-9 % from k = 5 up, a loss at k = 3
+    const size_t opb = (pipe ? 2 : 1) * (((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127);
+    const size_t tail = sizeof(float) * 2 * kRbMaxPairs * C + sizeof(uint64_t) * (pipe ? kPipeBars : kNumBars) + 16;
     if (R - 2 * halo < 32) return false;  // not enough useful rows per tile: per-layer kernels do better
     if (opb + 2 * stage_bytes + tail > kSmemBudget) continue;
     static const int max_stages = [] { const char* e = std::getenv("NVSE_RB_STAGES"); return e ? std::atoi(e) : kMaxStages; }();
@@ -453,9 +744,11 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
     // shared memory it takes is L1 that the load / final phases' global accesses need for misses in flight
     // (measured: C = 256 pairs 0.47 -> 0.41 ms (k = 3) with 3 stages, C = 128 pairs 0.89 -> 0.78 ms with 4)
     if (C >= 128) stages = std::min(stages, C == 256 ? 3 : 4);
+    if (C <= 64) stages = std::min(stages, std::min(max_stages, pipe ? 3 : 4));  // stages hold 2-4 taps: a few are enough
     // keep two CTAs per SM resident when tensor memory allows it (2 * ntile * C <= 256 columns)
     if (2 * ntile * C <= 256)
       while (stages > 2 && opb + stages * stage_bytes + tail > 110 * 1024) --stages;
+    p->pipe = pipe;
     p->ntile = ntile; p->halo = halo; p->V = R - 2 * halo; p->P = P; p->rows_pad = rows_pad;
     p->stages = stages; p->kc = kc;
     p->smem = opb + stages * stage_bytes + tail;
@@ -521,10 +814,17 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
     NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_tc_kernel<CC, NN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
     resblock_tc_kernel<CC, NN, SP><<<grid, kThreads, p.smem, st>>>(k);                                                      \
   } else
+#define RB_LAUNCH_PIPE(CC, NN, SP)                                                                                          \
+  if (p.pipe && a.C == CC && p.ntile == NN && (a.h_fp16 != 0) == SP) {                                                      \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_pipe_kernel<CC, NN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    resblock_pipe_kernel<CC, NN, SP><<<grid, kThreads, p.smem, st>>>(k);                                                    \
+  } else
+  RB_LAUNCH_PIPE(32, 4, false) RB_LAUNCH_PIPE(32, 4, true) RB_LAUNCH_PIPE(64, 4, false) RB_LAUNCH_PIPE(64, 4, true) RB_LAUNCH_PIPE(64, 2, false)
   RB_LAUNCH(32, 4, false) RB_LAUNCH(32, 4, true) RB_LAUNCH(32, 8, false) RB_LAUNCH(64, 4, false) RB_LAUNCH(64, 4, true)
   RB_LAUNCH(64, 2, false) RB_LAUNCH(128, 2, false) RB_LAUNCH(128, 1, false) RB_LAUNCH(256, 1, false)
   return fail(NVSE_ERR_UNSUPPORTED, "fused resblock: no kernel for C=%d with %d tiles", a.C, p.ntile);
 #undef RB_LAUNCH
+#undef RB_LAUNCH_PIPE
   NVSE_LAUNCH_CHECK("resblock_tc_kernel");
   return NVSE_OK;
 }
