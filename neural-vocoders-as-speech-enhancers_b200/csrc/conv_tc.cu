@@ -158,10 +158,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
           const float f[8] = {lrelu(f0[u].x, s), lrelu(f0[u].y, s), lrelu(f0[u].z, s), lrelu(f0[u].w, s),
                               lrelu(f1[u].x, s), lrelu(f1[u].y, s), lrelu(f1[u].z, s), lrelu(f1[u].w, s)};
           uint4 v;
-          v.x = pack_bf16(f[0], f[1]);
-          v.y = pack_bf16(f[2], f[3]);
-          v.z = pack_bf16(f[4], f[5]);
-          v.w = pack_bf16(f[6], f[7]);
+          if (a.ops_f16) {
+            v.x = pack_f16(f[0], f[1]);
+            v.y = pack_f16(f[2], f[3]);
+            v.z = pack_f16(f[4], f[5]);
+            v.w = pack_f16(f[6], f[7]);
+          } else {
+            v.x = pack_bf16(f[0], f[1]);
+            v.y = pack_bf16(f[2], f[3]);
+            v.z = pack_bf16(f[4], f[5]);
+            v.w = pack_bf16(f[6], f[7]);
+          }
           *reinterpret_cast<uint4*>(act + dst[u]) = v;
           if (split) {  // residual of the first rounding, itself rounded to bf16: ~16 mantissa bits in total
             uint4 lo;
@@ -204,7 +211,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
   } else if (warp == kEpiWarps + 1) {
     // ===== MMA issuer: one elected thread, a few instructions between consecutive MMAs =====
     if (elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      // operand formats: bits 7 / 10 set = bf16, clear = IEEE half
+      const uint32_t idesc = (1u << 4) | (a.ops_f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(act), (uint32_t)k.rows_pad * 16u);  // advances in rows (16-byte units)
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(wst), (uint32_t)Cout * 16u);
       const uint32_t hi = umma_desc_hi(128u);
@@ -372,6 +380,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   NVSE_REQUIRE(!(a.out_bf16 && (a.residual || a.accumulate)), NVSE_ERR_INVALID, "tensor-core conv: bf16 output takes no residual");
   NVSE_REQUIRE(!(a.split_act && a.in_bf16), NVSE_ERR_INVALID, "tensor-core conv: split activations need fp32 input");
   NVSE_REQUIRE(!(a.x_t32 && a.in_bf16) && !(a.y_t32 && a.out_bf16), NVSE_ERR_INVALID, "tensor-core conv: the T32 layout is fp32 only");
+  NVSE_REQUIRE(!(a.ops_f16 && (a.in_bf16 || a.split_act)), NVSE_ERR_INVALID, "tensor-core conv: half operands need fp32 input and no split");
   if (B == 0 || a.Trows <= 0) return NVSE_OK;
   KernelArgs k;
   k.a = a;
@@ -415,7 +424,9 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   int stages = (int)std::min<size_t>((budget - act_bytes - tail) / stage_bytes, (size_t)4);
   stages = std::max(2, std::min(stages, std::max(2, n_iters)));
   // more resident CTAs per SM beat a deeper weight ring: one CTA's staging / epilogue overlaps another's MMAs
-  while (stages > 2 && act_bytes + stages * stage_bytes + tail > 56 * 1024) --stages;
+  // (only where that is attainable: a tile that is > 56 KB by itself keeps its 4-stage ring)
+  if (act_bytes + 2 * stage_bytes + tail <= 56 * 1024)
+    while (stages > 2 && act_bytes + stages * stage_bytes + tail > 56 * 1024) --stages;
   k.stages = stages;
   const size_t smem = act_bytes + stages * stage_bytes + tail;
   dim3 grid((unsigned)((a.Trows + kTileM * ntile - 1) / (kTileM * ntile)), (unsigned)B);

@@ -36,6 +36,8 @@ struct ConvTcArgs {
   float in_slope, out_slope, out_scale;
   int accumulate;
   int split_act;          // stage activations as hi + lo bf16 planes (fp32 input only): 2 MMAs per K step
+  int ops_f16;            // stage the (fp32) activations as IEEE half; `wimg` must then be a half image.  Used by the
+                          // upsamplers, where bf16 rounding of the WEIGHTS is the largest error of the whole path
 };
 
 // shared memory one CTA of the kernel needs for this shape (used to decide whether split fits)

@@ -117,12 +117,13 @@ static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B
       }
       ConvTcArgs a{};
       a.x = x; a.x_bstride = (x_t32 ? t32_rows(Tin) : Tin) * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout;
-      a.wimg = reinterpret_cast<const __nv_bfloat16*>(L.w_bf16); a.bias = L.bias;
+      a.wimg = reinterpret_cast<const __nv_bfloat16*>(L.tc_f16 ? L.w_f16 : L.w_bf16); a.bias = L.bias;
+      a.ops_f16 = L.tc_f16;
       a.y = y; a.y_bstride = (y_t32 ? t32_rows(Tout) : Tout) * L.Cout; a.Tout = (int)Tout;
       a.x_t32 = x_t32; a.y_t32 = y_t32;
       a.out_mul = L.stride; a.Trows = (int)((Tout - r0 + L.stride - 1) / L.stride);
       a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
-      a.split_act = L.tc_split;
+      a.split_act = L.tc_split && !L.tc_f16;
       if (int rc = launch_conv_tc_phases(a, taps, out_add, n, B, st)) return rc;
     }
     return NVSE_OK;
@@ -286,7 +287,12 @@ int finalize_bf16(nvse_generator* g, cudaStream_t st) {
     // upsamplers: 3 % of the FLOPs; the <= 32-channel MRF stage: HBM-bound anyway) activations are
     // fed as hi + lo bf16 pairs (tools/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
     if (L.transposed) {
-      L.tc_split = tc_split_fits(L.Cin, L.Cout, (L.k + L.stride - 1) / L.stride);  // all phases share one tile
+      // upsamplers: IEEE-half activations AND weights.  tools/bf16_budget.py: bf16 rounding of the ups weights
+      // is the largest single error of the bf16 path (42.7 dB de-meaned SNR; hi+lo split activations with bf16
+      // weights 46.1 dB; half operands 54.3 dB) -- and half costs one MMA per step where the split cost two.
+      L.tc_f16 = true;
+      if (!L.w_f16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_f16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
+      if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_f16), L.Cin, L.Cout, L.k, st, true)) return rc;
     } else {
       L.tc_split = L.Cout <= 32 && tc_split_fits(L.Cin, L.Cout, (L.k - 1) * L.dilation);
     }

@@ -18,6 +18,7 @@ struct Layer {
   void* w_bf16 = nullptr;  // tensor-core weight image (see conv_tc.cuh), null for fp32-only layers
   void* w_f16 = nullptr;   // the same image in IEEE half: second conv of a ResBlock1 pair at C <= 32 (resblock_tc.cuh h_fp16)
   bool tc_split = false;   // activations as hi+lo bf16 pairs on the tensor-core path (accuracy)
+  bool tc_f16 = false;     // IEEE-half operands (w_f16) on the tensor-core path: the upsamplers
   bool have_w = false, have_bias = false;
 };
 

@@ -56,8 +56,10 @@ extern "C" int nvse_conv_transpose1d_bf16(const float* x, const float* w, const 
   Scratch wk(st), img(st);
   NVSE_CUDA_CHECK(wk.alloc(sizeof(float) * (size_t)Cin * Cout * k));
   NVSE_CUDA_CHECK(img.alloc(sizeof(__nv_bfloat16) * (size_t)Cin * Cout * k));
+  const char* f16env = std::getenv("NVSE_TC_F16");  // tests: IEEE-half operands, as the generator runs its upsamplers
+  const bool f16 = f16env && f16env[0] != '0';
   if (int rc = launch_repack_weight(w, (float*)wk.p, Cin, Cout, k, true, st)) return rc;
-  if (int rc = launch_pack_weight_tc((const float*)wk.p, (__nv_bfloat16*)img.p, Cin, Cout, k, st)) return rc;
+  if (int rc = launch_pack_weight_tc((const float*)wk.p, (__nv_bfloat16*)img.p, Cin, Cout, k, st, f16)) return rc;
   const int nph = (int)std::min<int64_t>(stride, Tout);
   for (int r0 = 0; r0 < nph; r0 += kTcMaxPhases) {
     const int n = std::min(kTcMaxPhases, nph - r0);
@@ -74,6 +76,7 @@ extern "C" int nvse_conv_transpose1d_bf16(const float* x, const float* w, const 
     a.y = y; a.y_bstride = Tout * Cout; a.Tout = (int)Tout;
     a.out_mul = stride; a.Trows = (int)((Tout - r0 + stride - 1) / stride);
     a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
+    a.ops_f16 = f16;
     if (int rc = launch_conv_tc_phases(a, taps, out_add, n, B, st)) return rc;
   }
   return NVSE_OK;

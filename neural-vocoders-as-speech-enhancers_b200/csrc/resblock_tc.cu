@@ -71,8 +71,7 @@ __device__ __forceinline__ void store_operand(uint8_t* op, int rows_pad, int bro
   for (int i = 0; i < 8; ++i) {
     const float a0 = keep ? lrelu(f[2 * i], slope) : 0.f, a1 = keep ? lrelu(f[2 * i + 1], slope) : 0.f;
     if (F16) {
-      const __half2 h = __floats2half2_rn(fminf(fmaxf(a0, -65504.f), 65504.f), fminf(fmaxf(a1, -65504.f), 65504.f));
-      hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+      hi[i] = pack_f16(a0, a1);
     } else {
       hi[i] = pack_bf16(a0, a1);
     }

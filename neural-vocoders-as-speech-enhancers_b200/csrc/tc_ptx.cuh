@@ -2,6 +2,8 @@
 // (TMEM alloc / mma / commit / ld) and the UMMA shared-memory descriptor.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace nvse {
@@ -112,6 +114,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// two floats -> packed IEEE half, saturated to the finite range
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ float lrelu(float v, float s) { return v >= 0.0f ? v : v * s; }
 // the two bf16 halves of a packed word, widened back to fp32 (exact)

@@ -269,6 +269,21 @@ def test_conv_transpose1d_tensor_core_matches_torch_on_bf16_operands(cin, cout, 
     assert torch.allclose(out, ref, atol=3e-5, rtol=1e-5), float((out - ref).abs().max())
 
 
+@pytest.mark.parametrize("cin,cout,k,u,T,B", [(512, 256, 16, 8, 9, 2), (256, 128, 16, 8, 140, 1), (128, 64, 4, 2, 130, 2),
+                                             (64, 32, 4, 2, 257, 1)])
+def test_conv_transpose1d_tensor_core_half_operands(monkeypatch, cin, cout, k, u, T, B):
+    """The upsamplers of the generator run with IEEE-half operands (NVSE_TC_F16): exact products of the
+    half-rounded operands, fp32 accumulation."""
+    monkeypatch.setenv("NVSE_TC_F16", "1")
+    f16 = lambda v: v.to(torch.float16).to(torch.float32)
+    x, w, b = _rand((B, cin, T), 26), _rand((cin, cout, k), 27, 1.0 / np.sqrt(cin * 2)), _rand((cout,), 28)
+    ref = F.conv_transpose1d(f16(F.leaky_relu(x, 0.1)), f16(w), b, stride=u, padding=(k - u) // 2)
+    out = conv_transpose1d_cl(x, w, b, u, (k - u) // 2, in_slope=0.1, tc=True)
+    assert not lib_mod.tc_abort_status()
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, atol=3e-5, rtol=1e-5), float((out - ref).abs().max())
+
+
 def test_weight_norm_fold_both_layouts():
     lib = lib_mod.load()
     for shape in [(256, 256, 11), (512, 256, 16), (1, 32, 7)]:  # Conv1d [Cout,Cin,k]; ConvT [Cin,Cout,k]: dim 0 either way
