@@ -183,7 +183,8 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
         single = (v < 0.0 || single < 0.0) ? -1.0 : single + v;
       }
       if (whole < 0.0 && single < 0.0) t32 = false;
-      int per = (single < 0.0 || (whole >= 0.0 && whole <= single)) ? nd : 1;
+      // C <= 64: the whole block always (measured); above, the cost model decides, then the measured overrides below
+      int per = (single < 0.0 || (whole >= 0.0 && (whole <= single || l0.Cin <= 64))) ? nd : 1;
       // measured (tools/rb_bench.py, C = 128, 32 x 55168 rows): the pipelined pair kernel beats the whole-block
       // launch from k = 5 up (k = 7: 3 x 0.86 ms vs 2.9 ms), the two-CTA whole-block launch wins at k = 3
       static const bool pairpipe_plan = [] { const char* e = std::getenv("NVSE_PAIRPIPE"); return !(e && e[0] == '0'); }();

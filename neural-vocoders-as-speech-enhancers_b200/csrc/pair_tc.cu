@@ -185,10 +185,9 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
   } else if (warp >= kEpiWarps + 2) {
     // ===== loader warps: x tile -> lrelu -> bf16 -> OP[i & 1] =====
     const int lw = warp - (kEpiWarps + 2);
-    constexpr int UNITS = R * nchunk;                      // (row, 8-channel chunk) units of one tile
-    constexpr int PER_THREAD = UNITS / (kLoadWarps * 32);  // 32 for C = 128, NT = 2
-    constexpr int UB = 8;                                  // units in flight per thread (16 LDG.128)
-    static_assert(PER_THREAD % UB == 0, "tile does not divide over the loader threads");
+    constexpr int UB = 8;  // (row, 8-channel chunk) units in flight per thread (16 LDG.128)
+    const int rows_all = R + 2 * k.P;  // the tile and the P rows of context on either side that c1 reads
+    const int units = rows_all * nchunk;
     for (int i = 0; i < my_items; ++i) {
       const int b = i & 1;
       const int item = (int)blockIdx.x + i * (int)gridDim.x;
@@ -200,14 +199,14 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
       if (i >= 2 && !wait_warp(bar_op_free + 8 * b, (uint32_t)((i >> 1) - 1) & 1u)) break;  // c2(i-2) has read OP[b]
       if (lw == 0) PT_STAMP(2);
 #pragma unroll 1
-      for (int g = 0; g < PER_THREAD / UB; ++g) {
+      for (int e0 = lw * 32 + lane; e0 < units; e0 += UB * kLoadWarps * 32) {
         float4 f0[UB], f1[UB];
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-          const int e = (g * UB + u) * (kLoadWarps * 32) + lw * 32 + lane;
-          const int chunk = e / R, r = e - chunk * R, t = t_in0 + r;
+          const int e = e0 + u * (kLoadWarps * 32);
+          const int chunk = e / rows_all, orow = e - chunk * rows_all, t = t_in0 + orow - k.P;
           f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (t >= 0 && t < a.T) {
+          if (e < units && t >= 0 && t < a.T) {
             const float4* src = reinterpret_cast<const float4*>(xb + t32_off(t, chunk * 8, C));
             f0[u] = __ldg(src);
             f1[u] = __ldg(src + 32);
@@ -215,14 +214,15 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
         }
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
-          const int e = (g * UB + u) * (kLoadWarps * 32) + lw * 32 + lane;
-          const int chunk = e / R, r = e - chunk * R;
+          const int e = e0 + u * (kLoadWarps * 32);
+          if (e >= units) continue;
+          const int chunk = e / rows_all, orow = e - chunk * rows_all;
           uint4 v;
           v.x = pack_bf16(lrelu(f0[u].x, slope), lrelu(f0[u].y, slope));
           v.y = pack_bf16(lrelu(f0[u].z, slope), lrelu(f0[u].w, slope));
           v.z = pack_bf16(lrelu(f1[u].x, slope), lrelu(f1[u].y, slope));
           v.w = pack_bf16(lrelu(f1[u].z, slope), lrelu(f1[u].w, slope));
-          *reinterpret_cast<uint4*>(op + ((size_t)chunk * k.rows_pad + k.P + r) * 16) = v;
+          *reinterpret_cast<uint4*>(op + ((size_t)chunk * k.rows_pad + orow) * 16) = v;
         }
       }
       fence_proxy_async_smem();
@@ -341,7 +341,8 @@ struct PairPlan {
 bool make_pair_plan(int C, int k, int dil, PairPlan* p) {
   if (C != 128 || k < 1 || !(k & 1) || k > kMaxTaps || dil < 1) return false;
   const int NT = 2, R = kTileM * NT;
-  const int halo = (k - 1) / 2 * (dil + 1), P = (k - 1) / 2 * dil;
+  // c1 reads its context (P rows on either side of the tile) from global memory: only c2 costs halo
+  const int halo = (k - 1) / 2, P = (k - 1) / 2 * dil;
   if (R - 2 * halo < 64) return false;
   const int rows_pad = R + 2 * P;
   const size_t opb = ((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127;

@@ -48,7 +48,9 @@ struct RbKernelArgs {
   int ntile;     // 128-row tiles per CTA
   int halo;      // rows of context the chain consumes on each side
   int V;         // 128 * ntile - 2 * halo: output rows one CTA produces
-  int P;         // zero rows on each side of the operand buffer (largest conv padding)
+  int P;         // rows on each side of the operand buffer beyond the tile (largest conv padding)
+  int P0;        // padding of the FIRST conv: that many rows beyond the tile on either side are loaded from
+                 // global memory (real data), so the first conv costs no halo
   int rows_pad;  // operand buffer rows per 8-channel chunk (P + R + P)
   int stages, kc;
   int sm_count;
@@ -246,6 +248,26 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
         if (r >= k.halo && r < R - k.halo && t < a.T)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + b * bstride + (a.t32 ? t32_off(t, ((i % CPW) * 2 + h) * 16, C) : (int64_t)t * C + ((i % CPW) * 2 + h) * 16)));
+      }
+    }
+    // Rows just outside the tile that the FIRST conv reads: real data (zero outside the sequence) instead of
+    // stale rows -- the first conv is then valid on the whole tile and the chain's halo excludes its padding.
+    {
+      const int n2 = 2 * k.P0;
+      for (int e = (warp * 32 + lane); e < n2 * nchunk; e += kWorkWarps * 32) {
+        const int chunk = e / n2, i = e - chunk * n2;
+        const int orow = i < k.P0 ? k.P - k.P0 + i : k.P + R + (i - k.P0);  // operand-buffer row
+        const int t = t_in0 + orow - k.P;
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0 && t < a.T) {
+          const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, chunk * 8, C) : (int64_t)t * C + chunk * 8));
+          const float4 f0 = __ldg(src), f1 = __ldg(src + ws4);
+          pk.x = pack_bf16(lrelu(f0.x, slope), lrelu(f0.y, slope));
+          pk.y = pack_bf16(lrelu(f0.z, slope), lrelu(f0.w, slope));
+          pk.z = pack_bf16(lrelu(f1.x, slope), lrelu(f1.y, slope));
+          pk.w = pack_bf16(lrelu(f1.z, slope), lrelu(f1.w, slope));
+        }
+        *reinterpret_cast<uint4*>(op + ((size_t)chunk * k.rows_pad + orow) * 16) = pk;
       }
     }
     // load: x -> X (TMEM, fp32) and OP = bf16(lrelu(x))
@@ -574,6 +596,26 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const float slope = a.slope;
     constexpr int CPW = C / 32;  // 16-column chunks per warp and tile
+    // Rows just outside the tile that the FIRST conv reads: real data (zero outside the sequence) instead of
+    // stale rows -- the first conv is then valid on the whole tile and the chain's halo excludes its padding.
+    {
+      const int n2 = 2 * k.P0;
+      for (int e = (warp * 32 + lane); e < n2 * nchunk; e += kWorkWarps * 32) {
+        const int chunk = e / n2, i = e - chunk * n2;
+        const int orow = i < k.P0 ? k.P - k.P0 + i : k.P + R + (i - k.P0);  // operand-buffer row
+        const int t = t_in0 + orow - k.P;
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        if (t >= 0 && t < a.T) {
+          const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, chunk * 8, C) : (int64_t)t * C + chunk * 8));
+          const float4 f0 = __ldg(src), f1 = __ldg(src + ws4);
+          pk.x = pack_bf16(lrelu(f0.x, slope), lrelu(f0.y, slope));
+          pk.y = pack_bf16(lrelu(f0.z, slope), lrelu(f0.w, slope));
+          pk.z = pack_bf16(lrelu(f1.x, slope), lrelu(f1.y, slope));
+          pk.w = pack_bf16(lrelu(f1.z, slope), lrelu(f1.w, slope));
+        }
+        *reinterpret_cast<uint4*>(op0 + ((size_t)chunk * k.rows_pad + orow) * 16) = pk;
+      }
+    }
     // load, two tiles' worth of global loads in flight, one "tile written" arrival per tile:
     // x -> X (TMEM, fp32) and S_0 = bf16(lrelu(x)) -> OP[0]
 #pragma unroll
@@ -703,7 +745,7 @@ done:
 constexpr size_t kSmemBudget = 224 * 1024;
 
 struct RbPlan {
-  int ntile, halo, V, P, rows_pad, stages, kc;
+  int ntile, halo, V, P, P0, rows_pad, stages, kc;
   bool pipe;  // software-pipelined kernel (two operand buffers)
   size_t smem;
 };
@@ -718,6 +760,8 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
     halo += (k - 1) / 2 * dil[m] + (k - 1) / 2;
     P = std::max(P, (k - 1) / 2 * dil[m]);
   }
+  const int P0 = (k - 1) / 2 * dil[0];
+  halo -= P0;  // the first conv reads its context from global memory (kernel: "rows just outside the tile")
   static const int forced = [] { const char* e = std::getenv("NVSE_RB_NTILE"); return e ? std::atoi(e) : 0; }();
   int ntile = std::min(C <= 64 ? 4 : 8, 256 / C);
   // C = 128, whole k = 3 ResBlock: one tile per CTA lets two CTAs share an SM (TMEM 256 columns each), and
@@ -748,7 +792,7 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
     if (2 * ntile * C <= 256)
       while (stages > 2 && opb + stages * stage_bytes + tail > 110 * 1024) --stages;
     p->pipe = pipe;
-    p->ntile = ntile; p->halo = halo; p->V = R - 2 * halo; p->P = P; p->rows_pad = rows_pad;
+    p->ntile = ntile; p->halo = halo; p->V = R - 2 * halo; p->P = P; p->P0 = P0; p->rows_pad = rows_pad;
     p->stages = stages; p->kc = kc;
     p->smem = opb + stages * stage_bytes + tail;
     return true;
@@ -803,7 +847,7 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   k.sm_count = sm_count;
   static const int dbg = [] { const char* e = std::getenv("NVSE_RB_DBG"); return e ? std::atoi(e) : 0; }();
   k.dbg = dbg;
-  k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
+  k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.P0 = p.P0; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
   dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
   const double rows = (double)B * a.T;
   ProfScope prof("resblock_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0 * a.npairs,

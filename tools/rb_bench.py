@@ -13,7 +13,7 @@ from util import lib_mod, stream_ptr  # noqa: E402
 Cc, k, T, B = (int(v) for v in sys.argv[1:5])
 npairs = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 iters = int(sys.argv[6]) if len(sys.argv) > 6 else 5
-dils = [1, 3, 5][:npairs]
+dils = [int(v) for v in os.environ["RB_DILS"].split(",")] if "RB_DILS" in os.environ else [1, 3, 5][:npairs]
 dev = "cuda:0"
 lib = lib_mod.load()
 x = torch.randn((B, T, Cc), device=dev)
