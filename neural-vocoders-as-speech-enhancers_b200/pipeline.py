@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 
 from .dataset import mel_spectrogram
+from .shard import bucket_by_length
 
 
 class Vocoder:
@@ -47,3 +48,16 @@ class Vocoder:
                 out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=torch.float32, pin_memory=True)
             out_host[s:s + y.shape[0]].copy_(y, non_blocking=True)
         return out_host
+
+    @torch.no_grad()
+    def run_list(self, wavs):
+        """Ragged input: a list of 1-D float32 waveforms (CPU or device) -> list of 1-D CPU waveforms,
+        in the input order.  Utterances are grouped by exact length (``bucket_by_length``), so no
+        padding is involved and each result equals the single-utterance result; empty list -> []."""
+        outs = [None] * len(wavs)
+        for group in bucket_by_length([int(w.shape[-1]) for w in wavs], self.micro_batch):
+            batch = torch.stack([wavs[i].reshape(-1).to(torch.float32) for i in group]).to(self.device, non_blocking=True)
+            y = self.generator(self.mel(batch)).reshape(len(group), -1).cpu()
+            for j, i in enumerate(group):
+                outs[i] = y[j]
+        return outs

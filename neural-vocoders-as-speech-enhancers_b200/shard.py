@@ -32,3 +32,20 @@ def shard_by_cost(costs: Sequence[float], world_size: int) -> List[List[int]]:
     for b in bins:
         b.sort()
     return bins
+
+
+def bucket_by_length(lengths: Sequence[int], max_batch: int) -> List[List[int]]:
+    """Ragged utterances on ONE GPU: groups of utterances of exactly equal length, at most
+    ``max_batch`` each, longest first.  Equal-length groups need no padding, so every utterance
+    comes out bit-identical to vocoding it alone (the reference's loop, infers/inference_hifigan.py:67),
+    whereas padding would change the last receptive field of the shorter ones."""
+    if max_batch < 1:
+        raise ValueError("max_batch must be >= 1")
+    by_len = {}
+    for i, n in enumerate(lengths):
+        by_len.setdefault(int(n), []).append(i)
+    out: List[List[int]] = []
+    for n in sorted(by_len, reverse=True):
+        idx = by_len[n]
+        out += [idx[s:s + max_batch] for s in range(0, len(idx), max_batch)]
+    return out

@@ -426,3 +426,20 @@ def test_full_size_cfg3_fp32_vs_bf16_and_torch():
     report(f"cfg3-shape (4 x 690 frames, init weights seed 1234): fp32 max-abs {float((o32 - ref).abs().max()):.2e}; "
            f"bf16 SNR {snr:.1f} dB (de-meaned), raw {np_oracle.snr_db(ref.cpu().numpy(), o16.cpu().numpy(), False):.1f} dB")
     assert snr >= 40.0
+
+
+def test_vocoder_run_list_ragged_matches_single_utterance_runs():
+    """Ragged utterances (and the empty list): grouped by exact length, each result identical to
+    vocoding that utterance alone, as the reference's per-file loop does."""
+    cfg = synth.HIFIGAN_V1
+    gen = build_generator(cfg, synth.make_state(cfg, 5, "init"), DEV, remove_wn=True)
+    gen.precision = "bf16"
+    voc = pkg.Vocoder(gen, synth.AttrDict(cfg), micro_batch=2, device=DEV)
+    assert voc.run_list([]) == []
+    lens = [3000, 1537, 3000, 2048, 1537, 3000]
+    wavs = [torch.from_numpy(synth.make_wave(1, n, 40 + i)[0]) for i, n in enumerate(lens)]
+    outs = voc.run_list(wavs)
+    assert [o.numel() for o in outs] == [(1 + n // cfg["hop_size"]) * cfg["hop_size"] for n in lens]
+    for w, o in zip(wavs, outs):
+        alone = voc.run_list([w])[0]
+        assert torch.equal(o, alone)

@@ -32,6 +32,18 @@ def test_shard_by_cost_balances_ragged_lengths():
     assert bins == pkg.shard_by_cost(costs, 4)  # deterministic
 
 
+def test_bucket_by_length_groups_equal_lengths_only():
+    lengths = [22050, 4000, 22050, 4000, 4000, 513, 22050, 4000]
+    groups = pkg.bucket_by_length(lengths, 2)
+    assert sorted(i for g in groups for i in g) == list(range(len(lengths)))
+    for g in groups:
+        assert len(g) <= 2 and len({lengths[i] for i in g}) == 1
+    assert [lengths[g[0]] for g in groups] == sorted((lengths[g[0]] for g in groups), reverse=True)
+    assert pkg.bucket_by_length([], 4) == []
+    with pytest.raises(ValueError):
+        pkg.bucket_by_length([1], 0)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
