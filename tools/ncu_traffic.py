@@ -14,7 +14,7 @@ def to_bytes(v, u):
 per_kernel, tot, n = {}, 0.0, 0
 for r in data:
     name = r[ix["Kernel Name"]]
-    if not any(s in name for s in ("resblock_tc", "pair_tc", "conv_tc")):
+    if not any(s in name for s in ("resblock_", "pair_tc", "conv_tc")):
         continue
     # ncu scales units per row in the raw page: re-read them from the per-row unit columns when present
     rd = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
