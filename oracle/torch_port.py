@@ -95,4 +95,4 @@ def istftnet_forward(folded, cfg, mel):
     hop = int(cfg["gen_istft_hop_size"])
     nb = n_fft // 2 + 1
     spec = torch.exp(x[:, :nb]) * torch.exp(1j * torch.sin(x[:, nb:]))
-    return torch.istft(spec, n_fft, hop, n_fft, window=torch.hann_window(n_fft))
+    return torch.istft(spec, n_fft, hop, n_fft, window=torch.hann_window(n_fft, device=spec.device))

@@ -428,6 +428,48 @@ def test_full_size_cfg3_fp32_vs_bf16_and_torch():
     assert snr >= 40.0
 
 
+@pytest.mark.parametrize("seed", [1234, 7, 99])
+def test_full_size_cfg4_istftnet_fp32_vs_bf16_and_torch(seed):
+    """BASELINE cfg4 shape at reduced batch (iSTFTNet, 4 x 8 s, F = 690) and the seeds SURVEY 8(d) names:
+    fp32 path vs PyTorch fp32 ops (max-abs <= 1e-4), 16-bit tensor-core path SNR >= 40 dB."""
+    from oracle import torch_port
+    cfg = synth.ISTFTNET
+    state = synth.make_state(cfg, seed, "init")
+    gen = build_generator(cfg, state, DEV, True)
+    mel = torch.from_numpy(synth.make_mel(4, 690, 30 + seed % 5)).to(DEV)
+    folded = {k: v.to(DEV) for k, v in torch_port.fold_state(state).items()}
+    with torch.no_grad():
+        ref = torch_port.istftnet_forward(folded, cfg, mel)
+        gen.precision = "fp32"
+        o32 = gen(mel)
+        gen.precision = "bf16"
+        o16 = gen(mel)
+    assert o32.reshape(4, -1).shape == (4, 176640)
+    assert float((o32.reshape(4, -1) - ref.reshape(4, -1)).abs().max()) <= 1e-4
+    snr = np_oracle.snr_db(ref.reshape(4, -1).cpu().numpy(), o16.reshape(4, -1).cpu().numpy())
+    report(f"cfg4-shape iSTFTNet (4 x 690 frames, init weights seed {seed}): fp32 max-abs "
+           f"{float((o32.reshape(4, -1) - ref.reshape(4, -1)).abs().max()):.2e}; 16-bit path SNR {snr:.1f} dB (de-meaned)")
+    assert snr >= 40.0
+
+
+@pytest.mark.parametrize("seed", [7, 99])
+def test_full_size_cfg3_other_seeds_bf16_snr(seed):
+    """cfg3 shape, the other weight seeds of SURVEY 8(d) (99 was the worst bf16 case of the survey's probe)."""
+    from oracle import torch_port
+    cfg = synth.HIFIGAN_V1
+    state = synth.make_state(cfg, seed, "init")
+    gen = build_generator(cfg, state, DEV, True)
+    mel = torch.from_numpy(synth.make_mel(2, 690, 31)).to(DEV)
+    folded = {k: v.to(DEV) for k, v in torch_port.fold_state(state).items()}
+    with torch.no_grad():
+        ref = torch_port.hifigan_forward(folded, cfg, mel)
+        gen.precision = "bf16"
+        o16 = gen(mel)
+    snr = np_oracle.snr_db(ref.cpu().numpy(), o16.cpu().numpy())
+    report(f"cfg3-shape (2 x 690 frames, init weights seed {seed}): 16-bit path SNR {snr:.1f} dB (de-meaned)")
+    assert snr >= 40.0
+
+
 def test_vocoder_run_list_ragged_matches_single_utterance_runs():
     """Ragged utterances (and the empty list): grouped by exact length, each result identical to
     vocoding that utterance alone, as the reference's per-file loop does."""
