@@ -55,9 +55,10 @@ constexpr int kStageUnroll = 4;  // independent 32-byte loads in flight per thre
 
 // KK (16-channel MMA steps per weight stage), the tile count and the split flag are compile-time so that the
 // MMA issue loop unrolls completely (an MMA issued from a loop with run-time trip counts costs more issue
-// cycles than the tensor core needs to execute it: tools/probe/mma_probe3.cu).
-template <int KK, int NT, bool SPLIT>
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ KernelArgs k) {
+// cycles than the tensor core needs to execute it: tools/probe/mma_probe3.cu).  MINB = resident CTAs per SM
+// the register budget is set for: 3 for the small memory-bound tiles, 1 where shared memory allows one CTA.
+template <int KK, int NT, bool SPLIT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_constant__ KernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const ConvTcArgs& a = k.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -436,14 +437,17 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
                          nphase * (a.Cout * (a.out_bf16 ? 2.0 : 4.0) * (a.accumulate ? 2.0 : 1.0) + (a.residual ? 4.0 * a.Cout : 0.0))),
                  st);
   const bool sp = a.split_act != 0;
-#define TC_LAUNCH(KKV, NTV, SPV)                                                                                          \
-  if (k.kc == 16 * KKV && ntile == NTV && sp == SPV) {                                                                    \
-    NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<KKV, NTV, SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
-    conv_tc_kernel<KKV, NTV, SPV><<<grid, kThreads, smem, st>>>(k);                                                       \
+  const bool small = smem <= 72 * 1024;  // three CTAs of this size fit an SM
+#define TC_LAUNCH(KKV, NTV, SPV, MB)                                                                                      \
+  if (k.kc == 16 * KKV && ntile == NTV && sp == SPV && small == (MB == 3)) {                                              \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<KKV, NTV, SPV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); \
+    conv_tc_kernel<KKV, NTV, SPV, MB><<<grid, kThreads, smem, st>>>(k);                                                   \
   } else
-  TC_LAUNCH(2, 1, false) TC_LAUNCH(2, 2, false) TC_LAUNCH(2, 4, false) TC_LAUNCH(4, 1, false) TC_LAUNCH(4, 2, false) TC_LAUNCH(4, 4, false)
-  TC_LAUNCH(2, 1, true) TC_LAUNCH(2, 2, true) TC_LAUNCH(2, 4, true) TC_LAUNCH(4, 1, true) TC_LAUNCH(4, 2, true) TC_LAUNCH(4, 4, true)
+#define TC_LAUNCH2(KKV, NTV, SPV) TC_LAUNCH(KKV, NTV, SPV, 1) TC_LAUNCH(KKV, NTV, SPV, 3)
+  TC_LAUNCH2(2, 1, false) TC_LAUNCH2(2, 2, false) TC_LAUNCH2(2, 4, false) TC_LAUNCH2(4, 1, false) TC_LAUNCH2(4, 2, false) TC_LAUNCH2(4, 4, false)
+  TC_LAUNCH2(2, 1, true) TC_LAUNCH2(2, 2, true) TC_LAUNCH2(2, 4, true) TC_LAUNCH2(4, 1, true) TC_LAUNCH2(4, 2, true) TC_LAUNCH2(4, 4, true)
   return fail(NVSE_ERR_UNSUPPORTED, "tensor-core conv: no kernel for kc=%d ntile=%d", k.kc, ntile);
+#undef TC_LAUNCH2
 #undef TC_LAUNCH
   NVSE_LAUNCH_CHECK("conv_tc_kernel");
   return NVSE_OK;
