@@ -241,15 +241,6 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     constexpr int IT = n * CPW;          // items per warp
     constexpr int UMAX = (2 * NT * C <= 256) ? 2 : 4;  // two resident CTAs: half the registers each
     constexpr int U = IT < UMAX ? IT : UMAX;           // items in flight (U * 64 bytes per thread)
-    if (a.accumulate) {
-      // the rows of y the final phase will read: pull them into L2 while the chain runs
-#pragma unroll
-      for (int i = 0; i < IT; ++i) {
-        const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
-        if (r >= k.halo && r < R - k.halo && t < a.T)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + b * bstride + (a.t32 ? t32_off(t, ((i % CPW) * 2 + h) * 16, C) : (int64_t)t * C + ((i % CPW) * 2 + h) * 16)));
-      }
-    }
     // Rows just outside the tile that the FIRST conv reads: real data (zero outside the sequence) instead of
     // stale rows -- the first conv is then valid on the whole tile and the chain's halo excludes its padding.
     {
@@ -517,6 +508,9 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_x = tmem_base, tmem_acc = tmem_base + (uint32_t)(n * C);
+  const bool tracing = k.trace != nullptr && blockIdx.x == 3 && blockIdx.y == gridDim.y / 2 && lane == 0;
+  int tr_i = 0;
+#define RP_STAMP(role) do { if (tracing && tr_i < 60) k.trace[(role) * 64 + tr_i++] = clock64(); } while (0)
 
   if (warp == kWorkWarps) {
     // ===== weight producer: every conv's stages twice (half A, half B) =====
@@ -559,6 +553,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
           for (int j = j_lo; j <= j_hi; ++j)
             if (!mbar_wait(bar_tile + 8 * j, (uint32_t)l & 1u)) goto mma_exit;
           tc_fence_after();
+          RP_STAMP(0);
           uint32_t acc = c2 ? 1u : 0u;
           uint32_t a_tap = a_buf + (uint32_t)(hf * HN * kTileM);
           for (int tap = 0; tap < a.k; tap += TPS) {
@@ -585,6 +580,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
             if (++s == nstage) { s = 0; ph ^= 1u; }
           }
           tc_commit(bar_accf + 8 * hf);
+          RP_STAMP(0);
         }
       }
     mma_exit:;
@@ -596,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const float slope = a.slope;
     constexpr int CPW = C / 32;  // 16-column chunks per warp and tile
+    if (warp == 0) RP_STAMP(1);
     // Rows just outside the tile that the FIRST conv reads: real data (zero outside the sequence) instead of
     // stale rows -- the first conv is then valid on the whole tile and the chain's halo excludes its padding.
     {
@@ -660,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
       }
     }
 
+    if (warp == 0) RP_STAMP(1);
     bool alive = true;
     for (int l = 0; l < L && alive; ++l) {
       const int m = l >> 1, c2 = l & 1;
@@ -671,6 +669,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         alive = mbar_wait_warp(bar_accf + 8 * hf, (uint32_t)l & 1u);
         if (!alive) break;
         tc_fence_after();
+        if (warp == 0) RP_STAMP(1);
 #pragma unroll
         for (int jj = 0; jj < HN; ++jj) {
           const int jt = hf * HN + jj;
@@ -737,6 +736,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     }
   }
 done:
+  if (warp == 0) RP_STAMP(1);
   tc_fence_before();
   __syncthreads();
   if (warp == kWorkWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
