@@ -254,6 +254,8 @@ def main():
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": workload, "weights": "random-init (reference-like N(0,0.01), seed 1234), weight_norm folded",
                    "l2": "inputs larger than L2 (113 MB waveforms, GB-scale activations per step)",
+                   "operands": "16-bit tensor-core path: bf16 MRF convs, IEEE-half upsamplers and C<=32 second convs, fp32 accumulate, "
+                               "fp32 residual stream / conv_pre / conv_post" if args.precision == "bf16" else "fp32 CUDA-core path",
                    "frames_per_utt": frames, "flop_per_step_per_gpu": FLOP_PER_FRAME * frames * U},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(U * T * 4), "d2h_bytes_per_step": int(U * t_out * 4),
