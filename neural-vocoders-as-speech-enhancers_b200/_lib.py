@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnvse_b200.so")
+# NVSE_LIB: an alternative build of the same library (same-box A/B timing of kernel variants, tools/ab_build.sh)
+LIB_PATH = os.environ.get("NVSE_LIB") or os.path.join(_HERE, "csrc", "libnvse_b200.so")
 
 NVSE_OK = 0
 PRECISION_F32, PRECISION_BF16 = 0, 1

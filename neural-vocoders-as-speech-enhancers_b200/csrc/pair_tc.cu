@@ -27,7 +27,13 @@ namespace {
 
 using namespace tc;
 
-constexpr int kEpiWarps = 8, kLoadWarps = 4;
+#ifndef NVSE_PAIR_LOADWARPS
+#define NVSE_PAIR_LOADWARPS 4
+#endif
+#ifndef NVSE_PAIR_FINAL_U
+#define NVSE_PAIR_FINAL_U 2
+#endif
+constexpr int kEpiWarps = 8, kLoadWarps = NVSE_PAIR_LOADWARPS;
 constexpr int kThreads = (kEpiWarps + 2 + kLoadWarps) * 32;
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
     // ===== epilogue warps =====
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    constexpr int CPW = C / 32, IT = NT * CPW, U = IT < 2 ? IT : 2;
+    constexpr int CPW = C / 32, IT = NT * CPW, U = IT < NVSE_PAIR_FINAL_U ? IT : NVSE_PAIR_FINAL_U;
     const float* b1 = bsm;
     const float* b2 = bsm + C;
     for (int i = 0; i < my_items; ++i) {
