@@ -39,14 +39,40 @@ class Vocoder:
     @torch.no_grad()
     def run_host(self, wav_host, out_host=None):
         """wav_host: [U, T] float32 CPU tensor (pinned for async copies).  Returns (and fills, if
-        given) a CPU tensor [U, T_out].  The caller synchronises the current stream."""
+        given) a CPU tensor [U, T_out].  Copies run on two side streams so that the host -> device copy
+        of micro-batch i+1 and the device -> host copy of micro-batch i-1 overlap the kernels of
+        micro-batch i; the caller synchronises the current stream (all side-stream work is joined to it)."""
         dev = self.device
-        for s in range(0, wav_host.shape[0], self.micro_batch):
-            chunk = wav_host[s:s + self.micro_batch].to(dev, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h2d"):
+            self._h2d, self._d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self._h2d.wait_stream(cur)
+        self._d2h.wait_stream(cur)
+        starts = list(range(0, wav_host.shape[0], self.micro_batch))
+
+        def upload(s):
+            with torch.cuda.stream(self._h2d):
+                chunk = wav_host[s:s + self.micro_batch].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._h2d)
+            return chunk, ev
+
+        nxt = upload(starts[0]) if starts else None
+        for i, s in enumerate(starts):
+            chunk, ev = nxt
+            nxt = upload(starts[i + 1]) if i + 1 < len(starts) else None
+            cur.wait_event(ev)
+            chunk.record_stream(cur)
             y = self.generator(self.mel(chunk))
             if out_host is None:
                 out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=torch.float32, pin_memory=True)
-            out_host[s:s + y.shape[0]].copy_(y, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(done)
+                y.record_stream(self._d2h)
+                out_host[s:s + y.shape[0]].copy_(y, non_blocking=True)
+        cur.wait_stream(self._d2h)
         return out_host
 
     @torch.no_grad()

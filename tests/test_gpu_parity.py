@@ -485,3 +485,18 @@ def test_vocoder_run_list_ragged_matches_single_utterance_runs():
     for w, o in zip(wavs, outs):
         alone = voc.run_list([w])[0]
         assert torch.equal(o, alone)
+
+
+def test_vocoder_run_host_overlapped_copies_match_device_run():
+    """Host-buffer pipeline (copies on side streams, overlapped with the kernels): identical to the
+    device-resident run, with an utterance count that is not a multiple of the micro-batch."""
+    cfg = synth.HIFIGAN_V1
+    gen = build_generator(cfg, synth.make_state(cfg, 6, "init"), DEV, remove_wn=True)
+    gen.precision = "bf16"
+    voc = pkg.Vocoder(gen, synth.AttrDict(cfg), micro_batch=2, device=DEV)
+    wav = torch.from_numpy(synth.make_wave(5, 2816, 77)).pin_memory()
+    ref = voc.run_device(wav.to(DEV)).cpu()
+    for _ in range(2):  # second pass reuses the side streams
+        out = voc.run_host(wav)
+        torch.cuda.synchronize()
+        assert tuple(out.shape) == (5, 12 * 256) and torch.equal(out.reshape(5, -1), ref.reshape(5, -1))
