@@ -54,7 +54,6 @@ struct RbKernelArgs {
   int rows_pad;  // operand buffer rows per 8-channel chunk (P + R + P)
   int stages, kc;
   int sm_count;
-  int dbg;  // experiments (NVSE_RB_DBG bitmask): 1 = the weight producer starts after the load phase
   long long* trace;  // debug: clock64 stamps of one CTA's phase boundaries (NVSE_RB_TRACE), else null
 };
 
@@ -153,7 +152,6 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     if (lane == 0) {
       const uint32_t nstage = (uint32_t)k.stages;
       uint32_t s = 0, ph = 1;
-      if ((k.dbg & 1) && !mbar_wait(bar_op, 0)) goto done;
       for (int m = 0; m < npairs; ++m)
         for (int half = 0; half < 2; ++half) {
           const __nv_bfloat16* wimg = half ? a.pair[m].w2 : a.pair[m].w1;
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
         const bool inb = t >= 0 && t < a.T;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) v[u][w] = (inb && !(k.dbg & 16)) ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < 4; ++w) v[u][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -286,8 +284,8 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         }
 #pragma unroll
         for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
-        if (!(k.dbg & 4)) tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
-        if (!(k.dbg & 8)) store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+        tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
+        store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
       }
     }
     tmem_st_wait();
@@ -845,8 +843,6 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   k.trace = trace_buffer();
   static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
   k.sm_count = sm_count;
-  static const int dbg = [] { const char* e = std::getenv("NVSE_RB_DBG"); return e ? std::atoi(e) : 0; }();
-  k.dbg = dbg;
   k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.P0 = p.P0; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
   dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
   const double rows = (double)B * a.T;
