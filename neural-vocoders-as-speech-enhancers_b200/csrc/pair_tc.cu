@@ -51,7 +51,7 @@ __device__ __forceinline__ bool wait_warp(uint32_t bar, uint32_t parity) {
   return __all_sync(0xffffffffu, ok);
 }
 
-template <int C, int NT>
+template <int C, int NT, bool ACCUM>
 __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_constant__ PairKernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const ResblockTcArgs& a = k.a;
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
     // ===== epilogue warps =====
     const int q = warp & 3, h = warp >> 2;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    constexpr int CPW = C / 32, IT = NT * CPW, U = IT < NVSE_PAIR_FINAL_U ? IT : NVSE_PAIR_FINAL_U;
+    // items of the final phase in flight: without the accumulate read the registers of yq go to a deeper batch of x
+    constexpr int CPW = C / 32, IT = NT * CPW, UF = ACCUM ? NVSE_PAIR_FINAL_U : 2 * NVSE_PAIR_FINAL_U, U = IT < UF ? IT : UF;
     const float* b1 = bsm;
     const float* b2 = bsm + C;
     for (int i = 0; i < my_items; ++i) {
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
       bool alive = true;
 #pragma unroll
       for (int i0 = 0; i0 < IT; i0 += U) {
-        float4 xq[U][4], yq[U][4];
+        float4 xq[U][4], yq[ACCUM ? U : 1][4];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int it = i0 + u, c0 = ((it % CPW) * 2 + h) * 16;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             xq[u][w] = valid ? __ldg(reinterpret_cast<const float4*>(a.x + off) + w * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-            yq[u][w] = (valid && a.accumulate) ? reinterpret_cast<const float4*>(a.y + off)[w * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ACCUM) yq[u][w] = valid ? reinterpret_cast<const float4*>(a.y + off)[w * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         if (i0 == 0) {
@@ -315,10 +316,10 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
             for (int w = 0; w < 4; ++w) {
               const float4 bq = *reinterpret_cast<const float4*>(b2 + c0 + 4 * w);
               float4 o;
-              o.x = (__uint_as_float(v[4 * w]) + bq.x + xq[u][w].x) * a.out_scale + yq[u][w].x;
-              o.y = (__uint_as_float(v[4 * w + 1]) + bq.y + xq[u][w].y) * a.out_scale + yq[u][w].y;
-              o.z = (__uint_as_float(v[4 * w + 2]) + bq.z + xq[u][w].z) * a.out_scale + yq[u][w].z;
-              o.w = (__uint_as_float(v[4 * w + 3]) + bq.w + xq[u][w].w) * a.out_scale + yq[u][w].w;
+              o.x = (__uint_as_float(v[4 * w]) + bq.x + xq[u][w].x) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].x : 0.f);
+              o.y = (__uint_as_float(v[4 * w + 1]) + bq.y + xq[u][w].y) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].y : 0.f);
+              o.z = (__uint_as_float(v[4 * w + 2]) + bq.z + xq[u][w].z) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].z : 0.f);
+              o.w = (__uint_as_float(v[4 * w + 3]) + bq.w + xq[u][w].w) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].w : 0.f);
               dst[w * 32] = o;
             }
           }
@@ -389,8 +390,13 @@ int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   const unsigned grid = (unsigned)std::min<int64_t>(n_items, sm_count);
   const double rows = (double)B * a.T;
   ProfScope prof("pair_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0, rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
-  NVSE_CUDA_CHECK(cudaFuncSetAttribute(pair_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-  pair_tc_kernel<128, 2><<<grid, kThreads, p.smem, st>>>(k);
+  if (a.accumulate) {
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(pair_tc_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    pair_tc_kernel<128, 2, true><<<grid, kThreads, p.smem, st>>>(k);
+  } else {
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(pair_tc_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+    pair_tc_kernel<128, 2, false><<<grid, kThreads, p.smem, st>>>(k);
+  }
   NVSE_LAUNCH_CHECK("pair_tc_kernel");
   return NVSE_OK;
 }
