@@ -141,6 +141,11 @@ NVSE_API int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t
  * w[r,:] = g[r] * v[r,:] / ||v[r,:]||_2,  v: [rows, cols]. */
 NVSE_API int nvse_weight_norm_fold_f32(const float* v, const float* g, float* w, int64_t rows, int64_t cols, void* stream);
 
+/* Float waveform -> PCM_16 samples exactly as the reference's output step writes them
+ * (sf.write(path, audio, sr, 'PCM_16'), infers/inference_hifigan.py:93-95: libsndfile's lrint(x * 0x7FFF)),
+ * so a host pipeline copies half the bytes back.  x, y: device pointers, n samples. */
+NVSE_API int nvse_pcm16_from_f32(const float* x, int16_t* y, int64_t n, void* stream);
+
 /* [B, C, T] -> [B, T, C] and back (module-boundary layout changes). */
 NVSE_API int nvse_transpose_bct_to_btc_f32(const float* x, float* y, int64_t B, int64_t C, int64_t T, void* stream);
 NVSE_API int nvse_transpose_btc_to_bct_f32(const float* x, float* y, int64_t B, int64_t T, int64_t C, void* stream);

@@ -144,6 +144,24 @@ int launch_relayout_t32(const float* x, float* y, int64_t B, int64_t T, int C, b
   return NVSE_OK;
 }
 
+namespace {
+// float waveform -> PCM_16 as libsndfile writes it for the reference (sf.write(..., 'PCM_16'),
+// infers/inference_hifigan.py:93): lrint(x * 0x7FFF), clipped to the int16 range
+__global__ void __launch_bounds__(256) pcm16_kernel(const float* __restrict__ x, int16_t* __restrict__ y, int64_t n) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(x[e] * 32767.0f, -32768.0f), 32767.0f);
+    y[e] = (int16_t)__float2int_rn(v);
+  }
+}
+}  // namespace
+
+int launch_pcm16(const float* x, int16_t* y, int64_t n, cudaStream_t st) {
+  if (n == 0) return NVSE_OK;
+  pcm16_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(x, y, n);
+  NVSE_LAUNCH_CHECK("pcm16_kernel");
+  return NVSE_OK;
+}
+
 int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st) {
   if (B == 0 || R == 0 || C == 0) return NVSE_OK;
   NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "transpose: batch %lld exceeds 65535", (long long)B);
@@ -211,6 +229,12 @@ extern "C" int nvse_weight_norm_fold_f32(const float* v, const float* g, float* 
   weight_norm_fold_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(v, g, w, cols);
   NVSE_LAUNCH_CHECK("weight_norm_fold_kernel");
   return NVSE_OK;
+}
+
+extern "C" int nvse_pcm16_from_f32(const float* x, int16_t* y, int64_t n, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(n >= 0 && (n == 0 || (x && y)), NVSE_ERR_INVALID, "nvse_pcm16_from_f32: bad argument");
+  return launch_pcm16(x, y, n, as_stream(stream));
 }
 
 extern "C" int nvse_transpose_bct_to_btc_f32(const float* x, float* y, int64_t B, int64_t C, int64_t T, void* stream) {

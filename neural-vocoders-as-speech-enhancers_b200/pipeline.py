@@ -7,8 +7,11 @@ through in micro-batches: pinned host -> device copy, fused front-end kernel, ge
 device -> pinned host copy, all stream-ordered with no synchronisation inside the loop."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
+from . import _lib
 from .dataset import mel_spectrogram
 from .shard import bucket_by_length
 
@@ -36,10 +39,19 @@ class Vocoder:
                 outs.append(y)
         return out_dev if out_dev is not None else torch.cat(outs, 0)
 
+    def pcm16(self, y):
+        """Device float waveform -> int16 PCM as the reference's sf.write(..., 'PCM_16') stores it
+        (infers/inference_hifigan.py:93): round(x * 32767), clipped."""
+        y = y.contiguous()
+        out = torch.empty(y.shape, dtype=torch.int16, device=y.device)
+        st = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        _lib.check(_lib.load().nvse_pcm16_from_f32(_lib.ptr(y), _lib.ptr(out), y.numel(), st))
+        return out
+
     @torch.no_grad()
-    def run_host(self, wav_host, out_host=None):
+    def run_host(self, wav_host, out_host=None, pcm16=False):
         """wav_host: [U, T] float32 CPU tensor (pinned for async copies).  Returns (and fills, if
-        given) a CPU tensor [U, T_out].  Copies run on two side streams so that the host -> device copy
+        given) a CPU tensor [U, T_out] (int16 PCM with ``pcm16=True``).  Copies run on two side streams so that the host -> device copy
         of micro-batch i+1 and the device -> host copy of micro-batch i-1 overlap the kernels of
         micro-batch i; the caller synchronises the current stream (all side-stream work is joined to it)."""
         dev = self.device
@@ -64,8 +76,11 @@ class Vocoder:
             cur.wait_event(ev)
             chunk.record_stream(cur)
             y = self.generator(self.mel(chunk))
+            y = y.reshape(y.shape[0], -1)
+            if pcm16:  # quantise on the device: half the bytes cross PCIe
+                y = self.pcm16(y)
             if out_host is None:
-                out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=torch.float32, pin_memory=True)
+                out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=y.dtype, pin_memory=True)
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(self._d2h):

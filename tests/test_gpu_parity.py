@@ -500,3 +500,20 @@ def test_vocoder_run_host_overlapped_copies_match_device_run():
         out = voc.run_host(wav)
         torch.cuda.synchronize()
         assert tuple(out.shape) == (5, 12 * 256) and torch.equal(out.reshape(5, -1), ref.reshape(5, -1))
+
+
+def test_pcm16_output_matches_libsndfile_rule():
+    """sf.write(..., 'PCM_16') of the reference's inference script = lrint(x * 0x7FFF) (round half to even), clipped."""
+    x = torch.cat([torch.linspace(-1.2, 1.2, 100001), torch.tensor([0.5 / 32767, 1.5 / 32767, 2.5 / 32767, -0.5 / 32767, 0.0])]).to(DEV)
+    cfg = synth.HIFIGAN_V1
+    voc = pkg.Vocoder(None, synth.AttrDict(cfg), device=DEV)
+    got = voc.pcm16(x).cpu().numpy()
+    want = np.clip(np.rint(x.cpu().numpy().astype(np.float32) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    assert got.dtype == np.int16 and np.array_equal(got, want)
+    assert voc.pcm16(torch.empty(0, device=DEV)).numel() == 0
+    gen = build_generator(cfg, synth.make_state(cfg, 6, "init"), DEV, remove_wn=True)
+    voc = pkg.Vocoder(gen, synth.AttrDict(cfg), micro_batch=2, device=DEV)
+    wav = torch.from_numpy(synth.make_wave(3, 2816, 78)).pin_memory()
+    f = voc.run_host(wav); torch.cuda.synchronize()
+    q = voc.run_host(wav, pcm16=True); torch.cuda.synchronize()
+    assert q.dtype == torch.int16 and np.array_equal(q.numpy(), np.rint(f.numpy() * np.float32(32767.0)).astype(np.int16))
