@@ -84,10 +84,27 @@ class GeneratorEngine:
                 yield name, m
 
     def _key(self, module, dev):
-        parts = [dev.index]
-        for _, p in module.named_parameters():
-            parts.append((p.data_ptr(), p._version, p.device.type))
-        return tuple(parts)
+        """Identity of the weights the handle holds: (data_ptr, version) of every parameter.  Walking
+        ``named_parameters()`` costs ~0.5 ms per call (more than a batch-1 forward on the GPU), so the
+        list of Parameter objects is cached; it is rebuilt when the module's structure changed
+        (``remove_weight_norm`` / re-parametrisation swap Parameter objects: detected through the total
+        parameter count of the conv modules) and, as a backstop, every 256 calls."""
+        self._calls = getattr(self, "_calls", 0) + 1
+        plist = getattr(self, "_plist", None)
+        convs = getattr(self, "_convs", None)
+        if convs is not None and (self._calls & 255) != 0:
+            n = 0
+            for m in convs:
+                n += len(m._parameters)
+            if n != self._nparam:
+                plist = None
+        else:
+            plist = None
+        if plist is None:
+            self._convs = [m for _, m in self._conv_modules(module)]
+            self._nparam = sum(len(m._parameters) for m in self._convs)
+            plist = self._plist = list(module.parameters())
+        return (dev.index,) + tuple([(p.data_ptr(), p._version) for p in plist])
 
     def _ensure(self, module, dev):
         lib = _lib.load()
