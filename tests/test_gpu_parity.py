@@ -531,3 +531,25 @@ def test_generator_forward_is_deterministic_under_repetition():
         for _ in range(20):
             assert torch.equal(gen(mel), first)
     assert not lib_mod.tc_abort_status()
+
+
+@pytest.mark.parametrize("frames,batch", [(1, 1), (2, 3), (3, 2), (5, 1), (33, 2)])
+def test_tiny_inputs_through_the_fused_t32_path(frames, batch):
+    """Fewer rows than a 32-row T32 block / a 128-row tile at every stage: HiFi-GAN V1 and iSTFTNet, fp32
+    path against the PyTorch ops, 16-bit path SNR."""
+    from oracle import torch_port
+    for cfg, fwd in ((synth.HIFIGAN_V1, torch_port.hifigan_forward), (synth.ISTFTNET, torch_port.istftnet_forward)):
+        state = synth.make_state(cfg, 11, "unit")
+        gen = build_generator(cfg, state, DEV, True)
+        mel = torch.from_numpy(synth.make_mel(batch, frames, 50 + frames)).to(DEV)
+        folded = {k: v.to(DEV) for k, v in torch_port.fold_state(state).items()}
+        with torch.no_grad():
+            ref = fwd(folded, cfg, mel).reshape(batch, -1)
+            gen.precision = "fp32"
+            o32 = gen(mel).reshape(batch, -1)
+            gen.precision = "bf16"
+            o16 = gen(mel).reshape(batch, -1)
+        assert o32.shape == ref.shape == o16.shape
+        assert float((o32 - ref).abs().max()) <= 1e-4
+        assert np_oracle.snr_db(ref.cpu().numpy(), o16.cpu().numpy()) >= 40.0
+    assert not lib_mod.tc_abort_status()
