@@ -34,6 +34,7 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st);
 int launch_repack_weight(const float* src, float* dst, int Cin, int Cout, int k, bool transposed, cudaStream_t st);
 int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st);
 int launch_pcm16(const float* x, int16_t* y, int64_t n, cudaStream_t st);
+int launch_add3(float* a, const float* b, const float* c, int64_t n, cudaStream_t st);  // a = (a + b) + c
 // channels-last [B, T, C] <-> T32 layout (common.cuh)
 int launch_relayout_t32(const float* x, float* y, int64_t B, int64_t T, int C, bool to_t32, cudaStream_t st);
 void conv1d_taps(int k, int dilation, ConvTaps* taps);

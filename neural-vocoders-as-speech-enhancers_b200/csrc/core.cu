@@ -155,6 +155,30 @@ __global__ void __launch_bounds__(256) pcm16_kernel(const float* __restrict__ x,
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) add3_kernel(float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, int64_t n4) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    float4 va = reinterpret_cast<float4*>(a)[e];
+    const float4 vb = reinterpret_cast<const float4*>(b)[e];
+    va.x += vb.x; va.y += vb.y; va.z += vb.z; va.w += vb.w;
+    if (c) {
+      const float4 vc = reinterpret_cast<const float4*>(c)[e];
+      va.x += vc.x; va.y += vc.y; va.z += vc.z; va.w += vc.w;
+    }
+    reinterpret_cast<float4*>(a)[e] = va;
+  }
+}
+}  // namespace
+
+// a = (a + b) + c  (c may be null); n a multiple of 4, 16-byte aligned buffers
+int launch_add3(float* a, const float* b, const float* c, int64_t n, cudaStream_t st) {
+  if (n == 0) return NVSE_OK;
+  NVSE_REQUIRE(n % 4 == 0, NVSE_ERR_INVALID, "add3: length must be a multiple of 4");
+  add3_kernel<<<(unsigned)std::min<int64_t>((n / 4 + 255) / 256, 148 * 8), 256, 0, st>>>(a, b, c, n / 4);
+  NVSE_LAUNCH_CHECK("add3_kernel");
+  return NVSE_OK;
+}
+
 int launch_pcm16(const float* x, int16_t* y, int64_t n, cudaStream_t st) {
   if (n == 0) return NVSE_OK;
   pcm16_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(x, y, n);

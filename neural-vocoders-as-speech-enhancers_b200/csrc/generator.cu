@@ -146,8 +146,20 @@ static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B
 // tc = false: fp32 CUDA cores everywhere.  tc = true: tcgen05 for the upsamplers and the MRF
 // convolutions (bf16 operands, fp32 accumulate, fp32 residual stream; the c1 -> c2 intermediate of
 // a ResBlock1 pair is stored activated, in bf16); conv_pre / conv_post stay fp32.
+// Small jobs (B * frames <= kConcurrentFrames): a ResBlock launch fills only a fraction of the SMs, and a forward
+// is a chain of ~25 dependent launches.  The ResBlocks of one MRF are independent, so they run concurrently on
+// the caller's stream and two side streams, each into its own buffer, and are summed afterwards.
+constexpr int64_t kConcurrentFrames = 1024;   // ~12 s of audio in total
+constexpr int64_t kConcurrentRows = 48 * 1024;  // per stage: B * T rows below which a launch is < 1 wave
+static int workspace_buffers(const nvse_generator* g, int64_t B, int64_t frames, int precision) {
+  static const bool on = [] { const char* e = std::getenv("NVSE_CONCURRENT"); return !(e && e[0] == '0'); }();
+  const bool small = on && precision == NVSE_PRECISION_BF16 && g->cfg.resblock_type == 1 && g->cfg.num_kernels >= 2 &&
+                     g->cfg.num_kernels <= 3 && B * frames <= kConcurrentFrames;
+  return small ? 12 : 4;
+}
+
 static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B, int64_t F, float* out, float* ws,
-                        int64_t buf_elems, cudaStream_t st) {
+                        int64_t buf_elems, int nbuf, cudaStream_t st) {
   const nvse_generator_config& c = g->cfg;
   float* bufA = ws;  // conv_pre output, then the MRF accumulator of every stage
   float* bufU = ws + buf_elems;
@@ -201,6 +213,17 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
     const Layer& up = g->layer("ups." + std::to_string(i));
     if (int rc = run_conv_transpose(up, tc, bufA, B, T, bufU, slope, st, t32 && i > 0, t32)) return rc;  // hifigan.py:111-112
     T = (T - 1) * up.stride - 2 * up.padding + up.k;
+    const bool stage_concurrent = t32 && nbuf >= 12 && B * T <= kConcurrentRows;
+    if (stage_concurrent) {
+      if (!g->ev_fork) {
+        NVSE_CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+        for (int q = 0; q < 2; ++q) {
+          NVSE_CUDA_CHECK(cudaStreamCreateWithFlags(&g->side[q], cudaStreamNonBlocking));
+          NVSE_CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_join[q], cudaEventDisableTiming));
+        }
+      }
+      NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
+    }
     const float inv = 1.0f / (float)c.num_kernels;  // hifigan.py:119
     for (int j = 0; j < c.num_kernels; ++j) {
       const std::string p = "resblocks." + std::to_string(i * c.num_kernels + j);
@@ -209,13 +232,20 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
       if (t32) {
         const int per = per_launch[(size_t)i * c.num_kernels + j];
         const Layer& l0 = g->layer(p + ".convs1.0");
+        // concurrent mode: ResBlock j on its own stream, with its own temporaries and its own output buffer
+        const bool conc = stage_concurrent;
+        cudaStream_t sj = (conc && j > 0) ? g->side[j - 1] : st;
+        float* tmpR = conc && j > 0 ? ws + (4 + 2 * j) * buf_elems : bufR;
+        float* tmpT = conc && j > 0 ? ws + (5 + 2 * j) * buf_elems : bufT;
+        float* outj = conc && j > 0 ? ws + (9 + j) * buf_elems : bufA;
+        if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
         for (int m0 = 0; m0 < nd; m0 += per) {
           const bool last = (m0 + per == nd);
-          float* dst = last ? bufA : (src == bufR ? bufT : bufR);
+          float* dst = last ? outj : (src == tmpR ? tmpT : tmpR);
           ResblockTcArgs ra{};
           ra.x = src; ra.y = dst; ra.T = (int)T; ra.C = l0.Cin; ra.k = l0.k; ra.npairs = per;
           ra.t32 = 1; ra.bstride = t32_rows(T) * l0.Cin;
-          ra.slope = slope; ra.out_scale = last ? inv : 1.0f; ra.accumulate = last && j > 0;
+          ra.slope = slope; ra.out_scale = last ? inv : 1.0f; ra.accumulate = last && j > 0 && !conc;
           ra.h_fp16 = l0.Cin <= 32;  // the c1 -> c2 intermediate and w2 in IEEE half (see finalize_bf16)
           for (int q = 0; q < per; ++q) {
             const Layer& c1 = g->layer(p + ".convs1." + std::to_string(m0 + q));
@@ -225,11 +255,18 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
           }
           static const bool pairpipe = [] { const char* e = std::getenv("NVSE_PAIRPIPE"); return !(e && e[0] == '0'); }();
           if (pairpipe && per == 1 && !ra.h_fp16 && pair_supported(ra.C, ra.k, ra.pair[0].dil)) {
-            if (int rc = launch_pair_tc(ra, B, st)) return rc;
-          } else if (int rc = launch_resblock_tc(ra, B, st)) {
+            if (int rc = launch_pair_tc(ra, B, sj)) return rc;
+          } else if (int rc = launch_resblock_tc(ra, B, sj)) {
             return rc;
           }
           src = dst;
+        }
+        if (conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
+        if (conc && j == c.num_kernels - 1) {  // join: bufA = (rb0 + rb1) + rb2, the order of the sequential path
+          for (int q = 1; q < c.num_kernels; ++q) NVSE_CUDA_CHECK(cudaStreamWaitEvent(st, g->ev_join[q - 1], 0));
+          if (int rc = launch_add3(bufA, ws + 10 * buf_elems, c.num_kernels > 2 ? ws + 11 * buf_elems : nullptr,
+                                   B * t32_rows(T) * l0.Cin, st))
+            return rc;
         }
         continue;
       }
@@ -343,6 +380,11 @@ extern "C" int nvse_generator_create(const nvse_generator_config* cfg, nvse_gene
 
 extern "C" int nvse_generator_destroy(nvse_generator* g) {
   if (!g) return NVSE_OK;
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  for (int q = 0; q < 2; ++q) {
+    if (g->ev_join[q]) cudaEventDestroy(g->ev_join[q]);
+    if (g->side[q]) cudaStreamDestroy(g->side[q]);
+  }
   for (Layer& L : g->layers) {
     cudaFree(L.w);
     cudaFree(L.bias);
@@ -406,8 +448,7 @@ extern "C" int64_t nvse_generator_out_samples(const nvse_generator* g, int64_t f
 extern "C" size_t nvse_generator_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames, int precision) {
   if (!g || B < 0 || frames < 0) return 0;
   const size_t buf = align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256);
-  (void)precision;  // both paths use the same four activation buffers
-  return 4 * buf + 256;
+  return (size_t)workspace_buffers(g, B, frames, precision) * buf + 256;
 }
 
 extern "C" int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
@@ -422,5 +463,6 @@ extern "C" int nvse_generator_forward(nvse_generator* g, const float* mel, int64
   NVSE_REQUIRE(max_activation_elems(g, frames) * 4 < (int64_t)1 << 40, NVSE_ERR_INVALID, "utterance too long");
   const int64_t buf_elems = (int64_t)(align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256) / sizeof(float));
   float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
-  return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, out, ws, buf_elems, as_stream(stream));
+  return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, out, ws, buf_elems,
+                      workspace_buffers(g, B, frames, precision), as_stream(stream));
 }

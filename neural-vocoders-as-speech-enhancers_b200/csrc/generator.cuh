@@ -29,6 +29,9 @@ struct nvse_generator {
   std::vector<nvse::Layer> layers;
   std::unordered_map<std::string, int> index;
   bool finalized = false;
+  // small-batch mode: the ResBlocks of a stage run concurrently on the caller's stream + two side streams
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   const nvse::Layer& layer(const std::string& name) const { return layers[index.at(name)]; }
 };
 
