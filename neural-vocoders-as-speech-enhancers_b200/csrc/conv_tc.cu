@@ -41,6 +41,7 @@ constexpr int kMaxPhases = 8;
 struct KernelArgs {
   ConvTcArgs a;
   int nphase;                      // output phases sharing one staged activation tile (ConvTranspose1d); 1 for Conv1d
+  int ph_per_cta;                  // phases one CTA computes (blockIdx.z selects the group): nphase, or fewer for small grids
   ConvTaps ptaps[kMaxPhases];      // tap list of each phase
   int pout_add[kMaxPhases];        // output row = out_mul * t + pout_add[phase]
   int ntile;       // 128-row M tiles per CTA: every weight stage feeds ntile MMAs (weight reuse from smem)
@@ -77,7 +78,9 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
   const uint32_t bar_accum = smem_u32(bars + 2 * kMaxStages), bar_tfree = smem_u32(bars + 2 * kMaxStages + 2);
-  const int nbuf = k.nphase > 1 ? 2 : 1;  // TMEM accumulator double-buffering across phases
+  const int ph_lo = (int)blockIdx.z * k.ph_per_cta;                                   // this CTA's phases
+  const int ph_n = k.nphase - ph_lo < k.ph_per_cta ? k.nphase - ph_lo : k.ph_per_cta;
+  const int nbuf = k.ph_per_cta > 1 ? 2 : 1;  // TMEM accumulator double-buffering across phases
   const uint32_t tmem_cols = (uint32_t)(Cout * nbuf * ntile) < 32u ? 32u : (uint32_t)(Cout * nbuf * ntile);  // power of two by construction
 
   if (tid == 0) {
@@ -97,10 +100,10 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
   //      into L2 now; staging + MMAs give the prefetch time to land ------------------------------
   if (warp < kEpiWarps && !a.out_bf16 && !a.y_t32 && (a.residual || a.accumulate)) {
     const int q = warp & 3, half = warp >> 2;
-    for (int ph = 0; ph < k.nphase; ++ph)
+    for (int ph = 0; ph < ph_n; ++ph)
       for (int j = 0; j < ntile; ++j) {
         const int t = t0 + j * kTileM + q * 32 + lane;
-        const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph];
+        const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph_lo + ph];
         if (t < a.Trows && orow < a.Tout) {
           const int64_t base = b * a.y_bstride + orow * Cout;
           for (int c = half * 32; c < Cout; c += 64) {  // one 128-byte line per 32 fp32 channels
@@ -194,8 +197,8 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
     // ===== weight producer: one bulk copy per (phase, tap, K chunk) stage =====
     if (lane == 0) {
       int it = 0;
-      for (int ph = 0; ph < k.nphase; ++ph) {
-        const ConvTaps& tp = k.ptaps[ph];
+      for (int ph = 0; ph < ph_n; ++ph) {
+        const ConvTaps& tp = k.ptaps[ph_lo + ph];
         for (int tap = 0; tap < tp.ntaps; ++tap) {
           const __nv_bfloat16* wsrc = a.wimg + (size_t)tp.widx[tap] * nkc * (stage_bytes / 2);
           for (int kc = 0; kc < nkc; ++kc, ++it) {
@@ -220,8 +223,8 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
       const uint32_t stage_units = stage_bytes >> 4, nstage = (uint32_t)k.stages, lo_plane = act_bytes >> 4;
       const uint32_t kc_rows = (uint32_t)(KK * 2) * (uint32_t)k.rows_pad;
       uint32_t s = 0, par = 0;
-      for (int ph = 0; ph < k.nphase; ++ph) {
-        const ConvTaps& tp = k.ptaps[ph];
+      for (int ph = 0; ph < ph_n; ++ph) {
+        const ConvTaps& tp = k.ptaps[ph_lo + ph];
         const int buf = ph & 1;
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ntile * Cout);
         if (ph >= 2) {  // the epilogue must have drained this accumulator (phase ph - 2)
@@ -259,13 +262,13 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
     // ===== epilogue warps: TMEM -> registers -> global =====
     const int quarter = warp & 3, chalf = warp >> 2;  // TMEM lane quarter; which 16-column chunks (even / odd)
     const int row = quarter * 32 + lane;
-    for (int ph = 0; ph < k.nphase; ++ph) {
+    for (int ph = 0; ph < ph_n; ++ph) {
       const int buf = ph & 1;
       if (!mbar_wait(bar_accum + 8 * buf, (ph >> 1) & 1)) break;
       tc_fence_after();
      for (int j = 0; j < ntile; ++j) {
       const int t = t0 + j * kTileM + row;
-      const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph];
+      const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph_lo + ph];
       const bool valid = t < a.Trows && orow < a.Tout;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * ntile + j) * Cout);
       for (int c0 = chalf * 16; c0 < Cout; c0 += 16 * (kEpiWarps / 4)) {
@@ -386,6 +389,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   KernelArgs k;
   k.a = a;
   k.nphase = nphase;
+  k.ph_per_cta = nphase;
   int mn = phase_taps[0].off[0], mx = mn, total_taps = 0;
   for (int p = 0; p < nphase; ++p) {
     NVSE_REQUIRE(phase_taps[p].ntaps >= 1 && phase_taps[p].ntaps <= kMaxTaps, NVSE_ERR_INVALID, "tensor-core conv: bad tap count");
@@ -431,6 +435,13 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   k.stages = stages;
   const size_t smem = act_bytes + stages * stage_bytes + tail;
   dim3 grid((unsigned)((a.Trows + kTileM * ntile - 1) / (kTileM * ntile)), (unsigned)B);
+  // Small grids (the batch-1 case): one phase per CTA, the phases of a tile on different SMs -- each CTA then
+  // streams 1 / nphase of the weights, which is what a few-CTA ConvTranspose1d launch is bound by.
+  static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+  if (nphase > 1 && (int64_t)grid.x * grid.y * nphase <= 2 * sm_count) {
+    k.ph_per_cta = 1;
+    grid.z = (unsigned)nphase;
+  }
   const double rows = (double)B * a.Trows;
   ProfScope prof("conv_tc", a.Cin, a.Cout, 2.0 * rows * a.Cin * a.Cout * total_taps,
                  rows * (a.Cin * (a.in_bf16 ? 2.0 : 4.0) +
