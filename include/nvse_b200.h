@@ -187,6 +187,41 @@ NVSE_API int nvse_conv_transpose1d_bf16(const float* x, const float* w, const fl
  * Supported: n_fft in {4..64} even, hop dividing n_fft. */
 NVSE_API int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, void* stream);
 
+/* ---- training path: backward of HiFiGAN.forward, fp32 ------------------
+ * Replaces what loss_gen_all.backward() runs through the generator in train_time_wi_inv.py:222-236
+ * (autograd over Models/hifigan.py:108-124).  Gradients are taken w.r.t. the FOLDED tensors loaded
+ * with nvse_generator_set_weight; weight_norm's own backward is nvse_weight_norm_backward_f32.
+ *
+ * forward_train = the fp32 forward, keeping the input of every convolution on the caller-owned `tape`
+ * (nvse_generator_tape_bytes).  backward consumes the tape, the forward's output and dL/dout [B, samples]
+ * and writes every layer's (dW, dbias) into the flat buffer `grads` (nvse_generator_grad_elems floats;
+ * nvse_generator_grad_offset maps "<layer>.weight" / "<layer>.bias" to its slice, PyTorch layouts), and
+ * dL/dmel [B, 80, frames] when dmel is not null.  Bit-reproducible (no atomics). */
+NVSE_API size_t nvse_generator_tape_bytes(const nvse_generator* g, int64_t B, int64_t frames);
+NVSE_API size_t nvse_generator_backward_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames);
+NVSE_API int64_t nvse_generator_grad_elems(const nvse_generator* g);
+NVSE_API int nvse_generator_grad_offset(const nvse_generator* g, const char* name, int64_t* offset, int64_t* numel);
+NVSE_API int nvse_generator_forward_train(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
+                                 void* tape, size_t tape_bytes, void* stream);
+NVSE_API int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frames, const float* out, const float* dout,
+                            const void* tape, size_t tape_bytes, float* grads, float* dmel, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Layer-level backward (channels-last fp32, the layouts of nvse_conv1d_f32 / nvse_conv_transpose1d_f32):
+ *   y = conv1d(lrelu(x, in_slope), w, dilation, "same") + bias [+ residual]
+ *   dx = lrelu'(x) * conv^T(dy) [+ dresidual_in],  dw [Cout,Cin,k],  dbias [Cout];  any of dx/dw/dbias may be null. */
+NVSE_API int nvse_conv1d_backward_f32(const float* x, const float* w, const float* dy, const float* dresidual_in,
+                             float* dx, float* dw, float* dbias, int64_t B, int64_t T, int Cin, int Cout, int k,
+                             int dilation, float in_slope, void* stream);
+/*   y = conv_transpose1d(lrelu(x, in_slope), w, stride, padding) + bias;  dy: [B, T_out, Cout];  dw [Cin,Cout,k] */
+NVSE_API int nvse_conv_transpose1d_backward_f32(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                                       float* dbias, int64_t B, int64_t T, int Cin, int Cout, int k, int stride,
+                                       int padding, float in_slope, void* stream);
+/* Backward of nvse_weight_norm_fold_f32:  dg[r] = <dw[r], v[r]> / ||v[r]||,
+ * dv[r] = g[r] / ||v[r]|| * (dw[r] - v[r] * <dw[r], v[r]> / ||v[r]||^2). */
+NVSE_API int nvse_weight_norm_backward_f32(const float* v, const float* g, const float* dw, float* dv, float* dg,
+                                  int64_t rows, int64_t cols, void* stream);
+
 /* The tensor-core kernels bound every mbarrier wait (a protocol bug must never hang the GPU); a
  * tripped timeout sets a device flag and later tensor-core launches return without computing.
  * *flag = 1 if it is set; reset != 0 clears it.  Synchronises the device. */

@@ -147,9 +147,8 @@ class GeneratorEngine:
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters()))):
-            raise NotImplementedError(
-                "the B200 generator implements inference only in this build; call it under torch.no_grad() "
-                "(backward kernels are scheduled next, SURVEY.md §8f)")
+            # training step (train_time_wi_inv.py:173-236): fp32 forward with a tape + the CUDA backward
+            return _GeneratorTrainFn.apply(self, module, x, *[p for _, p in module.named_parameters()])
         if x.is_cuda:
             dev = x.device
         else:
@@ -174,3 +173,97 @@ class GeneratorEngine:
             _lib.check(lib.nvse_generator_forward(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
                                                   _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
         return out if x.is_cuda else out.to(x.device)
+
+    # ---- training (fp32) -------------------------------------------------------------
+    def forward_train(self, module, x):
+        """fp32 forward that keeps every convolution input on a tape; returns (out, tape, xd)."""
+        if self.kind != _lib.GEN_HIFIGAN:
+            raise NotImplementedError("the B200 training path covers HiFiGAN; iSTFTNet's iSTFT head has no backward kernel yet")
+        if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
+            raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
+        if not x.is_cuda and not torch.cuda.is_available():
+            raise _lib.NvseError("the B200 generator needs a CUDA device: there is no CPU fallback")
+        dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        self._ensure(module, dev)
+        xd = x.detach().to(dev, torch.float32).contiguous()
+        batch, _, frames = xd.shape
+        if batch == 0 or frames == 0:
+            raise RuntimeError("empty batch on the training path")
+        out = torch.empty((batch, lib.nvse_generator_out_samples(self.handle, frames)), dtype=torch.float32, device=dev)
+        tape = torch.empty(lib.nvse_generator_tape_bytes(self.handle, batch, frames), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.nvse_generator_forward_train(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
+                                                        _lib.ptr(tape), tape.numel(), stream))
+        return out, tape
+
+    def backward(self, module, out, dout, tape, frames, want_dmel):
+        """-> (dict: folded tensor name -> gradient view, dmel or None)"""
+        lib = _lib.load()
+        dev = out.device
+        batch = out.shape[0]
+        grads = torch.empty(lib.nvse_generator_grad_elems(self.handle), dtype=torch.float32, device=dev)
+        dmel = torch.empty((batch, self.cfg.in_channels, frames), dtype=torch.float32, device=dev) if want_dmel else None
+        need = lib.nvse_generator_backward_workspace_bytes(self.handle, batch, frames)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        dout = dout.to(dev, torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.nvse_generator_backward(self.handle, batch, frames, _lib.ptr(out), _lib.ptr(dout), _lib.ptr(tape),
+                                                   tape.numel(), _lib.ptr(grads), _lib.ptr(dmel), _lib.ptr(ws), ws.numel(), stream))
+        views = {}
+        off, n = C.c_int64(), C.c_int64()
+        for name, m in self._conv_modules(module):
+            for leaf, shape in (("weight", tuple(m.weight.shape)), ("bias", tuple(m.bias.shape))):
+                _lib.check(lib.nvse_generator_grad_offset(self.handle, f"{name}.{leaf}".encode(), C.byref(off), C.byref(n)))
+                views[f"{name}.{leaf}"] = grads[off.value:off.value + n.value].view(shape)
+        return views, dmel
+
+
+class _GeneratorTrainFn(torch.autograd.Function):
+    """HiFiGAN.forward as one autograd node: ``apply(engine, module, mel, *module.named_parameters())``."""
+
+    @staticmethod
+    def forward(ctx, engine, module, x, *params):
+        out, tape = engine.forward_train(module, x)
+        ctx.engine, ctx.module, ctx.tape = engine, module, tape
+        ctx.frames, ctx.x_device, ctx.x_dtype = x.shape[2], x.device, x.dtype
+        ctx.key = engine.weights_key
+        ctx.save_for_backward(out)
+        return out if x.is_cuda else out.to(x.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        engine, module = ctx.engine, ctx.module
+        (out,) = ctx.saved_tensors
+        if engine.weights_key != ctx.key or engine._key(module, out.device) != ctx.key:
+            raise RuntimeError("generator parameters changed between forward and backward")
+        lib = _lib.load()
+        want_dmel = ctx.needs_input_grad[2]
+        folded, dmel = engine.backward(module, out, dout, ctx.tape, ctx.frames, want_dmel)
+        ctx.tape = None
+        grads = {}
+        dev = out.device
+        with torch.cuda.device(dev), torch.no_grad():
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for name, m in engine._conv_modules(module):
+                grads[f"{name}.bias"] = folded[f"{name}.bias"]
+                dw = folded[f"{name}.weight"]
+                if hasattr(m, "weight_g") and hasattr(m, "weight_v"):  # weight_norm(dim=0): w = g * v / ||v||
+                    v = m.weight_v.detach().to(dev, torch.float32).contiguous()
+                    g = m.weight_g.detach().to(dev, torch.float32).contiguous()
+                    dv, dg = torch.empty_like(v), torch.empty_like(g)
+                    _lib.check(lib.nvse_weight_norm_backward_f32(_lib.ptr(v), _lib.ptr(g), _lib.ptr(dw), _lib.ptr(dv), _lib.ptr(dg),
+                                                                 v.shape[0], v[0].numel(), stream))
+                    grads[f"{name}.weight_v"], grads[f"{name}.weight_g"] = dv, dg
+                else:
+                    grads[f"{name}.weight"] = dw
+        ordered = []
+        for i, (name, p) in enumerate(module.named_parameters()):
+            gr = grads.get(name) if ctx.needs_input_grad[3 + i] else None
+            ordered.append(None if gr is None else gr.to(p.device, p.dtype))
+        if dmel is not None:
+            dmel = dmel.to(ctx.x_device, ctx.x_dtype)
+        return (None, None, dmel, *ordered)

@@ -68,6 +68,15 @@ PROTOTYPES = {
     "nvse_conv_transpose1d_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_conv_transpose1d_bf16": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_istft_head_f32": (_i, [_vp, _vp, _i64, _i64, _i, _i, _vp]),
+    "nvse_generator_tape_bytes": (_sz, [_vp, _i64, _i64]),
+    "nvse_generator_backward_workspace_bytes": (_sz, [_vp, _i64, _i64]),
+    "nvse_generator_grad_elems": (_i64, [_vp]),
+    "nvse_generator_grad_offset": (_i, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "nvse_generator_forward_train": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "nvse_generator_backward": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "nvse_conv1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _f, _vp]),
+    "nvse_conv_transpose1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
+    "nvse_weight_norm_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "nvse_tc_abort_status": (_i, [_i, C.POINTER(_i)]),
     "nvse_debug_rb_trace": (_i, [C.POINTER(C.c_longlong)]),
 }

@@ -42,11 +42,12 @@ __global__ void __launch_bounds__(256) conv_taps_f32_kernel(const ConvF32Args a)
 
   const int a_row = tid >> 2, a_c4 = tid & 3;  // 64 rows x 4 float4 (16 channels)
   const bool vecB = (a.Cout % 4) == 0;
+  const int in_stride = a.in_stride > 1 ? a.in_stride : 1;
 
   for (int tap = 0; tap < a.taps.ntaps; ++tap) {
     const int off = a.taps.off[tap];
     const float* __restrict__ wt = a.w + (int64_t)a.taps.widx[tap] * a.Cin * a.Cout;
-    const int trow = t0 + a_row + off;
+    const int trow = in_stride * (t0 + a_row) + off;
     const bool row_ok = (t0 + a_row) < a.Trows && trow >= 0 && trow < a.Tin;
     for (int ci0 = 0; ci0 < a.Cin; ci0 += BK) {
       // A tile: activation rows (with the input leaky_relu fused), stored transposed
@@ -98,11 +99,13 @@ __global__ void __launch_bounds__(256) conv_taps_f32_kernel(const ConvF32Args a)
     if (orow >= a.Tout) continue;
     float* yr = a.y + b * a.y_bstride + orow * a.Cout;
     const float* rr = a.residual ? a.residual + b * a.y_bstride + orow * a.Cout : nullptr;
+    const float* mr = a.mask ? a.mask + b * a.y_bstride + orow * a.Cout : nullptr;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int co = co0 + tx * TN + j;
       if (co >= a.Cout) continue;
       float v = acc[i][j] + (a.bias ? a.bias[co] : 0.0f);
+      if (mr && !(mr[co] > 0.0f)) v *= a.mask_slope;
       if (rr) v += rr[co];
       v *= a.out_scale;
       if (a.accumulate) v += yr[co];
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
   for (int j = 0; j < NOUT; ++j) {
     if (j >= a.Cout) break;
     float v = acc[j] + (a.bias ? a.bias[j] : 0.0f);
+    if (a.mask && !(a.mask[b * a.y_bstride + orow * a.Cout + j] > 0.0f)) v *= a.mask_slope;
     if (a.residual) v += a.residual[b * a.y_bstride + orow * a.Cout + j];
     v *= a.out_scale;
     if (a.accumulate) v += yr[j];
@@ -284,9 +288,10 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
   NVSE_REQUIRE(!a.x_t32 || (thin && a.Cin % 4 == 0), NVSE_ERR_UNSUPPORTED, "fp32 conv: T32 input is only read by the thin kernel");
   if (thin) {
     NVSE_REQUIRE(a.Cout <= 32, NVSE_ERR_UNSUPPORTED, "thin conv: Cout=%d > 32", a.Cout);
+    NVSE_REQUIRE(a.in_stride <= 1, NVSE_ERR_UNSUPPORTED, "thin conv: strided input rows are not supported");
     NVSE_REQUIRE(max_off - min_off <= THIN_MAX_SPAN, NVSE_ERR_UNSUPPORTED, "thin conv: tap span %d too wide", max_off - min_off);
     const int span = max_off - min_off;
-    if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && a.out_mul == 1 && a.out_add == 0 && a.Cin <= 128) {
+    if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 && a.Cin <= 128) {
       const size_t smem = sizeof(float) * ((size_t)(POST_ROWS + span) * (a.Cin + 4) + (size_t)a.taps.ntaps * a.Cin);
       NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_post1_t32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((unsigned)((a.Trows + POST_ROWS - 1) / POST_ROWS), (unsigned)B);

@@ -28,6 +28,10 @@ struct ConvF32Args {
   int out_act;           // 0 none, 1 tanh
   int x_t32;             // x is in the T32 layout (thin kernel only: conv_post of the tensor-core path)
   int reflect_left;      // x is viewed through ReflectionPad1d((reflect_left, 0)) (istftnet.py:296,312)
+  // backward (grad.cu): a strided input row map and the leaky_relu derivative fused into the epilogue
+  int in_stride;         // input row of tap i = max(in_stride, 1) * t + off[i]  (dgrad of a ConvTranspose1d)
+  const float* mask;     // same shape as y, or null:  conv *= (mask > 0 ? 1 : mask_slope)  before `residual` is added
+  float mask_slope;
 };
 
 int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st);

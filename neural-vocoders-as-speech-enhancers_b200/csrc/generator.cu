@@ -18,6 +18,7 @@ static int build_layers(nvse_generator* g) {
     L.name = name;
     L.transposed = transposed;
     L.Cin = cin; L.Cout = cout; L.k = k; L.dilation = dil; L.stride = stride; L.padding = pad;
+    L.grad_off = g->layers.empty() ? 0 : g->layers.back().grad_off + (int64_t)g->layers.back().Cin * g->layers.back().Cout * g->layers.back().k + g->layers.back().Cout;
     g->index[name] = (int)g->layers.size();
     g->layers.push_back(L);
   };
@@ -390,6 +391,7 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     cudaFree(L.bias);
     cudaFree(L.w_bf16);
     cudaFree(L.w_f16);
+    cudaFree(L.wT);
   }
   delete g;
   return NVSE_OK;
@@ -407,6 +409,7 @@ extern "C" int nvse_generator_set_weight(nvse_generator* g, const char* name, co
   Layer& L = g->layers[it->second];
   cudaStream_t st = as_stream(stream);
   g->finalized = false;
+  g->train_ready = false;
   if (leaf == "bias") {
     NVSE_REQUIRE(ndim == 1 && shape[0] == L.Cout, NVSE_ERR_INVALID, "%s: expected shape [%d]", name, L.Cout);
     if (!L.bias) NVSE_CUDA_CHECK(cudaMalloc(&L.bias, sizeof(float) * L.Cout));

@@ -20,6 +20,8 @@ struct Layer {
   bool tc_split = false;   // activations as hi+lo bf16 pairs on the tensor-core path (accuracy)
   bool tc_f16 = false;     // IEEE-half operands (w_f16) on the tensor-core path: the upsamplers
   bool have_w = false, have_bias = false;
+  float* wT = nullptr;     // training path: per-tap transposed weights [k][Cout][Cin] (the dgrad operand), built lazily
+  int64_t grad_off = 0;    // offset of this layer's (dW, dbias) in the flat gradient buffer of nvse_generator_backward
 };
 
 }  // namespace nvse
@@ -29,6 +31,7 @@ struct nvse_generator {
   std::vector<nvse::Layer> layers;
   std::unordered_map<std::string, int> index;
   bool finalized = false;
+  bool train_ready = false;  // wT of every layer matches w
   // small-batch mode: the ResBlocks of a stage run concurrently on the caller's stream + two side streams
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};

@@ -77,12 +77,29 @@ def _trunk(w, cfg, mel):
     return x
 
 
-@torch.no_grad()
-def hifigan_forward(folded, cfg, mel):
-    """Models/hifigan.py:108-124 from a folded state dict (see ``fold_state``)."""
+def hifigan_forward_autograd(folded, cfg, mel):
+    """Models/hifigan.py:108-124, differentiable: the checker of the backward kernels (what
+    ``loss.backward()`` computes through the generator in train_time_wi_inv.py:222-236)."""
     x = _trunk(folded, cfg, mel)
     x = F.conv1d(F.leaky_relu(x), folded["conv_post.weight"], folded["conv_post.bias"], padding=3)
     return torch.tanh(x).squeeze(1)
+
+
+@torch.no_grad()
+def hifigan_forward(folded, cfg, mel):
+    """Models/hifigan.py:108-124 from a folded state dict (see ``fold_state``)."""
+    return hifigan_forward_autograd(folded, cfg, mel)
+
+
+def hifigan_gradients(state, cfg, mel, dout):
+    """Gradients of ``(HiFiGAN(mel) * dout).sum()`` w.r.t. every tensor of a reference-format state dict
+    (weight_g / weight_v / bias, or folded weight / bias) and w.r.t. ``mel``, by torch autograd over the port.
+    -> (out, {name: grad}, dmel)"""
+    leaves = {k: torch.as_tensor(v, dtype=torch.float32).clone().requires_grad_(True) for k, v in state.items()}
+    mel = torch.as_tensor(mel, dtype=torch.float32).clone().requires_grad_(True)
+    out = hifigan_forward_autograd(fold_state(leaves), cfg, mel)
+    (out * torch.as_tensor(dout, dtype=torch.float32)).sum().backward()
+    return out.detach(), {k: v.grad for k, v in leaves.items()}, mel.grad
 
 
 @torch.no_grad()

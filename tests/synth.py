@@ -34,10 +34,14 @@ HIFIGAN_SMALL = dict(HIFIGAN_V1, upsample_initial_channel=64)
 HIFIGAN_SMALL_RB2 = dict(HIFIGAN_V1, upsample_initial_channel=64, resblock="2",
                          resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]])
 ISTFTNET_SMALL = dict(ISTFTNET, upsample_initial_channel=64)
+# training-path fixtures: every channel count a multiple of 16 (128, 64, 32, 16)
+HIFIGAN_TRAIN = dict(HIFIGAN_V1, upsample_initial_channel=256)
+HIFIGAN_TRAIN_RB2 = dict(HIFIGAN_SMALL_RB2, upsample_initial_channel=256)
 
 CONFIGS = {
     "hifigan_v1": HIFIGAN_V1, "istftnet": ISTFTNET, "hifigan_small": HIFIGAN_SMALL,
     "hifigan_small_rb2": HIFIGAN_SMALL_RB2, "istftnet_small": ISTFTNET_SMALL,
+    "hifigan_train": HIFIGAN_TRAIN, "hifigan_train_rb2": HIFIGAN_TRAIN_RB2,
 }
 
 
@@ -115,6 +119,23 @@ def make_mel(batch, frames, seed):
     """log-mel-like input in the range real log-mels occupy ([-11.5, 2])."""
     rng = np.random.default_rng(seed)
     return rng.uniform(-6.0, 1.0, size=(batch, 80, frames)).astype(np.float32)
+
+
+def make_dout(batch, samples, seed):
+    """dL/d(waveform) of a synthetic loss ``(wav * dout).sum()``."""
+    rng = np.random.default_rng(seed)
+    return rng.normal(0.0, 1.0, size=(batch, samples)).astype(np.float32)
+
+
+GRAD_SAMPLES = 8
+
+
+def grad_summary(g):
+    """(l2 norm, sum, GRAD_SAMPLES evenly spaced entries) of one gradient tensor -- what the backward
+    fixtures store per parameter (full gradients of 3.5 M parameters would be 14 MB)."""
+    f = np.asarray(g, dtype=np.float64).reshape(-1)
+    idx = np.linspace(0, f.size - 1, GRAD_SAMPLES).astype(np.int64)
+    return float(np.sqrt((f * f).sum())), float(f.sum()), f[idx].astype(np.float32)
 
 
 def load_golden(name):

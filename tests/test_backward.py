@@ -1,0 +1,238 @@
+"""Backward pass of the generator (what ``loss_gen_all.backward()`` runs through
+HiFiGAN.forward in train_time_wi_inv.py:222-236).
+
+not-gpu: the oracle's autograd is pinned against fixtures made by the unmodified reference
+(tests/golden/make_golden_grads.py).  gpu: the CUDA backward (through the C ABI and through the drop-in
+module under torch autograd) against the oracle on the same inputs and against the fixtures."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+from util import lib_mod, pkg, stream_ptr, report, build_generator
+from oracle import torch_port
+
+GRAD_CASES = ["grads_hifigan_train_f6", "grads_hifigan_train_rb2_f5", "grads_hifigan_train_init_f4"]
+
+
+def _summary_mismatch(grads, gold):
+    """Worst deviation of {name: grad} from a fixture's per-parameter summaries, relative to each tensor's scale."""
+    worst = 0.0
+    for i, name in enumerate(gold["meta"]["params"]):
+        l2, sm, smp = synth.grad_summary(grads[name].detach().cpu().numpy())
+        n = grads[name].numel()
+        scale = max(gold["g_l2"][i] / np.sqrt(n), 1e-12)  # rms entry of the reference gradient
+        worst = max(worst, abs(l2 - gold["g_l2"][i]) / max(gold["g_l2"][i], 1e-12))
+        worst = max(worst, abs(sm - gold["g_sum"][i]) / (scale * n))
+        worst = max(worst, float(np.abs(smp - gold["g_samples"][i]).max()) / (scale * 30.0))
+    return worst
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_oracle_autograd_matches_reference_fixture(name):
+    gold = synth.load_golden(name)
+    meta = gold["meta"]
+    cfg = synth.CONFIGS[meta["cfg"]]
+    state = synth.make_state(cfg, meta["weight_seed"], meta["regime"])
+    out, grads, dmel = torch_port.hifigan_gradients(state, cfg, gold["mel"], gold["dout"])
+    assert np.abs(out.numpy() - gold["out"]).max() <= 1e-5
+    assert sorted(grads) == sorted(meta["params"])
+    assert np.abs(dmel.numpy() - gold["dmel"]).max() <= 1e-4 * np.abs(gold["dmel"]).max()
+    assert _summary_mismatch(grads, gold) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU: layer-level entry points against torch autograd (fp32, TF32 off)
+# ---------------------------------------------------------------------------------------------
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _close(a, b, rel=1e-4):
+    scale = float(b.abs().max())
+    return float((a - b).abs().max()) <= rel * scale + 1e-7
+
+
+CONV_BWD_CASES = [  # Cin, Cout, k, dilation, in_slope, residual, B, T
+    (32, 32, 11, 5, 0.1, True, 2, 300),
+    (64, 64, 3, 3, 0.1, False, 3, 129),
+    (80, 64, 7, 1, 1.0, False, 2, 33),     # conv_pre: no activation
+    (32, 1, 7, 1, 0.01, False, 2, 517),    # conv_post: one output channel (thin dgrad kernel)
+    (128, 128, 7, 1, 0.1, True, 1, 64),
+    (16, 16, 3, 1, 0.1, True, 2, 5),       # shorter than the receptive field
+    (256, 256, 3, 5, 0.1, False, 1, 70),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CONV_BWD_CASES)
+def test_conv1d_backward_layer(case):
+    cin, cout, k, d, slope, use_res, b, t = case
+    _no_tf32()
+    gen = torch.Generator(device="cuda").manual_seed(cin * 131 + k)
+    x = torch.randn(b, cin, t, device="cuda", generator=gen).requires_grad_(True)
+    w = (torch.randn(cout, cin, k, device="cuda", generator=gen) / np.sqrt(cin * k)).requires_grad_(True)
+    bias = torch.randn(cout, device="cuda", generator=gen).requires_grad_(True)
+    dy = torch.randn(b, cout, t, device="cuda", generator=gen)
+    xin = F.leaky_relu(x, slope) if slope != 1.0 else x
+    y = F.conv1d(xin, w, bias, dilation=d, padding=(k * d - d) // 2)
+    y.backward(dy)
+    dres = torch.randn(b, cin, t, device="cuda", generator=gen) if use_res else None
+    dx_ref = x.grad + (dres if use_res else 0)
+
+    lib = lib_mod.load()
+    x_cl = x.detach().transpose(1, 2).contiguous()
+    dy_cl = dy.transpose(1, 2).contiguous()
+    dres_cl = dres.transpose(1, 2).contiguous() if use_res else None
+    dx = torch.full((b, t, cin), float("nan"), device="cuda")
+    dw = torch.full((cout, cin, k), float("nan"), device="cuda")
+    db = torch.full((cout,), float("nan"), device="cuda")
+    lib_mod.check(lib.nvse_conv1d_backward_f32(lib_mod.ptr(x_cl), lib_mod.ptr(w.detach().contiguous()), lib_mod.ptr(dy_cl),
+                                               lib_mod.ptr(dres_cl), lib_mod.ptr(dx), lib_mod.ptr(dw), lib_mod.ptr(db),
+                                               b, t, cin, cout, k, d, slope, stream_ptr()))
+    torch.cuda.synchronize()
+    assert _close(dx.transpose(1, 2), dx_ref), "dx"
+    assert _close(dw, w.grad), "dw"
+    assert _close(db, bias.grad), "dbias"
+
+
+CONVT_BWD_CASES = [  # Cin, Cout, k, stride, B, T
+    (64, 32, 16, 8, 2, 40),
+    (32, 16, 4, 2, 2, 301),
+    (128, 64, 16, 8, 1, 7),
+    (256, 128, 16, 8, 2, 6),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CONVT_BWD_CASES)
+def test_conv_transpose1d_backward_layer(case):
+    cin, cout, k, u, b, t = case
+    _no_tf32()
+    pad = (k - u) // 2
+    gen = torch.Generator(device="cuda").manual_seed(cin + 7 * k)
+    x = torch.randn(b, cin, t, device="cuda", generator=gen).requires_grad_(True)
+    w = (torch.randn(cin, cout, k, device="cuda", generator=gen) / np.sqrt(cin * k / u)).requires_grad_(True)
+    bias = torch.randn(cout, device="cuda", generator=gen).requires_grad_(True)
+    y = F.conv_transpose1d(F.leaky_relu(x, 0.1), w, bias, stride=u, padding=pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    lib = lib_mod.load()
+    x_cl = x.detach().transpose(1, 2).contiguous()
+    dy_cl = dy.transpose(1, 2).contiguous()
+    dx = torch.full((b, t, cin), float("nan"), device="cuda")
+    dw = torch.full((cin, cout, k), float("nan"), device="cuda")
+    db = torch.full((cout,), float("nan"), device="cuda")
+    lib_mod.check(lib.nvse_conv_transpose1d_backward_f32(lib_mod.ptr(x_cl), lib_mod.ptr(w.detach().contiguous()),
+                                                         lib_mod.ptr(dy_cl), lib_mod.ptr(dx), lib_mod.ptr(dw), lib_mod.ptr(db),
+                                                         b, t, cin, cout, k, u, pad, 0.1, stream_ptr()))
+    torch.cuda.synchronize()
+    assert _close(dx.transpose(1, 2), x.grad), "dx"
+    assert _close(dw, w.grad), "dw"
+    assert _close(db, bias.grad), "dbias"
+
+
+@pytest.mark.gpu
+def test_weight_norm_backward():
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for shape in [(64, 32, 7), (16, 128, 16), (1, 32, 7)]:
+        v = torch.randn(*shape, device="cuda", generator=gen).requires_grad_(True)
+        g = torch.rand(shape[0], 1, 1, device="cuda", generator=gen).add(0.5).requires_grad_(True)
+        w = g * v / v.reshape(shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
+        dw = torch.randn(*shape, device="cuda", generator=gen)
+        w.backward(dw)
+        dv, dg = torch.empty_like(v), torch.empty_like(g)
+        lib = lib_mod.load()
+        lib_mod.check(lib.nvse_weight_norm_backward_f32(lib_mod.ptr(v.detach()), lib_mod.ptr(g.detach()), lib_mod.ptr(dw),
+                                                        lib_mod.ptr(dv), lib_mod.ptr(dg), shape[0], shape[1] * shape[2], stream_ptr()))
+        torch.cuda.synchronize()
+        assert _close(dv, v.grad, 2e-5) and _close(dg, g.grad, 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU: the whole generator under torch autograd through the drop-in module
+# ---------------------------------------------------------------------------------------------
+def _module_grads(cfg, state, mel, dout, remove_wn=False):
+    gen = build_generator(cfg, state, "cuda", remove_wn=remove_wn).train()
+    x = torch.from_numpy(mel).cuda().requires_grad_(True)
+    out = gen(x)
+    (out * torch.from_numpy(dout).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    return out.detach(), {k: p.grad for k, p in gen.named_parameters()}, x.grad, gen
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_generator_backward_vs_fixture_and_oracle(name):
+    gold = synth.load_golden(name)
+    meta = gold["meta"]
+    cfg = synth.CONFIGS[meta["cfg"]]
+    state = synth.make_state(cfg, meta["weight_seed"], meta["regime"])
+    out, grads, dmel, _ = _module_grads(cfg, state, gold["mel"], gold["dout"])
+    assert np.abs(out.cpu().numpy() - gold["out"]).max() <= 1e-4          # the fp32 parity gate of the forward
+    assert np.abs(dmel.cpu().numpy() - gold["dmel"]).max() <= 1e-4 * np.abs(gold["dmel"]).max()
+    mism = _summary_mismatch(grads, gold)
+    # every tensor in full against the oracle's autograd
+    _, ref, _ = torch_port.hifigan_gradients(state, cfg, gold["mel"], gold["dout"])
+    worst = 0.0
+    for k, gr in ref.items():
+        got = grads[k].cpu()
+        assert got.shape == gr.shape and torch.isfinite(got).all(), k
+        worst = max(worst, float((got - gr).abs().max()) / (float(gr.abs().max()) + 1e-12))
+    report(f"backward {name}: fixture-summary mismatch {mism:.2e}, worst per-tensor rel. max error vs oracle {worst:.2e}")
+    assert mism <= 1e-4
+    assert worst <= 2e-4
+
+
+@pytest.mark.gpu
+def test_generator_backward_folded_weights_and_determinism():
+    """After remove_weight_norm() the parameters are plain weight/bias; two backward runs are bit-identical."""
+    gold = synth.load_golden("grads_hifigan_train_f6")
+    meta = gold["meta"]
+    cfg = synth.CONFIGS[meta["cfg"]]
+    state = synth.make_state(cfg, meta["weight_seed"], meta["regime"])
+    out1, g1, d1, gen = _module_grads(cfg, state, gold["mel"], gold["dout"], remove_wn=True)
+    assert np.abs(out1.cpu().numpy() - gold["out"]).max() <= 1e-4
+    folded = torch_port.fold_state({k: torch.from_numpy(v) for k, v in state.items()})
+    _, ref, _ = torch_port.hifigan_gradients(folded, cfg, gold["mel"], gold["dout"])
+    for k, gr in ref.items():
+        assert _close(g1[k].cpu(), gr, 2e-4), k
+    gen.zero_grad(set_to_none=True)
+    x = torch.from_numpy(gold["mel"]).cuda().requires_grad_(True)
+    (gen(x) * torch.from_numpy(gold["dout"]).cuda()).sum().backward()
+    for k, p in gen.named_parameters():
+        assert torch.equal(p.grad, g1[k]), k
+    assert torch.equal(x.grad, d1)
+
+
+@pytest.mark.gpu
+def test_training_step_reduces_loss():
+    """A few Adam steps on a fixed target through the CUDA forward/backward: the loss must go down."""
+    cfg = synth.CONFIGS["hifigan_train"]
+    gen = build_generator(cfg, synth.make_state(cfg, 1234, "init"), "cuda").train()
+    opt = torch.optim.AdamW(gen.parameters(), 2e-3, betas=(0.8, 0.99))   # train_time_wi_inv.py:73
+    mel = torch.from_numpy(synth.make_mel(4, 8, 5)).cuda()
+    target = torch.from_numpy(synth.make_wave(4, 8 * 256, 6)).cuda() * 0.2
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = F.l1_loss(gen(mel), target)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    report(f"training smoke: L1 {losses[0]:.4f} -> {losses[-1]:.4f} in 12 AdamW steps")
+    assert losses[-1] < 0.9 * losses[0]
+
+
+@pytest.mark.gpu
+def test_istftnet_training_is_rejected_loudly():
+    cfg = synth.CONFIGS["istftnet_small"]
+    gen = build_generator(cfg, synth.make_state(cfg, 9, "unit"), "cuda").train()
+    with pytest.raises(NotImplementedError):
+        gen(torch.zeros(1, 80, 4, device="cuda"))

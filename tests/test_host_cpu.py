@@ -109,8 +109,14 @@ def test_no_cpu_fallback_fails_loudly():
         pkg.mel_spectrogram(torch.zeros(1, 4096), 1024, 80, 22050, 256, 1024, 0, 8000)
 
 
-def test_forward_rejects_training_mode_grad():
-    gen = pkg.HiFiGAN(synth.AttrDict(synth.HIFIGAN_SMALL)).train()
+def test_training_mode_has_no_cpu_fallback_either():
+    """HiFiGAN in train mode takes the CUDA forward-with-tape/backward path (never a torch fallback);
+    iSTFTNet's training path is not built yet and says so."""
+    if not torch.cuda.is_available():
+        gen = pkg.HiFiGAN(synth.AttrDict(synth.HIFIGAN_SMALL)).train()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            gen(torch.zeros(1, 80, 4))
+    gen = pkg.iSTFTNet(synth.AttrDict(synth.ISTFTNET_SMALL)).train()
     with pytest.raises(NotImplementedError):
         gen(torch.zeros(1, 80, 4))
 
