@@ -207,6 +207,14 @@ NVSE_API int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frame
                             const void* tape, size_t tape_bytes, float* grads, float* dmel, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* Backward of nvse_frontend_mel_f32 (the mel-L1 term of the generator loss differentiates
+ * mel_spectrogram(y_g_hat), train_time_wi_inv.py:173-179,231-235): dmel [B, n_mels, frames] -> dy [B, T] (dense).
+ * The spectra are recomputed from y (nothing is saved by the forward).  Bit-reproducible. */
+NVSE_API size_t nvse_frontend_backward_scratch_bytes(const nvse_frontend* fe, int64_t B, int64_t T);
+NVSE_API int nvse_frontend_mel_backward_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
+                                   int64_t y_row_stride, const float* dmel, float* dy, void* scratch,
+                                   size_t scratch_bytes, void* stream);
+
 /* Layer-level backward (channels-last fp32, the layouts of nvse_conv1d_f32 / nvse_conv_transpose1d_f32):
  *   y = conv1d(lrelu(x, in_slope), w, dilation, "same") + bias [+ residual]
  *   dx = lrelu'(x) * conv^T(dy) [+ dresidual_in],  dw [Cout,Cin,k],  dbias [Cout];  any of dx/dw/dbias may be null. */

@@ -14,6 +14,7 @@
 // [B,513,F] complex / magnitude tensors of the reference never exist.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -207,6 +208,211 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, NVSE_FE_MINB) mel_frontend_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the front-end (the mel-L1 term of the generator loss back-propagates through
+// mel_spectrogram(y_g_hat), train_time_wi_inv.py:173-179,231-235).  Per frame pair, one warp:
+//   recompute the two spectra A, B (same packed FFT as the forward) -> |.| -> mel sums
+//   d(mel sum) = dmel / sum  where sum >= 1e-5 (log + clamp, dataset.py:27-28), else 0
+//   d|X[k]|   = sum_m basis[m][k] d(mel sum)[m];   G[k] = d|X[k]| * X[k] / |X[k]|   (0 where |X| = 0)
+//   d frame[n] = w[n] * Re sum_{k=0}^{N/2} G[k] e^{+2 pi i k n / N}
+// The last line for both frames is ONE more packed 1024-point FFT: with H the Hermitian extension of G
+// (H[k] = G[k]/2, H[N-k] = conj(G[k])/2, H[0] = Re G[0], H[N/2] = Re G[N/2]),  ya + i yb = conj(FFT(conj(Ha + i Hb))).
+// Frame gradients go to a scratch [B, F, 1024]; mel_overlap_add_kernel sums the (up to 4) overlapping
+// frames and the reflected padding into dy in a fixed order (bit-reproducible, no atomics).
+// ------------------------------------------------------------------------------------------------
+struct FrontendBwdParams {
+  FrontendParams f;
+  const float* dmel;    // [B, n_mels, F]
+  const int* bin_mlo;   // [513] first / last mel filter with a non-zero weight at the bin
+  const int* bin_mhi;
+  float* frames;        // scratch [B, F, 1024]
+};
+
+__device__ __forceinline__ void fft1024_warp(float (&re)[32], float (&im)[32], float* sre, float* sim,
+                                             const float2* __restrict__ twiddle, int lane) {
+  fft32_dif(re, im);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    const int r = brev5(k1);
+    const float2 t = __ldg(twiddle + k1 * 32 + lane);
+    sre[k1 * kTransposeStride + lane] = re[r] * t.x - im[r] * t.y;
+    sim[k1 * kTransposeStride + lane] = re[r] * t.y + im[r] * t.x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int l = 0; l < 32; ++l) {
+    re[l] = sre[lane * kTransposeStride + l];
+    im[l] = sim[lane * kTransposeStride + l];
+  }
+  __syncwarp();
+  fft32_dif(re, im);  // X[lane + 32*k2] is now at register brev5(k2)
+}
+
+constexpr int kBwdWarpSmemFloats = kWarpSmemFloats + 2 * 256;  // + d(mel sum) of both frames
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) mel_frontend_bwd_kernel(const FrontendBwdParams q) {
+  extern __shared__ float smem[];
+  const FrontendParams& p = q.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t task = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+  if (task >= p.B * p.pairs) return;
+  float* sre = smem + warp * kBwdWarpSmemFloats;
+  float* sim = sre + 32 * kTransposeStride;
+  float* dm_a = sre + kWarpSmemFloats;
+  float* dm_b = dm_a + 256;
+
+  const int64_t b = task / p.pairs;
+  const int64_t f0 = 2 * (task % p.pairs);
+  const bool has_b = (f0 + 1) < p.F;
+  const float* __restrict__ yrow = p.y + b * p.y_stride;
+  const int64_t sa = f0 * p.hop - kNfft / 2;
+  const int64_t sb = sa + p.hop;
+
+  float re[32], im[32];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    const int n = lane + 32 * m;
+    const float w = __ldg(p.window + n);
+    re[m] = __ldg(yrow + reflect_index(sa + n, p.T)) * w;
+    im[m] = has_b ? __ldg(yrow + reflect_index(sb + n, p.T)) * w : 0.0f;
+  }
+  fft1024_warp(re, im, sre, sim, p.twiddle, lane);
+
+  // the two spectra (bins lane + 32*k2, k2 < 16; the Nyquist bin on lane 0) and their magnitudes
+  float a_re[16], a_im[16], b_re[16], b_im[16];
+  float* mag_a = sre;
+  float* mag_b = sim;
+  const int src_lane = (32 - lane) & 31;
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+    float pr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], src_lane);
+    float pi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], src_lane);
+    if (lane == 0) {
+      pr = re[brev5((32 - k2) & 31)];
+      pi = im[brev5((32 - k2) & 31)];
+    }
+    a_re[k2] = 0.5f * (zr + pr); a_im[k2] = 0.5f * (zi - pi);   // A = (Z[k] + conj Z[N-k]) / 2
+    b_re[k2] = 0.5f * (zi + pi); b_im[k2] = -0.5f * (zr - pr);  // B = (Z[k] - conj Z[N-k]) / 2i
+    mag_a[lane + 32 * k2] = sqrtf(a_re[k2] * a_re[k2] + a_im[k2] * a_im[k2]);
+    mag_b[lane + 32 * k2] = sqrtf(b_re[k2] * b_re[k2] + b_im[k2] * b_im[k2]);
+  }
+  const float a_ny = re[brev5(16)], b_ny = im[brev5(16)];  // meaningful on lane 0 only
+  if (lane == 0) {
+    mag_a[512] = fabsf(a_ny);
+    mag_b[512] = fabsf(b_ny);
+  }
+  __syncwarp();
+
+  // mel sums and their gradients
+  for (int m = lane; m < p.n_mels; m += 32) {
+    const int lo = __ldg(p.band_lo + m), len = __ldg(p.band_len + m);
+    float acc_a = 0.0f, acc_b = 0.0f;
+    for (int t = 0; t < len; ++t) {
+      const float w = __ldg(p.wpack + (int64_t)t * p.n_mels + m);
+      acc_a = fmaf(w, mag_a[lo + t], acc_a);
+      acc_b = fmaf(w, mag_b[lo + t], acc_b);
+    }
+    const float* g = q.dmel + (b * p.n_mels + m) * p.F + f0;
+    dm_a[m] = acc_a >= 1e-5f ? g[0] / acc_a : 0.0f;
+    dm_b[m] = (has_b && acc_b >= 1e-5f) ? g[1] / acc_b : 0.0f;
+  }
+  __syncwarp();
+
+  // d|X[k]| / |X[k]|, in place over the magnitudes
+  for (int k = lane; k < kBins; k += 32) {
+    float da = 0.0f, db = 0.0f;
+    const int mlo = __ldg(q.bin_mlo + k), mhi = __ldg(q.bin_mhi + k);
+    for (int m = mlo; m <= mhi; ++m) {
+      const int t = k - __ldg(p.band_lo + m);
+      if (t >= 0 && t < __ldg(p.band_len + m)) {
+        const float w = __ldg(p.wpack + (int64_t)t * p.n_mels + m);
+        da = fmaf(w, dm_a[m], da);
+        db = fmaf(w, dm_b[m], db);
+      }
+    }
+    const float ma = mag_a[k], mb = mag_b[k];
+    mag_a[k] = ma > 0.0f ? da / ma : 0.0f;
+    mag_b[k] = mb > 0.0f ? db / mb : 0.0f;
+  }
+  __syncwarp();
+
+  // G = ratio * X;  scale by 1/2 for the Hermitian extension (bins 0 and N/2 keep their full real part)
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) {
+    const float ra = mag_a[lane + 32 * k2], rb = mag_b[lane + 32 * k2];
+    const float h = (k2 == 0 && lane == 0) ? 1.0f : 0.5f;
+    a_re[k2] *= ra * h; a_im[k2] *= ra * h;
+    b_re[k2] *= rb * h; b_im[k2] *= rb * h;
+  }
+  const float ga_ny = lane == 0 ? a_ny * mag_a[512] : 0.0f, gb_ny = lane == 0 ? b_ny * mag_b[512] : 0.0f;
+  __syncwarp();  // the magnitude planes are reused by the transpose below
+
+  // input of the second FFT: conj(Ha + i Hb) at index lane + 32*m in register m
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    if (m == 0 && lane == 0) {  // DC: Re Ga + i Re Gb  (imaginary parts are exactly zero)
+      re[m] = a_re[0];
+      im[m] = -b_re[0];
+    } else {
+      re[m] = a_re[m] - b_im[m];
+      im[m] = -(a_im[m] + b_re[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m < 32; ++m) {  // index N - k: conj(Ga[k])/2 + i conj(Gb[k])/2, G[k] owned by lane 32 - L at k2 = 31 - m
+    float gar = __shfl_sync(0xffffffffu, a_re[31 - m], src_lane);
+    float gai = __shfl_sync(0xffffffffu, a_im[31 - m], src_lane);
+    float gbr = __shfl_sync(0xffffffffu, b_re[31 - m], src_lane);
+    float gbi = __shfl_sync(0xffffffffu, b_im[31 - m], src_lane);
+    if (lane == 0) {  // lane 0 pairs with itself: k2 = 32 - m (m = 16: the Nyquist bin, real)
+      if (m == 16) {
+        gar = ga_ny; gai = 0.0f; gbr = gb_ny; gbi = 0.0f;
+      } else {
+        gar = a_re[(32 - m) & 15]; gai = a_im[(32 - m) & 15]; gbr = b_re[(32 - m) & 15]; gbi = b_im[(32 - m) & 15];
+      }
+    }
+    re[m] = gar + gbi;
+    im[m] = -(gbr - gai);
+  }
+  fft1024_warp(re, im, sre, sim, p.twiddle, lane);
+
+  float* fa = q.frames + (b * p.F + f0) * kNfft;
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) {
+    const int n = lane + 32 * k2;
+    const float w = __ldg(p.window + n);
+    fa[n] = w * re[brev5(k2)];
+    if (has_b) fa[kNfft + n] = -w * im[brev5(k2)];
+  }
+}
+
+// dy[b][t] = sum over the padded positions that read sample t (itself and its reflections) of the frames covering them
+__global__ void __launch_bounds__(256) mel_overlap_add_kernel(const float* __restrict__ frames, float* __restrict__ dy, int64_t B,
+                                                              int64_t T, int64_t F, int hop) {
+  const int64_t n = B * T;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / T, t = e - b * T;
+    const float* fb = frames + b * F * kNfft;
+    int64_t qs[3];
+    int nq = 0;
+    qs[nq++] = t + kNfft / 2;
+    if (t >= 1 && t <= kNfft / 2) qs[nq++] = kNfft / 2 - t;                              // left reflection: i = -t
+    if (t <= T - 2 && 2 * (T - 1) - t <= T - 1 + kNfft / 2) qs[nq++] = 2 * (T - 1) - t + kNfft / 2;  // right reflection
+    float acc = 0.0f;
+    for (int i = 0; i < nq; ++i) {
+      const int64_t qq = qs[i];
+      int64_t f_lo = (qq - (kNfft - 1) + hop - 1) / hop;
+      if (qq - (kNfft - 1) < 0) f_lo = 0;
+      int64_t f_hi = qq / hop;
+      if (f_hi > F - 1) f_hi = F - 1;
+      for (int64_t f = f_lo; f <= f_hi; ++f) acc += fb[f * kNfft + (qq - f * hop)];
+    }
+    dy[e] = acc;
+  }
+}
+
 }  // namespace
 
 }  // namespace nvse
@@ -218,6 +424,8 @@ struct nvse_frontend {
   float* wpack = nullptr;
   int* band_lo = nullptr;
   int* band_len = nullptr;
+  int* bin_mlo = nullptr;  // backward: range of mel filters touching each bin
+  int* bin_mhi = nullptr;
 };
 
 extern "C" int nvse_frontend_create(int n_fft, int hop, int n_mels, const float* window_host,
@@ -251,6 +459,16 @@ extern "C" int nvse_frontend_create(int n_fft, int hop, int n_mels, const float*
   std::vector<float> wpack((size_t)max_band * n_mels, 0.0f);
   for (int m = 0; m < n_mels; ++m)
     for (int t = 0; t < len[m]; ++t) wpack[(size_t)t * n_mels + m] = mel_basis_host[(size_t)m * kBins + lo[m] + t];
+  std::vector<int> bin_mlo(kBins, 0), bin_mhi(kBins, -1);
+  for (int k = 0; k < kBins; ++k) {
+    int first = -1, last = -1;
+    for (int m = 0; m < n_mels; ++m)
+      if (mel_basis_host[(size_t)m * kBins + k] != 0.0f) {
+        if (first < 0) first = m;
+        last = m;
+      }
+    if (first >= 0) { bin_mlo[k] = first; bin_mhi[k] = last; }
+  }
   std::vector<float2> tw(32 * 32);
   for (int k1 = 0; k1 < 32; ++k1)
     for (int l = 0; l < 32; ++l) {
@@ -282,6 +500,10 @@ extern "C" int nvse_frontend_create(int n_fft, int hop, int n_mels, const float*
   FE_TRY(cudaMemcpy(fe->wpack, wpack.data(), sizeof(float) * wpack.size(), cudaMemcpyHostToDevice));
   FE_TRY(cudaMemcpy(fe->band_lo, lo.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
   FE_TRY(cudaMemcpy(fe->band_len, len.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+  FE_TRY(cudaMalloc(&fe->bin_mlo, sizeof(int) * kBins));
+  FE_TRY(cudaMalloc(&fe->bin_mhi, sizeof(int) * kBins));
+  FE_TRY(cudaMemcpy(fe->bin_mlo, bin_mlo.data(), sizeof(int) * kBins, cudaMemcpyHostToDevice));
+  FE_TRY(cudaMemcpy(fe->bin_mhi, bin_mhi.data(), sizeof(int) * kBins, cudaMemcpyHostToDevice));
 #undef FE_TRY
   *out = fe;
   return NVSE_OK;
@@ -294,6 +516,8 @@ extern "C" int nvse_frontend_destroy(nvse_frontend* fe) {
   cudaFree(fe->wpack);
   cudaFree(fe->band_lo);
   cudaFree(fe->band_len);
+  cudaFree(fe->bin_mlo);
+  cudaFree(fe->bin_mhi);
   delete fe;
   return NVSE_OK;
 }
@@ -337,5 +561,42 @@ extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, in
                  as_stream(stream));
   mel_frontend_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, as_stream(stream)>>>(p);
   NVSE_LAUNCH_CHECK("mel_frontend_kernel");
+  return NVSE_OK;
+}
+
+extern "C" size_t nvse_frontend_backward_scratch_bytes(const nvse_frontend* fe, int64_t B, int64_t T) {
+  if (!fe || B < 0 || T < 0) return 0;
+  return (size_t)B * (size_t)(1 + T / fe->hop) * nvse::kNfft * sizeof(float) + 256;
+}
+
+extern "C" int nvse_frontend_mel_backward_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
+                                              int64_t y_row_stride, const float* dmel, float* dy, void* scratch,
+                                              size_t scratch_bytes, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(fe && y && dmel && dy && scratch, NVSE_ERR_INVALID, "nvse_frontend_mel_backward_f32: null argument");
+  NVSE_REQUIRE(B >= 0 && y_row_stride >= T, NVSE_ERR_INVALID, "nvse_frontend_mel_backward_f32: bad B/stride");
+  NVSE_REQUIRE(T > fe->n_fft / 2, NVSE_ERR_INVALID,
+               "nvse_frontend_mel_backward_f32: reflect padding needs T > n_fft/2 (T=%lld, n_fft=%d)", (long long)T, fe->n_fft);
+  NVSE_REQUIRE(scratch_bytes >= nvse_frontend_backward_scratch_bytes(fe, B, T), NVSE_ERR_INVALID, "scratch too small");
+  if (B == 0) return NVSE_OK;
+  FrontendBwdParams q;
+  FrontendParams& p = q.f;
+  p.y = y; p.y_stride = y_row_stride; p.T = T; p.B = B;
+  p.F = 1 + T / fe->hop; p.pairs = (p.F + 1) / 2; p.hop = fe->hop; p.n_mels = fe->n_mels;
+  p.window = fe->window; p.twiddle = fe->twiddle; p.wpack = fe->wpack; p.band_lo = fe->band_lo; p.band_len = fe->band_len;
+  p.out = nullptr;
+  q.dmel = dmel; q.bin_mlo = fe->bin_mlo; q.bin_mhi = fe->bin_mhi;
+  q.frames = reinterpret_cast<float*>((reinterpret_cast<size_t>(scratch) + 255) / 256 * 256);
+  const int64_t tasks = B * p.pairs;
+  const int64_t ctas = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;
+  NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_mel_backward_f32: problem too large for one launch");
+  const size_t smem = sizeof(float) * kBwdWarpSmemFloats * kWarpsPerCta;
+  NVSE_CUDA_CHECK(cudaFuncSetAttribute(mel_frontend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = as_stream(stream);
+  mel_frontend_bwd_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(q);
+  NVSE_LAUNCH_CHECK("mel_frontend_bwd_kernel");
+  const int64_t n = B * T;
+  mel_overlap_add_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1 << 20), 256, 0, st>>>(q.frames, dy, B, T, p.F, fe->hop);
+  NVSE_LAUNCH_CHECK("mel_overlap_add_kernel");
   return NVSE_OK;
 }

@@ -73,8 +73,8 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     global mel_window
     if y.dim() not in (1, 2):
         raise RuntimeError(f"mel_spectrogram expects a 1-D or 2-D waveform tensor, got {tuple(y.shape)}")
-    if torch.is_grad_enabled() and y.requires_grad:
-        raise NotImplementedError("mel_spectrogram backward (STFT adjoint) is not implemented in this build")
+    if torch.is_grad_enabled() and y.requires_grad:  # the mel-L1 loss of the trainer (train_time_wi_inv.py:173-179,231-235)
+        return _MelFn.apply(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, in_dataset)
     out_device = torch.device("cpu") if in_dataset else y.device
     ps = param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, out_device)
     if ps in mel_window:
@@ -103,3 +103,44 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     if squeeze:
         out = out[0]
     return out if out.device == out_device else out.to(out_device)
+
+
+class _MelFn(torch.autograd.Function):
+    """mel_spectrogram as an autograd node: the CUDA forward above, and the CUDA backward
+    (nvse_frontend_mel_backward_f32: recomputed spectra -> d|X| -> packed inverse FFT -> overlap-add)."""
+
+    @staticmethod
+    def forward(ctx, y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, in_dataset):
+        with torch.no_grad():
+            out = mel_spectrogram(y.detach(), n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax,
+                                  in_dataset=in_dataset)
+        ctx.args = (n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, in_dataset)
+        ctx.save_for_backward(y)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dmel):
+        (y,) = ctx.saved_tensors
+        n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, in_dataset = ctx.args
+        out_device = torch.device("cpu") if in_dataset else y.device
+        mel_basis, hann_window = mel_window[param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, out_device)]
+        dev = _cuda_device_for(y)
+        fe = _frontend(sampling_rate, n_fft, num_mels, hop_size, win_size, fmin, fmax, mel_basis, hann_window, dev)
+        squeeze = y.dim() == 1
+        yd = y.detach().to(dev, torch.float32)
+        gd = dmel.detach().to(dev, torch.float32)
+        if squeeze:
+            yd, gd = yd.unsqueeze(0), gd.unsqueeze(0)
+        yd, gd = yd.contiguous(), gd.contiguous()
+        batch, samples = yd.shape
+        dy = torch.empty_like(yd)
+        lib = _lib.load()
+        scratch = torch.empty(lib.nvse_frontend_backward_scratch_bytes(fe, batch, samples), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.nvse_frontend_mel_backward_f32(fe, _lib.ptr(yd), batch, samples, samples, _lib.ptr(gd), _lib.ptr(dy),
+                                                          _lib.ptr(scratch), scratch.numel(), C.c_void_p(stream)))
+        if squeeze:
+            dy = dy[0]
+        return (dy.to(y.device, y.dtype),) + (None,) * 8

@@ -236,3 +236,84 @@ def test_istftnet_training_is_rejected_loudly():
     gen = build_generator(cfg, synth.make_state(cfg, 9, "unit"), "cuda").train()
     with pytest.raises(NotImplementedError):
         gen(torch.zeros(1, 80, 4, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------
+# mel_spectrogram backward (the mel-L1 term of the generator loss, train_time_wi_inv.py:173-179,231-235)
+# ---------------------------------------------------------------------------------------------
+def _mel_grad_oracle(y, fmax, dmel):
+    a = synth.HIFIGAN_V1
+    yt = torch.from_numpy(y).double().requires_grad_(True)   # float64 autograd over the port's formula
+    basis = torch.from_numpy(torch_port.np_oracle.mel_filterbank(a["sampling_rate"], a["n_fft"], a["num_mels"], a["fmin"], fmax)).double()
+    spec = torch.stft(yt, a["n_fft"], hop_length=a["hop_size"], win_length=a["win_size"],
+                      window=torch.hann_window(a["win_size"], dtype=torch.float64), center=True, return_complex=True)
+    mel = torch.log(torch.clamp(basis @ spec.abs(), min=1e-5))
+    (mel * torch.from_numpy(dmel).double()).sum().backward()
+    return mel.detach(), yt.grad
+
+
+def test_mel_gradient_oracle_is_the_reference_formula():
+    """The float64 checker above reproduces the reference-made mel fixture (so its autograd differentiates the
+    reference's own expression, dataset.py:78-89)."""
+    gold = synth.load_golden("mel_b2_t4100")
+    mel, _ = _mel_grad_oracle(gold["y"], gold["meta"]["fmax"], np.zeros_like(gold["out"]))
+    assert synth.mel_mismatch(mel.numpy(), gold["out"]) <= 1.0
+
+
+MEL_BWD_CASES = [("mel_b2_t4100", 1), ("mel_b1_t513", 2), ("mel_b3_t8192_fmax_half", 3), ("mel_tone_silence", 4)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seed", MEL_BWD_CASES)
+def test_mel_spectrogram_backward(name, seed):
+    gold = synth.load_golden(name)
+    a = synth.HIFIGAN_V1
+    fmax = gold["meta"]["fmax"]
+    y = gold["y"] if gold["y"].ndim == 2 else gold["y"][None]
+    dmel = np.random.default_rng(seed).normal(size=gold["out"].reshape(y.shape[0], 80, -1).shape).astype(np.float32)
+    _, ref = _mel_grad_oracle(y, fmax, dmel)
+    yt = torch.from_numpy(y).cuda().requires_grad_(True)
+    mel = pkg.mel_spectrogram(yt, a["n_fft"], a["num_mels"], a["sampling_rate"], a["hop_size"], a["win_size"], a["fmin"], fmax)
+    assert synth.mel_mismatch(mel.detach().cpu().numpy(), gold["out"].reshape(mel.shape)) <= 1.0
+    (mel * torch.from_numpy(dmel).cuda()).sum().backward()
+    got = yt.grad.cpu().double()
+    # bins at the 1e-5 clamp floor have gradient dmel/1e-5 * ...: compare relative to the gradient's own scale
+    err = float((got - ref).abs().max()) / float(ref.abs().max())
+    err_l2 = float((got - ref).norm() / ref.norm())
+    report(f"mel backward {name}: max |dy - ref| / max |ref| = {err:.2e}, relative L2 {err_l2:.2e}  (max |ref| = {float(ref.abs().max()):.3e})")
+    assert torch.isfinite(got).all()
+    if name == "mel_tone_silence":
+        # silence: mel sums sit AT the 1e-5 clamp (dataset.py:27-28), where the gradient is dmel / 1e-5 or 0 depending on
+        # which side fp32 rounding lands -- the fp32 kernel and the float64 checker legitimately pick different bins
+        assert err_l2 <= 2e-2
+    else:
+        assert err <= 2e-5
+
+
+@pytest.mark.gpu
+def test_generator_plus_mel_loss_step():
+    """The generator part of one training step as the reference composes it (train_time_wi_inv.py:173-179,231-235):
+    y_g = G(mel);  L = 45 * L1(mel(y), mel(y_g));  L.backward() -- gradients against the oracle port on CPU."""
+    cfg = synth.CONFIGS["hifigan_train"]
+    a = synth.HIFIGAN_V1
+    state = synth.make_state(cfg, 51, "unit")
+    mel_in = synth.make_mel(2, 8, 81)
+    y = synth.make_wave(2, 8 * 256, 82)
+    margs = (a["n_fft"], a["num_mels"], a["sampling_rate"], a["hop_size"], a["win_size"], a["fmin"], a["sampling_rate"] / 2)
+
+    gen = build_generator(cfg, state, "cuda").train()
+    y_g = gen(torch.from_numpy(mel_in).cuda())
+    loss = F.l1_loss(pkg.mel_spectrogram(torch.from_numpy(y).cuda(), *margs), pkg.mel_spectrogram(y_g, *margs)) * 45
+    loss.backward()
+
+    leaves = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in state.items()}
+    y_ref = torch_port.hifigan_forward_autograd(torch_port.fold_state(leaves), cfg, torch.from_numpy(mel_in))
+    loss_ref = F.l1_loss(torch_port.mel_spectrogram(torch.from_numpy(y), *margs), torch_port.mel_spectrogram(y_ref, *margs)) * 45
+    loss_ref.backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-4 * abs(float(loss_ref.detach()))
+    worst = 0.0
+    for k, p in gen.named_parameters():
+        gr = leaves[k].grad
+        worst = max(worst, float((p.grad.cpu() - gr).abs().max()) / (float(gr.abs().max()) + 1e-12))
+    report(f"generator + mel-L1 step: loss {float(loss.detach()):.5f} (oracle {float(loss_ref.detach()):.5f}), worst per-tensor rel. grad error {worst:.2e}")
+    assert worst <= 5e-3   # L1's sign() makes single entries flip between fp32 implementations
