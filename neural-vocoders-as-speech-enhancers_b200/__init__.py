@@ -10,7 +10,8 @@ from . import _lib  # noqa: F401
 from .dataset import mel_spectrogram  # noqa: F401
 from .Models import HiFiGAN, iSTFTNet  # noqa: F401
 from .pipeline import Vocoder  # noqa: F401
-from .shard import shard_range, shard_by_cost, bucket_by_length  # noqa: F401
+from .shard import shard_range, shard_by_cost, bucket_by_length, allreduce_gradients  # noqa: F401
 from . import melbasis, _engine  # noqa: F401
 
-__all__ = ["mel_spectrogram", "HiFiGAN", "iSTFTNet", "Vocoder", "shard_range", "shard_by_cost", "bucket_by_length"]
+__all__ = ["mel_spectrogram", "HiFiGAN", "iSTFTNet", "Vocoder", "shard_range", "shard_by_cost", "bucket_by_length",
+           "allreduce_gradients"]

@@ -14,10 +14,11 @@ namespace {
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.0f ? v : v * slope; }
 
-constexpr int WG_TILE = 64, WG_BK = 16;
+constexpr int WG_BK = 16;
 
-// 64 x WG_BK channel slab of one operand: row `r` of the chunk from `src_row` (null: zeros), channels c0 .. c0+63
-__device__ __forceinline__ void wg_load(float (*S)[WG_TILE], int r, int c4, const float* __restrict__ src_row, int c0, int C,
+// TILE x WG_BK channel slab of one operand: row `r` of the chunk from `src_row` (null: zeros), channels c0 .. c0+TILE-1
+template <int TILE>
+__device__ __forceinline__ void wg_load(float (*S)[TILE], int r, int c4, const float* __restrict__ src_row, int c0, int C,
                                         float slope) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   const int c = c0 + c4 * 4;
@@ -35,14 +36,17 @@ __device__ __forceinline__ void wg_load(float (*S)[WG_TILE], int r, int c4, cons
   *reinterpret_cast<float4*>(&S[r][c4 * 4]) = v;
 }
 
-// grid: (tiles_a * tiles_b, ntaps, nsplit); one 64 x 64 tile of G[tap] over rows [split * rows_per_split, +rows_per_split)
-__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int64_t rows_total, int rows_per_split, int tiles_b,
-                                                    float* __restrict__ partial) {
-  __shared__ __align__(16) float As[WG_BK][WG_TILE];  // As[row][ca]
-  __shared__ __align__(16) float Bs[WG_BK][WG_TILE];  // Bs[row][cb]
+// grid: (tiles_a * tiles_b, ntaps, nsplit); one TILE x TILE tile of G[tap] over rows [split * rows_per_split, +rows_per_split);
+// (TILE/4)^2 threads, 4 x 4 outputs each (TILE = 32 for the <= 32-channel layers: a 64-wide tile would idle 3/4 of the FMAs)
+template <int TILE>
+__global__ void __launch_bounds__((TILE / 4) * (TILE / 4)) wgrad_kernel(const WgradArgs a, int64_t rows_total, int rows_per_split,
+                                                                        int tiles_b, float* __restrict__ partial) {
+  constexpr int TQ = TILE / 4, NT = TQ * TQ;
+  __shared__ __align__(16) float As[WG_BK][TILE];  // As[row][ca]
+  __shared__ __align__(16) float Bs[WG_BK][TILE];  // Bs[row][cb]
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int ca0 = ((int)blockIdx.x / tiles_b) * WG_TILE, cb0 = ((int)blockIdx.x % tiles_b) * WG_TILE;
+  const int tx = tid % TQ, ty = tid / TQ;
+  const int ca0 = ((int)blockIdx.x / tiles_b) * TILE, cb0 = ((int)blockIdx.x % tiles_b) * TILE;
   const int tap = blockIdx.y, off = a.off[tap];
   const int64_t r_lo = (int64_t)blockIdx.z * rows_per_split;
   const int64_t r_hi = r_lo + rows_per_split < rows_total ? r_lo + rows_per_split : rows_total;
@@ -54,20 +58,23 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, int64_t r
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  const int l_row = tid >> 4, l_c4 = tid & 15;
   for (int64_t r0 = r_lo; r0 < r_hi; r0 += WG_BK) {
-    const int64_t r = r0 + l_row;
-    const float* urow = nullptr;
-    const float* vrow = nullptr;
-    if (r < r_hi) {
-      const int64_t b = r / a.Tv;
-      const int t = (int)(r - b * a.Tv);
-      const int64_t tu = (int64_t)u_stride * t + off;
-      vrow = a.V + b * a.v_bstride + (int64_t)t * a.Cb;
-      if (tu >= 0 && tu < a.Tu) urow = a.U + b * a.u_bstride + tu * a.Ca;
+#pragma unroll
+    for (int e = tid; e < WG_BK * TQ; e += NT) {  // WG_BK rows x TQ float4 per operand
+      const int l_row = e / TQ, l_c4 = e % TQ;
+      const int64_t r = r0 + l_row;
+      const float* urow = nullptr;
+      const float* vrow = nullptr;
+      if (r < r_hi) {
+        const int64_t b = r / a.Tv;
+        const int t = (int)(r - b * a.Tv);
+        const int64_t tu = (int64_t)u_stride * t + off;
+        vrow = a.V + b * a.v_bstride + (int64_t)t * a.Cb;
+        if (tu >= 0 && tu < a.Tu) urow = a.U + b * a.u_bstride + tu * a.Ca;
+      }
+      wg_load<TILE>(As, l_row, l_c4, urow, ca0, a.Ca, a.u_slope);
+      wg_load<TILE>(Bs, l_row, l_c4, urow ? vrow : nullptr, cb0, a.Cb, a.v_slope);
     }
-    wg_load(As, l_row, l_c4, urow, ca0, a.Ca, a.u_slope);
-    wg_load(Bs, l_row, l_c4, urow ? vrow : nullptr, cb0, a.Cb, a.v_slope);
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < WG_BK; ++kk) {
@@ -178,9 +185,11 @@ __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __res
 }
 
 struct WgSplit { int nsplit; int rows_per_split; };
+inline int wg_tile(int Ca, int Cb) { return (Ca <= 32 && Cb <= 32) ? 32 : 64; }
 WgSplit wg_split(int Ca, int Cb, int ntaps, int64_t rows) {
-  const int64_t tiles = (int64_t)((Ca + WG_TILE - 1) / WG_TILE) * ((Cb + WG_TILE - 1) / WG_TILE) * ntaps;
-  int64_t want = (592 + tiles - 1) / tiles;  // ~4 CTAs per SM in flight
+  const int tile = wg_tile(Ca, Cb);
+  const int64_t tiles = (int64_t)((Ca + tile - 1) / tile) * ((Cb + tile - 1) / tile) * ntaps;
+  int64_t want = ((tile == 32 ? 2368 : 592) + tiles - 1) / tiles;  // ~1024 threads per SM in flight
   const int64_t cap = (rows + 127) / 128;    // at least 128 rows per split
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -221,12 +230,14 @@ int launch_wgrad(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st)
   }
   const WgSplit s = wg_split(a.Ca, a.Cb, a.ntaps, rows);
   NVSE_REQUIRE(s.nsplit <= 65535, NVSE_ERR_INVALID, "wgrad: too many splits");
-  const int tiles_a = (a.Ca + WG_TILE - 1) / WG_TILE, tiles_b = (a.Cb + WG_TILE - 1) / WG_TILE;
+  const int tile = wg_tile(a.Ca, a.Cb);
+  const int tiles_a = (a.Ca + tile - 1) / tile, tiles_b = (a.Cb + tile - 1) / tile;
   {
     ProfScope prof("wgrad_f32", a.Ca, a.Cb, 2.0 * (double)rows * a.Ca * a.Cb * a.ntaps,
                    (double)rows * 4.0 * (a.Ca + a.Cb) * a.ntaps, st);
     dim3 grid((unsigned)(tiles_a * tiles_b), (unsigned)a.ntaps, (unsigned)s.nsplit);
-    wgrad_kernel<<<grid, 256, 0, st>>>(a, rows, s.rows_per_split, tiles_b, scratch);
+    if (tile == 32) wgrad_kernel<32><<<grid, 64, 0, st>>>(a, rows, s.rows_per_split, tiles_b, scratch);
+    else wgrad_kernel<64><<<grid, 256, 0, st>>>(a, rows, s.rows_per_split, tiles_b, scratch);
     NVSE_LAUNCH_CHECK("wgrad_kernel");
   }
   const int64_t n = (int64_t)a.ntaps * a.Ca * a.Cb;

@@ -75,3 +75,35 @@ def _worker(rank, world, port, n_utts):
 
 def test_two_rank_gloo_sharding():
     mp.spawn(_worker, args=(2, _free_port(), 37), nprocs=2, join=True)
+
+
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Conv1d(4, 8, 3), torch.nn.Conv1d(8, 1, 3))
+        frozen = net[1].bias
+        frozen.requires_grad_(False)
+        for i, p in enumerate(net.parameters()):
+            if p.requires_grad:
+                p.grad = torch.full_like(p, float(rank + 1) * (i + 1))   # rank-dependent "local" gradient
+        n = pkg.allreduce_gradients(list(net.parameters()))
+        assert n == sum(p.numel() for p in net.parameters() if p.requires_grad)
+        for i, p in enumerate(net.parameters()):
+            if p.requires_grad:
+                assert torch.equal(p.grad, torch.full_like(p, (i + 1) * (1 + world) / 2.0))   # the mean over ranks
+        assert frozen.grad is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce():
+    """Data-parallel training: one flat all-reduce of the generator gradients, mean written back per parameter."""
+    mp.spawn(_grad_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_allreduce_gradients_is_a_no_op_without_a_process_group():
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.full((3,), 2.0)
+    assert pkg.allreduce_gradients([p]) == 0 and torch.equal(p.grad, torch.full((3,), 2.0))
