@@ -196,7 +196,10 @@ NVSE_API int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t 
  * (nvse_generator_tape_bytes).  backward consumes the tape, the forward's output and dL/dout [B, samples]
  * and writes every layer's (dW, dbias) into the flat buffer `grads` (nvse_generator_grad_elems floats;
  * nvse_generator_grad_offset maps "<layer>.weight" / "<layer>.bias" to its slice, PyTorch layouts), and
- * dL/dmel [B, 80, frames] when dmel is not null.  Bit-reproducible (no atomics). */
+ * dL/dmel [B, 80, frames] when dmel is not null.  Bit-reproducible (no atomics).
+ * precision: NVSE_PRECISION_F32 = every gradient on the fp32 CUDA cores (parity gate: the fp32 reference);
+ * NVSE_PRECISION_BF16 = the weight gradients of the MRF convolutions (96 % of the FLOPs) on the tcgen05 tensor cores
+ * with bf16 operands and fp32 accumulation (mixed-precision training arithmetic); data gradients stay fp32. */
 NVSE_API size_t nvse_generator_tape_bytes(const nvse_generator* g, int64_t B, int64_t frames);
 NVSE_API size_t nvse_generator_backward_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames);
 NVSE_API int64_t nvse_generator_grad_elems(const nvse_generator* g);
@@ -205,7 +208,7 @@ NVSE_API int nvse_generator_forward_train(nvse_generator* g, const float* mel, i
                                  void* tape, size_t tape_bytes, void* stream);
 NVSE_API int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frames, const float* out, const float* dout,
                             const void* tape, size_t tape_bytes, float* grads, float* dmel, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            size_t workspace_bytes, int precision, void* stream);
 
 /* Backward of nvse_frontend_mel_f32 (the mel-L1 term of the generator loss differentiates
  * mel_spectrogram(y_g_hat), train_time_wi_inv.py:173-179,231-235): dmel [B, n_mels, frames] -> dy [B, T] (dense).
@@ -217,10 +220,11 @@ NVSE_API int nvse_frontend_mel_backward_f32(const nvse_frontend* fe, const float
 
 /* Layer-level backward (channels-last fp32, the layouts of nvse_conv1d_f32 / nvse_conv_transpose1d_f32):
  *   y = conv1d(lrelu(x, in_slope), w, dilation, "same") + bias [+ residual]
- *   dx = lrelu'(x) * conv^T(dy) [+ dresidual_in],  dw [Cout,Cin,k],  dbias [Cout];  any of dx/dw/dbias may be null. */
+ *   dx = lrelu'(x) * conv^T(dy) [+ dresidual_in],  dw [Cout,Cin,k],  dbias [Cout];  any of dx/dw/dbias may be null.
+ *   precision = NVSE_PRECISION_BF16: dw on the tensor cores (bf16 operands) where the shape allows, else fp32. */
 NVSE_API int nvse_conv1d_backward_f32(const float* x, const float* w, const float* dy, const float* dresidual_in,
                              float* dx, float* dw, float* dbias, int64_t B, int64_t T, int Cin, int Cout, int k,
-                             int dilation, float in_slope, void* stream);
+                             int dilation, float in_slope, int precision, void* stream);
 /*   y = conv_transpose1d(lrelu(x, in_slope), w, stride, padding) + bias;  dy: [B, T_out, Cout];  dw [Cin,Cout,k] */
 NVSE_API int nvse_conv_transpose1d_backward_f32(const float* x, const float* w, const float* dy, float* dx, float* dw,
                                        float* dbias, int64_t B, int64_t T, int Cin, int Cout, int k, int stride,

@@ -198,7 +198,7 @@ class GeneratorEngine:
                                                         _lib.ptr(tape), tape.numel(), stream))
         return out, tape
 
-    def backward(self, module, out, dout, tape, frames, want_dmel):
+    def backward(self, module, out, dout, tape, frames, want_dmel, precision=None):
         """-> (dict: folded tensor name -> gradient view, dmel or None)"""
         lib = _lib.load()
         dev = out.device
@@ -211,7 +211,8 @@ class GeneratorEngine:
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.nvse_generator_backward(self.handle, batch, frames, _lib.ptr(out), _lib.ptr(dout), _lib.ptr(tape),
-                                                   tape.numel(), _lib.ptr(grads), _lib.ptr(dmel), _lib.ptr(ws), ws.numel(), stream))
+                                                   tape.numel(), _lib.ptr(grads), _lib.ptr(dmel), _lib.ptr(ws), ws.numel(),
+                                                   resolve_precision(precision or getattr(module, "precision", None)), stream))
         views = {}
         off, n = C.c_int64(), C.c_int64()
         for name, m in self._conv_modules(module):

@@ -125,6 +125,7 @@ struct GradSink {
   float* scratch;
   int64_t B;
   cudaStream_t st;
+  int tc;  // weight gradients of the MRF convolutions on the tensor cores (bf16 operands)
   float* dw(const Layer& L) const { return grads + L.grad_off; }
   float* db(const Layer& L) const { return grads + L.grad_off + (int64_t)L.Cin * L.Cout * L.k; }
   // Conv1d: dW = scale * corr(lrelu(x_in, in_slope), dy), db = scale * sum dy
@@ -134,7 +135,7 @@ struct GradSink {
     w.V = dy; w.v_bstride = T * L.Cout; w.Tv = (int)T; w.Cb = L.Cout; w.v_slope = 1.0f;
     w.u_stride = 1; w.ntaps = L.k;
     for (int j = 0; j < L.k; ++j) w.off[j] = j * L.dilation - L.padding;
-    w.dst = dw(L); w.scale = scale;
+    w.dst = dw(L); w.scale = scale; w.tc = tc;
     if (int rc = launch_wgrad(w, B, scratch, st)) return rc;
     return launch_colsum(dy, B * T, L.Cout, db(L), scale, scratch, st);
   }
@@ -275,7 +276,7 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
 
 extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frames, const float* out, const float* dout,
                                        const void* tape, size_t tape_bytes, float* grads, float* dmel, void* workspace,
-                                       size_t workspace_bytes, void* stream) {
+                                       size_t workspace_bytes, int precision, void* stream) {
   NVSE_REQUIRE(g && out && dout && tape && grads && workspace, NVSE_ERR_INVALID, "nvse_generator_backward: null argument");
   NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_backward: call nvse_generator_finalize first");
   NVSE_REQUIRE(g->cfg.kind == NVSE_GEN_HIFIGAN, NVSE_ERR_UNSUPPORTED,
@@ -283,6 +284,7 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   NVSE_REQUIRE(B >= 1 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_backward: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
   NVSE_REQUIRE(tape_bytes >= nvse_generator_tape_bytes(g, B, frames), NVSE_ERR_INVALID, "tape too small");
   NVSE_REQUIRE(workspace_bytes >= nvse_generator_backward_workspace_bytes(g, B, frames), NVSE_ERR_INVALID, "workspace too small");
+  NVSE_REQUIRE(precision == NVSE_PRECISION_F32 || precision == NVSE_PRECISION_BF16, NVSE_ERR_INVALID, "bad precision %d", precision);
   const nvse_generator_config& c = g->cfg;
   const TapePlan p = make_tape(g, B, frames);
   const float* tp = reinterpret_cast<const float*>((reinterpret_cast<size_t>(tape) + 255) / 256 * 256);
@@ -296,7 +298,7 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   float* gR = ws + 3 * be;   // running gradient of the residual stream (ping)
   float* gS = ws + 4 * be;   //                                         (pong)
   float* dz = ws + 5 * be;   // gradient w.r.t. the conv_post output
-  const GradSink sink{g, grads, ws + kBwdBuffers * be, B, st};
+  const GradSink sink{g, grads, ws + kBwdBuffers * be, B, st, precision == NVSE_PRECISION_BF16 ? 1 : 0};
   const float slope = 0.1f;
   const float inv = 1.0f / (float)c.num_kernels;
 

@@ -217,7 +217,14 @@ CsSplit cs_split(int C, int64_t rows) {
 
 size_t wgrad_scratch_elems(int Ca, int Cb, int ntaps, int64_t B, int Tv) {
   const WgSplit s = wg_split(Ca, Cb, ntaps, B * Tv);
-  return (size_t)s.nsplit * ntaps * Ca * Cb;
+  return std::max((size_t)s.nsplit * ntaps * Ca * Cb, wgrad_tc_scratch_elems(Ca, Cb, ntaps, B, Tv));
+}
+
+int launch_wgrad_reduce(const float* partial, int nsplit, int ntaps, int Ca, int Cb, float* dst, float scale, cudaStream_t st) {
+  const int64_t n = (int64_t)ntaps * Ca * Cb;
+  wgrad_reduce_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, st>>>(partial, nsplit, ntaps, Ca, Cb, dst, scale);
+  NVSE_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return NVSE_OK;
 }
 
 int launch_wgrad(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st) {
@@ -228,6 +235,7 @@ int launch_wgrad(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st)
     NVSE_CUDA_CHECK(cudaMemsetAsync(a.dst, 0, sizeof(float) * (size_t)a.ntaps * a.Ca * a.Cb, st));
     return NVSE_OK;
   }
+  if (a.tc && wgrad_tc_supported(a.Ca, a.Cb, a.ntaps, a.off, a.u_stride, B, a.Tv)) return launch_wgrad_tc(a, B, scratch, st);
   const WgSplit s = wg_split(a.Ca, a.Cb, a.ntaps, rows);
   NVSE_REQUIRE(s.nsplit <= 65535, NVSE_ERR_INVALID, "wgrad: too many splits");
   const int tile = wg_tile(a.Ca, a.Cb);
@@ -240,11 +248,7 @@ int launch_wgrad(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st)
     else wgrad_kernel<64><<<grid, 256, 0, st>>>(a, rows, s.rows_per_split, tiles_b, scratch);
     NVSE_LAUNCH_CHECK("wgrad_kernel");
   }
-  const int64_t n = (int64_t)a.ntaps * a.Ca * a.Cb;
-  wgrad_reduce_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, st>>>(scratch, s.nsplit, a.ntaps, a.Ca, a.Cb,
-                                                                                         a.dst, a.scale);
-  NVSE_LAUNCH_CHECK("wgrad_reduce_kernel");
-  return NVSE_OK;
+  return launch_wgrad_reduce(scratch, s.nsplit, a.ntaps, a.Ca, a.Cb, a.dst, a.scale, st);
 }
 
 size_t colsum_scratch_elems(int C, int64_t rows) { return (size_t)cs_split(C, rows).nsplit * C; }
@@ -308,7 +312,7 @@ using namespace nvse;
 
 extern "C" int nvse_conv1d_backward_f32(const float* x, const float* w, const float* dy, const float* dresidual_in,
                                         float* dx, float* dw, float* dbias, int64_t B, int64_t T, int Cin, int Cout, int k,
-                                        int dilation, float in_slope, void* stream) {
+                                        int dilation, float in_slope, int precision, void* stream) {
   NVSE_REQUIRE(x && w && dy, NVSE_ERR_INVALID, "nvse_conv1d_backward_f32: null argument");
   NVSE_REQUIRE(B >= 0 && T >= 0 && Cin > 0 && Cout > 0 && dilation >= 1, NVSE_ERR_INVALID, "nvse_conv1d_backward_f32: bad shape");
   NVSE_REQUIRE(k >= 1 && (k & 1) && k <= kMaxTaps, NVSE_ERR_UNSUPPORTED, "nvse_conv1d_backward_f32: k=%d (odd k <= %d only)", k, kMaxTaps);
@@ -337,7 +341,7 @@ extern "C" int nvse_conv1d_backward_f32(const float* x, const float* w, const fl
     g.V = dy; g.v_bstride = T * Cout; g.Tv = (int)T; g.Cb = Cout; g.v_slope = 1.0f;
     g.u_stride = 1; g.ntaps = k;
     for (int j = 0; j < k; ++j) g.off[j] = j * dilation - pad;
-    g.dst = dw; g.scale = 1.0f;
+    g.dst = dw; g.scale = 1.0f; g.tc = precision == NVSE_PRECISION_BF16;
     Scratch sc(st);
     NVSE_CUDA_CHECK(sc.alloc(wgrad_scratch_elems(Cin, Cout, k, B, (int)T)));
     if (int rc = launch_wgrad(g, B, sc.p, st)) return rc;

@@ -21,10 +21,19 @@ struct WgradArgs {
   int ntaps; int off[kMaxTaps];
   float* dst;
   float scale;
+  int tc;   // use the tcgen05 kernel (wgrad_tc.cu: bf16 operands, fp32 accumulate) when it supports the shape
 };
 // scratch floats needed by launch_wgrad for this shape (partial sums of the split reduction, deterministic order)
 size_t wgrad_scratch_elems(int Ca, int Cb, int ntaps, int64_t B, int Tv);
 int launch_wgrad(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st);
+// dst[(cb*Ca + ca)*ntaps + j] = scale * sum_s partial[s][j][ca][cb], s ascending
+int launch_wgrad_reduce(const float* partial, int nsplit, int ntaps, int Ca, int Cb, float* dst, float scale, cudaStream_t st);
+
+// wgrad_tc.cu: the same correlation on the tensor cores (stride-1 U, Cb in {32, 64, 128, 256}, Ca a multiple of 8)
+bool wgrad_tc_supported(int Ca, int Cb, int ntaps, const int* off, int u_stride, int64_t B, int Tv);
+size_t wgrad_tc_scratch_elems(int Ca, int Cb, int ntaps, int64_t B, int Tv);
+int launch_wgrad_tc(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st);
+int wgrad_abort_status(bool reset, unsigned int* flag);
 
 // dst[c] = scale * sum over rows of V[row][c]   (bias gradient; V dense [rows, C]);  scratch: colsum_scratch_elems floats
 size_t colsum_scratch_elems(int C, int64_t rows);

@@ -6,6 +6,7 @@
 #include "conv_tc.cuh"
 #include "generator.cuh"
 #include "resblock_tc.cuh"
+#include "grad.cuh"
 
 using namespace nvse;
 
@@ -141,8 +142,9 @@ extern "C" int nvse_tc_abort_status(int reset, int* flag) {
   unsigned int v = 0, v2 = 0;
   if (int rc = tc_abort_status(reset != 0, &v)) return rc;
   if (int rc = rb_abort_status(reset != 0, &v2)) return rc;
-  unsigned int v3 = 0;
+  unsigned int v3 = 0, v4 = 0;
   if (int rc = pair_abort_status(reset != 0, &v3)) return rc;
-  *flag = (int)(v | v2 | v3);
+  if (int rc = wgrad_abort_status(reset != 0, &v4)) return rc;
+  *flag = (int)(v | v2 | v3 | v4);
   return NVSE_OK;
 }

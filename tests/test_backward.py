@@ -95,7 +95,7 @@ def test_conv1d_backward_layer(case):
     db = torch.full((cout,), float("nan"), device="cuda")
     lib_mod.check(lib.nvse_conv1d_backward_f32(lib_mod.ptr(x_cl), lib_mod.ptr(w.detach().contiguous()), lib_mod.ptr(dy_cl),
                                                lib_mod.ptr(dres_cl), lib_mod.ptr(dx), lib_mod.ptr(dw), lib_mod.ptr(db),
-                                               b, t, cin, cout, k, d, slope, stream_ptr()))
+                                               b, t, cin, cout, k, d, slope, lib_mod.PRECISION_F32, stream_ptr()))
     torch.cuda.synchronize()
     assert _close(dx.transpose(1, 2), dx_ref), "dx"
     assert _close(dw, w.grad), "dw"
@@ -158,8 +158,9 @@ def test_weight_norm_backward():
 # ---------------------------------------------------------------------------------------------
 # GPU: the whole generator under torch autograd through the drop-in module
 # ---------------------------------------------------------------------------------------------
-def _module_grads(cfg, state, mel, dout, remove_wn=False):
+def _module_grads(cfg, state, mel, dout, remove_wn=False, precision="fp32"):
     gen = build_generator(cfg, state, "cuda", remove_wn=remove_wn).train()
+    gen.precision = precision
     x = torch.from_numpy(mel).cuda().requires_grad_(True)
     out = gen(x)
     (out * torch.from_numpy(dout).cuda()).sum().backward()
@@ -317,3 +318,65 @@ def test_generator_plus_mel_loss_step():
         worst = max(worst, float((p.grad.cpu() - gr).abs().max()) / (float(gr.abs().max()) + 1e-12))
     report(f"generator + mel-L1 step: loss {float(loss.detach()):.5f} (oracle {float(loss_ref.detach()):.5f}), worst per-tensor rel. grad error {worst:.2e}")
     assert worst <= 5e-3   # L1's sign() makes single entries flip between fp32 implementations
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core weight gradients (precision "bf16": bf16 operands, fp32 accumulation)
+# ---------------------------------------------------------------------------------------------
+WGRAD_TC_CASES = [  # Cin, Cout, k, dilation, B, T
+    (32, 32, 11, 5, 2, 700),
+    (64, 64, 3, 1, 3, 129),
+    (128, 128, 7, 3, 2, 513),
+    (256, 256, 11, 1, 1, 260),
+    (64, 64, 11, 5, 1, 40),      # shorter than the receptive field, one partial chunk
+    (128, 128, 3, 5, 16, 2048),  # many chunks per split
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", WGRAD_TC_CASES)
+def test_conv1d_weight_gradient_tensor_core(case):
+    cin, cout, k, d, b, t = case
+    _no_tf32()
+    gen = torch.Generator(device="cuda").manual_seed(cin + 3 * k + d)
+    x = torch.randn(b, cin, t, device="cuda", generator=gen)
+    w = torch.randn(cout, cin, k, device="cuda", generator=gen) / np.sqrt(cin * k)
+    dy = torch.randn(b, cout, t, device="cuda", generator=gen)
+    # the exact result for bf16-rounded operands (what the kernel is specified to compute), in float64
+    xr = F.leaky_relu(x, 0.1).bfloat16().double()
+    dyr = dy.bfloat16().double()
+    ref = torch.nn.grad.conv1d_weight(xr, w.shape, dyr, dilation=d, padding=(k * d - d) // 2)
+    ref32 = torch.nn.grad.conv1d_weight(F.leaky_relu(x, 0.1).double(), w.shape, dy.double(), dilation=d, padding=(k * d - d) // 2)
+    lib = lib_mod.load()
+    x_cl, dy_cl = x.transpose(1, 2).contiguous(), dy.transpose(1, 2).contiguous()
+    dw = torch.full((cout, cin, k), float("nan"), device="cuda")
+    lib_mod.check(lib.nvse_conv1d_backward_f32(lib_mod.ptr(x_cl), lib_mod.ptr(w), lib_mod.ptr(dy_cl), None, None, lib_mod.ptr(dw),
+                                               None, b, t, cin, cout, k, d, 0.1, lib_mod.PRECISION_BF16, stream_ptr()))
+    torch.cuda.synchronize()
+    assert not lib_mod.tc_abort_status()
+    err = float((dw.double() - ref).abs().max()) / float(ref.abs().max())
+    err32 = float((dw.double() - ref32).norm() / ref32.norm())
+    report(f"wgrad_tc C={cin} k={k} d={d} B={b} T={t}: vs bf16-operand reference {err:.2e} (max-rel), vs fp32 operands {err32:.2e} (rel. L2)")
+    assert err <= 2e-5
+    assert err32 <= 1e-2
+
+
+@pytest.mark.gpu
+def test_generator_backward_bf16_weight_gradients():
+    """precision 'bf16': MRF weight gradients on the tensor cores; everything else identical to the fp32 path."""
+    gold = synth.load_golden("grads_hifigan_train_f6")
+    meta = gold["meta"]
+    cfg = synth.CONFIGS[meta["cfg"]]
+    state = synth.make_state(cfg, meta["weight_seed"], meta["regime"])
+    _, g32, d32, _ = _module_grads(cfg, state, gold["mel"], gold["dout"], precision="fp32")
+    out, g16, d16, _ = _module_grads(cfg, state, gold["mel"], gold["dout"], precision="bf16")
+    assert not lib_mod.tc_abort_status()
+    assert torch.equal(d16, d32)   # data gradients do not depend on the weight-gradient arithmetic
+    worst = 0.0
+    for k, gr in g32.items():
+        if k.endswith("bias"):
+            assert torch.equal(g16[k], gr), k
+        else:
+            worst = max(worst, float((g16[k] - gr).norm() / (gr.norm() + 1e-20)))
+    report(f"backward bf16 weight gradients: worst per-tensor relative L2 difference to the fp32 path {worst:.2e}")
+    assert worst <= 1e-2
