@@ -198,14 +198,15 @@ NVSE_API int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t 
  * nvse_generator_grad_offset maps "<layer>.weight" / "<layer>.bias" to its slice, PyTorch layouts), and
  * dL/dmel [B, 80, frames] when dmel is not null.  Bit-reproducible (no atomics).
  * precision: NVSE_PRECISION_F32 = every gradient on the fp32 CUDA cores (parity gate: the fp32 reference);
- * NVSE_PRECISION_BF16 = the weight gradients of the MRF convolutions (96 % of the FLOPs) on the tcgen05 tensor cores
- * with bf16 operands and fp32 accumulation (mixed-precision training arithmetic); data gradients stay fp32. */
+ * NVSE_PRECISION_BF16 = the MRF convolutions (96 % of the FLOPs) on the tcgen05 tensor cores in the forward, the data
+ * gradients and the weight gradients, with bf16 operands and fp32 accumulation (mixed-precision training arithmetic;
+ * activations, gradients and the tape stay fp32); conv_pre, the upsamplers and conv_post stay on the fp32 path. */
 NVSE_API size_t nvse_generator_tape_bytes(const nvse_generator* g, int64_t B, int64_t frames);
 NVSE_API size_t nvse_generator_backward_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames);
 NVSE_API int64_t nvse_generator_grad_elems(const nvse_generator* g);
 NVSE_API int nvse_generator_grad_offset(const nvse_generator* g, const char* name, int64_t* offset, int64_t* numel);
 NVSE_API int nvse_generator_forward_train(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
-                                 void* tape, size_t tape_bytes, void* stream);
+                                 void* tape, size_t tape_bytes, int precision, void* stream);
 NVSE_API int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frames, const float* out, const float* dout,
                             const void* tape, size_t tape_bytes, float* grads, float* dmel, void* workspace,
                             size_t workspace_bytes, int precision, void* stream);

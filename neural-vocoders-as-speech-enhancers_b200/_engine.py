@@ -176,7 +176,7 @@ class GeneratorEngine:
 
     # ---- training (fp32) -------------------------------------------------------------
     def forward_train(self, module, x):
-        """fp32 forward that keeps every convolution input on a tape; returns (out, tape, xd)."""
+        """Forward that keeps every convolution input on an fp32 tape; returns (out, tape, precision)."""
         if self.kind != _lib.GEN_HIFIGAN:
             raise NotImplementedError("the B200 training path covers HiFiGAN; iSTFTNet's iSTFT head has no backward kernel yet")
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
@@ -194,11 +194,12 @@ class GeneratorEngine:
         tape = torch.empty(lib.nvse_generator_tape_bytes(self.handle, batch, frames), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            prec = resolve_precision(getattr(module, "precision", None))
             _lib.check(lib.nvse_generator_forward_train(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
-                                                        _lib.ptr(tape), tape.numel(), stream))
-        return out, tape
+                                                        _lib.ptr(tape), tape.numel(), prec, stream))
+        return out, tape, prec
 
-    def backward(self, module, out, dout, tape, frames, want_dmel, precision=None):
+    def backward(self, module, out, dout, tape, frames, want_dmel, precision):
         """-> (dict: folded tensor name -> gradient view, dmel or None)"""
         lib = _lib.load()
         dev = out.device
@@ -212,7 +213,7 @@ class GeneratorEngine:
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             _lib.check(lib.nvse_generator_backward(self.handle, batch, frames, _lib.ptr(out), _lib.ptr(dout), _lib.ptr(tape),
                                                    tape.numel(), _lib.ptr(grads), _lib.ptr(dmel), _lib.ptr(ws), ws.numel(),
-                                                   resolve_precision(precision or getattr(module, "precision", None)), stream))
+                                                   precision, stream))
         views = {}
         off, n = C.c_int64(), C.c_int64()
         for name, m in self._conv_modules(module):
@@ -227,8 +228,8 @@ class _GeneratorTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, engine, module, x, *params):
-        out, tape = engine.forward_train(module, x)
-        ctx.engine, ctx.module, ctx.tape = engine, module, tape
+        out, tape, prec = engine.forward_train(module, x)
+        ctx.engine, ctx.module, ctx.tape, ctx.prec = engine, module, tape, prec
         ctx.frames, ctx.x_device, ctx.x_dtype = x.shape[2], x.device, x.dtype
         ctx.key = engine.weights_key
         ctx.save_for_backward(out)
@@ -243,7 +244,7 @@ class _GeneratorTrainFn(torch.autograd.Function):
             raise RuntimeError("generator parameters changed between forward and backward")
         lib = _lib.load()
         want_dmel = ctx.needs_input_grad[2]
-        folded, dmel = engine.backward(module, out, dout, ctx.tape, ctx.frames, want_dmel)
+        folded, dmel = engine.backward(module, out, dout, ctx.tape, ctx.frames, want_dmel, ctx.prec)
         ctx.tape = None
         grads = {}
         dev = out.device

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
           const float* rr = a.residual ? a.residual + yoff : nullptr;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            bq[q] = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q);
+            bq[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             rq[q] = (valid && rr) ? *reinterpret_cast<const float4*>(rr + qs * q) : make_float4(0.f, 0.f, 0.f, 0.f);
             yq[q] = (valid && a.accumulate) ? *reinterpret_cast<const float4*>(yr + qs * q) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -312,6 +312,13 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
               if (a.out_slope != 1.0f) {
                 o.x = lrelu(o.x, a.out_slope); o.y = lrelu(o.y, a.out_slope);
                 o.z = lrelu(o.z, a.out_slope); o.w = lrelu(o.w, a.out_slope);
+              }
+              if (a.mask) {  // dgrad: the derivative of the leaky_relu in front of the layer
+                const float4 mq = *reinterpret_cast<const float4*>(a.mask + yoff + qs * q);
+                if (!(mq.x > 0.0f)) o.x *= a.mask_slope;
+                if (!(mq.y > 0.0f)) o.y *= a.mask_slope;
+                if (!(mq.z > 0.0f)) o.z *= a.mask_slope;
+                if (!(mq.w > 0.0f)) o.w *= a.mask_slope;
               }
               o.x = (o.x + rq[q].x) * a.out_scale + yq[q].x;
               o.y = (o.y + rq[q].y) * a.out_scale + yq[q].y;
@@ -382,6 +389,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   NVSE_REQUIRE(nphase >= 1 && nphase <= kMaxPhases, NVSE_ERR_INVALID, "tensor-core conv: %d phases per launch", nphase);
   NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "tensor-core conv: batch %lld exceeds 65535 per launch", (long long)B);
   NVSE_REQUIRE(!(a.out_bf16 && (a.residual || a.accumulate)), NVSE_ERR_INVALID, "tensor-core conv: bf16 output takes no residual");
+  NVSE_REQUIRE(!(a.out_bf16 && (a.mask || !a.bias)), NVSE_ERR_INVALID, "tensor-core conv: bf16 output needs a bias and takes no mask");
   NVSE_REQUIRE(!(a.split_act && a.in_bf16), NVSE_ERR_INVALID, "tensor-core conv: split activations need fp32 input");
   NVSE_REQUIRE(!(a.x_t32 && a.in_bf16) && !(a.y_t32 && a.out_bf16), NVSE_ERR_INVALID, "tensor-core conv: the T32 layout is fp32 only");
   NVSE_REQUIRE(!(a.ops_f16 && (a.in_bf16 || a.split_act)), NVSE_ERR_INVALID, "tensor-core conv: half operands need fp32 input and no split");

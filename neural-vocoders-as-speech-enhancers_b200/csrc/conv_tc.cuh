@@ -24,7 +24,7 @@ struct ConvTcArgs {
   int in_bf16;
   int x_t32;           // fp32 x is in the T32 layout (common.cuh); x_bstride then counts padded rows
   const __nv_bfloat16* wimg;
-  const float* bias;
+  const float* bias;      // [Cout] or null
   const float* residual;  // fp32, same shape as y (fp32 output only; added after the out_slope activation)
   void* y;                // [B, Tout, Cout] fp32, or bf16 when out_bf16
   int64_t y_bstride;
@@ -36,6 +36,8 @@ struct ConvTcArgs {
   float in_slope, out_slope, out_scale;
   int accumulate;
   int split_act;          // stage activations as hi + lo bf16 planes (fp32 input only): 2 MMAs per K step
+  const float* mask;      // backward (dgrad): same shape as y, or null -- conv *= (mask > 0 ? 1 : mask_slope) before `residual`
+  float mask_slope;       //   is added (the leaky_relu derivative of the layer input); fp32 channels-last output only
   int ops_f16;            // stage the (fp32) activations as IEEE half; `wimg` must then be a half image.  Used by the
                           // upsamplers, where bf16 rounding of the WEIGHTS is the largest error of the whole path
 };

@@ -392,6 +392,7 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     cudaFree(L.w_bf16);
     cudaFree(L.w_f16);
     cudaFree(L.wT);
+    cudaFree(L.wT_bf16);
   }
   delete g;
   return NVSE_OK;

@@ -21,6 +21,7 @@ struct Layer {
   bool tc_f16 = false;     // IEEE-half operands (w_f16) on the tensor-core path: the upsamplers
   bool have_w = false, have_bias = false;
   float* wT = nullptr;     // training path: per-tap transposed weights [k][Cout][Cin] (the dgrad operand), built lazily
+  void* wT_bf16 = nullptr; // training path, tensor-core dgrad: the bf16 image of wT (as a layer with Cin <-> Cout)
   int64_t grad_off = 0;    // offset of this layer's (dW, dbias) in the flat gradient buffer of nvse_generator_backward
 };
 

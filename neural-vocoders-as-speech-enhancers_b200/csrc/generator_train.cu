@@ -1,4 +1,4 @@
-// Training path of the generator handle (fp32): a forward that keeps the input of every convolution
+// Training path of the generator handle (fp32, or tensor cores for the MRF convolutions): a forward that keeps the input of every convolution
 // on a caller-owned tape, and the backward that walks it.  Reference: the generator step of
 // train_time_wi_inv.py:222-236 (loss.backward() through HiFiGAN.forward, Models/hifigan.py:108-124;
 // ResBlock1/2 hifigan.py:43-50,71-76).  Gradients are produced for the FOLDED weights (weight, bias of
@@ -11,6 +11,7 @@
 // derivative mask and the "+ g" are its epilogue (conv_f32.cu), and corr is grad.cu's split reduction.
 #include "generator.cuh"
 #include "grad.cuh"
+#include "conv_tc.cuh"
 
 #include <cstring>
 
@@ -62,7 +63,18 @@ TapePlan make_tape(const nvse_generator* g, int64_t B, int64_t F) {
 
 // fp32 Conv1d layer:  y = [accumulate ? y : 0] + out_scale * (conv(lrelu(x, in_slope)) + bias [+ residual])
 int conv_fwd(const Layer& L, const float* x, const float* residual, float* y, int64_t B, int64_t T, float in_slope,
-             float out_scale, int accumulate, int out_act, cudaStream_t st) {
+             float out_scale, int accumulate, int out_act, cudaStream_t st, bool tc = false) {
+  if (tc && L.w_bf16 && !L.transposed && out_act == 0) {  // MRF convolutions on the tensor cores (bf16 operands, fp32 in / out)
+    ConvTcArgs t{};
+    t.x = x; t.x_bstride = T * L.Cin; t.Tin = (int)T; t.Cin = L.Cin; t.Cout = L.Cout;
+    t.wimg = reinterpret_cast<const __nv_bfloat16*>(L.w_bf16); t.bias = L.bias; t.residual = residual;
+    t.y = y; t.y_bstride = T * L.Cout; t.Tout = (int)T;
+    conv1d_taps(L.k, L.dilation, &t.taps);
+    t.out_mul = 1; t.Trows = (int)T;
+    t.in_slope = in_slope; t.out_slope = 1.0f; t.out_scale = out_scale; t.accumulate = accumulate;
+    t.split_act = L.tc_split;
+    return launch_conv_tc(t, B, st);
+  }
   ConvF32Args a{};
   a.x = x; a.x_bstride = T * L.Cin; a.Tin = (int)T; a.Cin = L.Cin;
   a.w = L.w; a.bias = L.bias; a.residual = residual;
@@ -91,7 +103,19 @@ int convT_fwd(const Layer& L, const float* x, float* y, int64_t B, int64_t Tin, 
 
 // data gradient of a Conv1d layer:  dx = [accumulate ? dx : 0] + out_scale * (lrelu'(x_in) * conv^T(dy) [+ dres])
 int conv_dgrad(const Layer& L, const float* dy, const float* x_in, float mask_slope, const float* dres, float* dx, int64_t B,
-               int64_t T, float out_scale, int accumulate, cudaStream_t st) {
+               int64_t T, float out_scale, int accumulate, cudaStream_t st, bool tc = false) {
+  if (tc && L.wT_bf16) {
+    ConvTcArgs t{};
+    t.x = dy; t.x_bstride = T * L.Cout; t.Tin = (int)T; t.Cin = L.Cout; t.Cout = L.Cin;
+    t.wimg = reinterpret_cast<const __nv_bfloat16*>(L.wT_bf16); t.residual = dres;
+    t.y = dx; t.y_bstride = T * L.Cin; t.Tout = (int)T;
+    t.taps.ntaps = L.k;
+    for (int j = 0; j < L.k; ++j) { t.taps.off[j] = L.padding - j * L.dilation; t.taps.widx[j] = j; }
+    t.out_mul = 1; t.Trows = (int)T;
+    t.in_slope = 1.0f; t.out_slope = 1.0f; t.out_scale = out_scale; t.accumulate = accumulate;
+    if (x_in && mask_slope != 1.0f) { t.mask = x_in; t.mask_slope = mask_slope; }
+    return launch_conv_tc(t, B, st);
+  }
   ConvF32Args a{};
   a.x = dy; a.x_bstride = T * L.Cout; a.Tin = (int)T; a.Cin = L.Cout;
   a.w = L.wT; a.residual = dres;
@@ -177,6 +201,10 @@ int prepare_train(nvse_generator* g, cudaStream_t st) {
   for (Layer& L : g->layers) {
     if (!L.wT) NVSE_CUDA_CHECK(cudaMalloc(&L.wT, sizeof(float) * (size_t)L.Cin * L.Cout * L.k));
     if (int rc = launch_transpose_taps(L.w, L.wT, L.k, L.Cin, L.Cout, st)) return rc;
+    if (L.w_bf16 && !L.transposed && tc_supported(L.Cout, L.Cin)) {  // the dgrad is a layer with Cin <-> Cout
+      if (!L.wT_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.wT_bf16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cout, L.Cin, L.k)));
+      if (int rc = launch_pack_weight_tc(L.wT, reinterpret_cast<__nv_bfloat16*>(L.wT_bf16), L.Cout, L.Cin, L.k, st)) return rc;
+    }
   }
   g->train_ready = true;
   return NVSE_OK;
@@ -224,18 +252,20 @@ extern "C" int nvse_generator_grad_offset(const nvse_generator* g, const char* n
 }
 
 extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
-                                            void* tape, size_t tape_bytes, void* stream) {
+                                            void* tape, size_t tape_bytes, int precision, void* stream) {
   NVSE_REQUIRE(g && mel && out && tape, NVSE_ERR_INVALID, "nvse_generator_forward_train: null argument");
   NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_forward_train: call nvse_generator_finalize first");
   NVSE_REQUIRE(g->cfg.kind == NVSE_GEN_HIFIGAN, NVSE_ERR_UNSUPPORTED,
                "the training path covers HiFiGAN; the iSTFT head has no backward kernel yet");
   NVSE_REQUIRE(B >= 1 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_forward_train: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
   NVSE_REQUIRE(tape_bytes >= nvse_generator_tape_bytes(g, B, frames), NVSE_ERR_INVALID, "tape too small");
+  NVSE_REQUIRE(precision == NVSE_PRECISION_F32 || precision == NVSE_PRECISION_BF16, NVSE_ERR_INVALID, "bad precision %d", precision);
   const nvse_generator_config& c = g->cfg;
   const TapePlan p = make_tape(g, B, frames);
   float* tp = reinterpret_cast<float*>((reinterpret_cast<size_t>(tape) + 255) / 256 * 256);
   cudaStream_t st = as_stream(stream);
   const float slope = 0.1f;  // LRELU_SLOPE, hifigan.py:7
+  const bool tc = precision == NVSE_PRECISION_BF16;
 
   if (int rc = launch_transpose(mel, tp + p.melT, B, c.in_channels, frames, st)) return rc;
   if (int rc = conv_fwd(g->layer("conv_pre"), tp + p.melT, nullptr, tp + p.x_pre, B, frames, 1.0f, 1.0f, 0, 0, st)) return rc;
@@ -259,10 +289,10 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
         const int accum = last && j > 0;
         if (c.resblock_type == 1) {  // hifigan.py:43-50
           float* h = tp + p.h[i][j][m];
-          if (int rc = conv_fwd(g->layer(pj + ".convs1." + std::to_string(m)), src, nullptr, h, B, T, slope, 1.0f, 0, 0, st)) return rc;
-          if (int rc = conv_fwd(g->layer(pj + ".convs2." + std::to_string(m)), h, src, dst, B, T, slope, scale, accum, 0, st)) return rc;
+          if (int rc = conv_fwd(g->layer(pj + ".convs1." + std::to_string(m)), src, nullptr, h, B, T, slope, 1.0f, 0, 0, st, tc)) return rc;
+          if (int rc = conv_fwd(g->layer(pj + ".convs2." + std::to_string(m)), h, src, dst, B, T, slope, scale, accum, 0, st, tc)) return rc;
         } else {  // hifigan.py:71-76
-          if (int rc = conv_fwd(g->layer(pj + ".convs." + std::to_string(m)), src, src, dst, B, T, slope, scale, accum, 0, st)) return rc;
+          if (int rc = conv_fwd(g->layer(pj + ".convs." + std::to_string(m)), src, src, dst, B, T, slope, scale, accum, 0, st, tc)) return rc;
         }
         src = dst;
       }
@@ -298,7 +328,8 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   float* gR = ws + 3 * be;   // running gradient of the residual stream (ping)
   float* gS = ws + 4 * be;   //                                         (pong)
   float* dz = ws + 5 * be;   // gradient w.r.t. the conv_post output
-  const GradSink sink{g, grads, ws + kBwdBuffers * be, B, st, precision == NVSE_PRECISION_BF16 ? 1 : 0};
+  const bool tc = precision == NVSE_PRECISION_BF16;
+  const GradSink sink{g, grads, ws + kBwdBuffers * be, B, st, tc ? 1 : 0};
   const float slope = 0.1f;
   const float inv = 1.0f / (float)c.num_kernels;
 
@@ -326,13 +357,13 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
           const Layer& c1 = g->layer(pj + ".convs1." + std::to_string(m));
           const Layer& c2 = g->layer(pj + ".convs2." + std::to_string(m));
           const float* h = tp + p.h[i][j][m];
-          if (int rc = conv_dgrad(c2, gcur, h, slope, nullptr, gT, B, T, 1.0f, 0, st)) return rc;
+          if (int rc = conv_dgrad(c2, gcur, h, slope, nullptr, gT, B, T, 1.0f, 0, st, tc)) return rc;
           if (int rc = sink.conv(c2, h, slope, gcur, T, inv)) return rc;
-          if (int rc = conv_dgrad(c1, gT, x_m, slope, gcur, gnext, B, T, oscale, accum, st)) return rc;
+          if (int rc = conv_dgrad(c1, gT, x_m, slope, gcur, gnext, B, T, oscale, accum, st, tc)) return rc;
           if (int rc = sink.conv(c1, x_m, slope, gT, T, inv)) return rc;
         } else {
           const Layer& cv = g->layer(pj + ".convs." + std::to_string(m));
-          if (int rc = conv_dgrad(cv, gcur, x_m, slope, gcur, gnext, B, T, oscale, accum, st)) return rc;
+          if (int rc = conv_dgrad(cv, gcur, x_m, slope, gcur, gnext, B, T, oscale, accum, st, tc)) return rc;
           if (int rc = sink.conv(cv, x_m, slope, gcur, T, inv)) return rc;
         }
         gcur = gnext;

@@ -303,6 +303,7 @@ def test_generator_plus_mel_loss_step():
     margs = (a["n_fft"], a["num_mels"], a["sampling_rate"], a["hop_size"], a["win_size"], a["fmin"], a["sampling_rate"] / 2)
 
     gen = build_generator(cfg, state, "cuda").train()
+    gen.precision = "fp32"
     y_g = gen(torch.from_numpy(mel_in).cuda())
     loss = F.l1_loss(pkg.mel_spectrogram(torch.from_numpy(y).cuda(), *margs), pkg.mel_spectrogram(y_g, *margs)) * 45
     loss.backward()
@@ -362,21 +363,28 @@ def test_conv1d_weight_gradient_tensor_core(case):
 
 
 @pytest.mark.gpu
-def test_generator_backward_bf16_weight_gradients():
-    """precision 'bf16': MRF weight gradients on the tensor cores; everything else identical to the fp32 path."""
-    gold = synth.load_golden("grads_hifigan_train_f6")
+@pytest.mark.parametrize("name", ["grads_hifigan_train_f6", "grads_hifigan_train_rb2_f5"])
+def test_generator_backward_tensor_core_path(name):
+    """precision 'bf16' (the default): the MRF convolutions run on the tensor cores in the forward, the data gradients and
+    the weight gradients (bf16 operands, fp32 accumulate).  Checked against the fp32 CUDA path and the fixture output."""
+    gold = synth.load_golden(name)
     meta = gold["meta"]
     cfg = synth.CONFIGS[meta["cfg"]]
     state = synth.make_state(cfg, meta["weight_seed"], meta["regime"])
-    _, g32, d32, _ = _module_grads(cfg, state, gold["mel"], gold["dout"], precision="fp32")
-    out, g16, d16, _ = _module_grads(cfg, state, gold["mel"], gold["dout"], precision="bf16")
+    o32, g32, d32, _ = _module_grads(cfg, state, gold["mel"], gold["dout"], precision="fp32")
+    o16, g16, d16, _ = _module_grads(cfg, state, gold["mel"], gold["dout"], precision="bf16")
     assert not lib_mod.tc_abort_status()
-    assert torch.equal(d16, d32)   # data gradients do not depend on the weight-gradient arithmetic
-    worst = 0.0
+    ref = torch.from_numpy(gold["out"]).cuda()
+    snr = 10 * torch.log10(((ref - ref.mean()) ** 2).sum() / ((o16 - ref - (o16 - ref).mean()) ** 2).sum())
+    worst = float((d16 - d32).norm() / d32.norm())
+    cos = float(F.cosine_similarity(d16.flatten(), d32.flatten(), dim=0))
     for k, gr in g32.items():
-        if k.endswith("bias"):
-            assert torch.equal(g16[k], gr), k
-        else:
-            worst = max(worst, float((g16[k] - gr).norm() / (gr.norm() + 1e-20)))
-    report(f"backward bf16 weight gradients: worst per-tensor relative L2 difference to the fp32 path {worst:.2e}")
-    assert worst <= 1e-2
+        assert torch.isfinite(g16[k]).all(), k
+        worst = max(worst, float((g16[k] - gr).norm() / (gr.norm() + 1e-20)))
+        cos = min(cos, float(F.cosine_similarity(g16[k].flatten(), gr.flatten(), dim=0)))
+    report(f"backward tensor-core path {name}: forward SNR {float(snr):.1f} dB; gradients vs the fp32 path: worst per-tensor "
+           f"relative L2 {worst:.2e}, worst cosine {cos:.5f}")
+    assert float(snr) >= 40.0          # the bf16 gate of the forward (SURVEY.md 8d)
+    # bf16 operands through ~25 chained convolutions of the backward: a few per cent per tensor (tools/grad_diag.py),
+    # the arithmetic of mixed-precision training; precision="fp32" is the exact path (tests above)
+    assert worst <= 0.1 and cos >= 0.995

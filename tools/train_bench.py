@@ -78,7 +78,10 @@ def stock():
 res = {"batch": B, "frames": FR, "segment": FR * 256}
 l_ours, l_stock = float(ours().detach()), float(stock().detach())
 res["loss_ours"], res["loss_stock_torch"] = l_ours, l_stock
-res["ours_ms"] = timed(ours, STEPS)
+for prec in ("fp32", "bf16"):
+    gen.precision = prec
+    res[f"ours_{prec}_ms"] = timed(ours, STEPS)
+    res[f"loss_ours_{prec}"] = float(ours().detach())
 for tf32 in (True, False):
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
