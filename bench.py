@@ -126,6 +126,41 @@ def cpu_reference(args, n_utts, steps, warmup):
     return samples / SR / dt, dt / steps, torch.get_num_threads()
 
 
+def train_step(pkg, synth, cfg, dev, batch=16, frames=32, steps=5):
+    """Secondary number (not the headline metric): the generator part of the reference's training
+    step at its own shape (cfgs/hifigan_v1_config.json: batch 16 x segment 8192) through the CUDA forward/backward:
+    y_g = G(mel); L = 45 * L1(mel(y), mel(y_g)); L.backward()  (train_time_wi_inv.py:166-179,222-236)."""
+    import torch.nn.functional as F
+    gen = pkg.HiFiGAN(synth.AttrDict(cfg))
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state(cfg, 1234, "init").items()})
+    gen = gen.to(dev).train()
+    margs = (cfg["n_fft"], cfg["num_mels"], cfg["sampling_rate"], cfg["hop_size"], cfg["win_size"], cfg["fmin"], cfg["sampling_rate"] / 2)
+    mel_in = torch.from_numpy(synth.make_mel(batch, frames, 1)).to(dev)
+    y_mel = pkg.mel_spectrogram(torch.from_numpy(synth.make_wave(batch, frames * 256, 2)).to(dev), *margs)
+
+    def step():
+        gen.zero_grad(set_to_none=True)
+        (F.l1_loss(y_mel, pkg.mel_spectrogram(gen(mel_in), *margs)) * 45).backward()
+
+    out = {"config": f"HiFi-GAN V1 generator + mel-L1, batch {batch} x {frames * 256} samples, forward + backward + per-step weight upload"}
+    for prec in ("bf16", "fp32"):
+        gen.precision = prec
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = pkg._lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"ms_{prec}"] = e0.elapsed_time(e1) / steps
+        out[f"gpu_launches_{prec}"] = int((pkg._lib.launch_count() - l0) / steps)
+    out["note"] = "bf16 = MRF convs, dgrad and wgrad on tcgen05 (bf16 operands, fp32 accumulate); fp32 = CUDA cores, the parity path"
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -273,6 +308,8 @@ def main():
                             "gbs": k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else 0.0} for k in prof),
                           key=lambda r: -r["ms_per_step"]),
     }
+    if world == 1:
+        line["train_step"] = train_step(pkg, synth, cfg, dev)
     if world == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference(args, args.cpu_utts, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port",

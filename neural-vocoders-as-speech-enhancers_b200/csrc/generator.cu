@@ -324,9 +324,9 @@ int finalize_bf16(nvse_generator* g, cudaStream_t st) {
     }
     // Where bf16 rounding of the ACTIVATION operand costs the most SNR and the least time (the
     // upsamplers: 3 % of the FLOPs; the <= 32-channel MRF stage: HBM-bound anyway) activations are
-    // fed as hi + lo bf16 pairs (tools/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
+    // fed as hi + lo bf16 pairs (tests/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
     if (L.transposed) {
-      // upsamplers: IEEE-half activations AND weights.  tools/bf16_budget.py: bf16 rounding of the ups weights
+      // upsamplers: IEEE-half activations AND weights.  tests/bf16_budget.py: bf16 rounding of the ups weights
       // is the largest single error of the bf16 path (42.7 dB de-meaned SNR; hi+lo split activations with bf16
       // weights 46.1 dB; half operands 54.3 dB) -- and half costs one MMA per step where the split cost two.
       L.tc_f16 = true;

@@ -29,7 +29,7 @@ struct ResblockTcArgs {
   float out_scale;
   int accumulate;
   int h_fp16;        // the c1 -> c2 intermediate and the w2 images are IEEE half instead of bf16 (same range of values,
-                     // three more mantissa bits): where rounding of that intermediate costs the most SNR (tools/bf16_budget.py)
+                     // three more mantissa bits): where rounding of that intermediate costs the most SNR (tests/bf16_budget.py)
 };
 
 // true when the fused kernel handles this shape (otherwise the caller uses the per-layer kernels)

@@ -8,7 +8,7 @@ import json, os, sys
 import torch
 import torch.nn.functional as F
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from util import build_generator, pkg, lib_mod  # noqa: E402
 import synth  # noqa: E402
 from oracle import torch_port  # noqa: E402  (checker / comparison arm only)
