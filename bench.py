@@ -138,11 +138,14 @@ def train_step(pkg, synth, cfg, dev, batch=16, frames=32, steps=5):
     mel_in = torch.from_numpy(synth.make_mel(batch, frames, 1)).to(dev)
     y_mel = pkg.mel_spectrogram(torch.from_numpy(synth.make_wave(batch, frames * 256, 2)).to(dev), *margs)
 
-    def step():
-        gen.zero_grad(set_to_none=True)
-        (F.l1_loss(y_mel, pkg.mel_spectrogram(gen(mel_in), *margs)) * 45).backward()
+    opt = torch.optim.AdamW(gen.parameters(), 1e-7, betas=(0.8, 0.99))  # the weights change every step, as in training
 
-    out = {"config": f"HiFi-GAN V1 generator + mel-L1, batch {batch} x {frames * 256} samples, forward + backward + per-step weight upload"}
+    def step():
+        opt.zero_grad(set_to_none=True)
+        (F.l1_loss(y_mel, pkg.mel_spectrogram(gen(mel_in), *margs)) * 45).backward()
+        opt.step()
+
+    out = {"config": f"HiFi-GAN V1 generator + mel-L1, batch {batch} x {frames * 256} samples, forward + backward + AdamW step + per-step weight upload"}
     for prec in ("bf16", "fp32"):
         gen.precision = prec
         for _ in range(3):

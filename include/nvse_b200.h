@@ -121,6 +121,16 @@ NVSE_API int nvse_generator_set_weight(nvse_generator* g, const char* name, cons
 /* Verifies every tensor was set and builds the bf16 tensor-core weight images. */
 NVSE_API int nvse_generator_finalize(nvse_generator* g, void* stream);
 
+/* Batched alternative to set_weight x N + finalize: load EVERY layer in two launches, straight from the module's
+ * parameters (what a training step does once per optimiser step).  Arrays of nvse_generator_num_layers() device
+ * pointers in the order of nvse_generator_layer_name(): weight[i] = weight_v (weight_g[i] = weight_g, folded on the
+ * fly exactly like nvse_weight_norm_fold_f32) or the plain weight (weight_g[i] = NULL), bias[i]; fp32, contiguous,
+ * PyTorch layouts.  with_train != 0 also builds the transposed copies the backward reads.  Leaves the handle finalized. */
+NVSE_API int nvse_generator_num_layers(const nvse_generator* g);
+NVSE_API int nvse_generator_layer_name(const nvse_generator* g, int index, char* out, size_t capacity);
+NVSE_API int nvse_generator_load_weights(nvse_generator* g, const float* const* weight, const float* const* weight_g,
+                                const float* const* bias, int n_layers, int with_train, void* stream);
+
 /* samples out per mel frame in: prod(upsample_rates) (* istft_hop for iSTFTNet) */
 NVSE_API int64_t nvse_generator_out_samples(const nvse_generator* g, int64_t frames);
 NVSE_API size_t nvse_generator_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames, int precision);

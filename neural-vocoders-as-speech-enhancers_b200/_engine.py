@@ -106,7 +106,40 @@ class GeneratorEngine:
             plist = self._plist = list(module.parameters())
         return (dev.index,) + tuple([(p.data_ptr(), p._version) for p in plist])
 
-    def _ensure(self, module, dev):
+    def _layer_names(self, lib):
+        names = getattr(self, "_names", None)
+        if names is None:
+            buf = C.create_string_buffer(256)
+            names = []
+            for i in range(lib.nvse_generator_num_layers(self.handle)):
+                _lib.check(lib.nvse_generator_layer_name(self.handle, i, buf, len(buf)))
+                names.append(buf.value.decode())
+            self._names = names
+        return names
+
+    def _load_batched(self, module, dev, train, lib, stream):
+        """All layers in two launches (nvse_generator_load_weights) when every parameter already is a contiguous fp32
+        CUDA tensor on ``dev`` -- the training case, where the weights change every step.  Returns False if not eligible."""
+        mods = dict(self._conv_modules(module))
+        names = self._layer_names(lib)
+        n = len(names)
+        w_arr, g_arr, b_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+        for i, name in enumerate(names):
+            m = mods.get(name)
+            if m is None:
+                return False
+            wn = hasattr(m, "weight_g") and hasattr(m, "weight_v")
+            tensors = (m.weight_v, m.weight_g, m.bias) if wn else (m.weight, m.bias)
+            for t in tensors:
+                if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                    return False
+            w_arr[i] = (m.weight_v if wn else m.weight).data_ptr()
+            g_arr[i] = m.weight_g.data_ptr() if wn else None
+            b_arr[i] = m.bias.data_ptr()
+        _lib.check(lib.nvse_generator_load_weights(self.handle, w_arr, g_arr, b_arr, n, 1 if train else 0, stream))
+        return True
+
+    def _ensure(self, module, dev, train=False):
         lib = _lib.load()
         if self.handle is not None and self.device != dev:
             self.close()
@@ -115,10 +148,15 @@ class GeneratorEngine:
             with torch.cuda.device(dev):
                 _lib.check(lib.nvse_generator_create(C.byref(self.cfg), C.byref(h)))
             self.handle, self.device, self.weights_key = h, dev, None
+            self._names = None
         key = self._key(module, dev)
-        if key == self.weights_key:
+        if key == self.weights_key and (not train or getattr(self, "_train_loaded", False)):
             return
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev), torch.no_grad():
+            if self._load_batched(module, dev, train, lib, stream):
+                self.weights_key, self._train_loaded = key, train
+                return
         keep = []  # keep staging tensors alive until the copies are enqueued (same stream -> safe after)
         with torch.cuda.device(dev), torch.no_grad():
             for name, m in self._conv_modules(module):
@@ -140,7 +178,7 @@ class GeneratorEngine:
             _lib.check(lib.nvse_generator_finalize(self.handle, stream))
             torch.cuda.current_stream(dev).synchronize()  # staging tensors may now be freed
         del keep
-        self.weights_key = key
+        self.weights_key, self._train_loaded = key, True  # the per-layer path builds the backward's copies lazily
 
     # ---- forward ---------------------------------------------------------------------
     def forward(self, module, x, precision=None):
@@ -185,7 +223,7 @@ class GeneratorEngine:
             raise _lib.NvseError("the B200 generator needs a CUDA device: there is no CPU fallback")
         dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
         lib = _lib.load()
-        self._ensure(module, dev)
+        self._ensure(module, dev, train=True)
         xd = x.detach().to(dev, torch.float32).contiguous()
         batch, _, frames = xd.shape
         if batch == 0 or frames == 0:

@@ -56,6 +56,9 @@ PROTOTYPES = {
     "nvse_generator_destroy": (_i, [_vp]),
     "nvse_generator_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i, _vp]),
     "nvse_generator_finalize": (_i, [_vp, _vp]),
+    "nvse_generator_num_layers": (_i, [_vp]),
+    "nvse_generator_layer_name": (_i, [_vp, _i, C.c_char_p, _sz]),
+    "nvse_generator_load_weights": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _i, _vp]),
     "nvse_generator_out_samples": (_i64, [_vp, _i64]),
     "nvse_generator_workspace_bytes": (_sz, [_vp, _i64, _i64, _i]),
     "nvse_generator_forward": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _i, _vp]),

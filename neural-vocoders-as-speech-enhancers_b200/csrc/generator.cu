@@ -312,29 +312,34 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   return launch_istft_head(bufU, out, B, T + 1, c.istft_n_fft, c.istft_hop, st);
 }
 
-int finalize_bf16(nvse_generator* g, cudaStream_t st) {
+static bool wants_tc(const Layer& L) { return L.name != "conv_pre" && L.name != "conv_post" && tc_supported(L.Cin, L.Cout); }
+static bool wants_f16_copy(const Layer& L) { return !L.transposed && L.Cout <= 32 && L.name.find(".convs2.") != std::string::npos; }
+
+// Buffers and precision flags of the tensor-core path (no launches).  Where bf16 rounding costs the most SNR:
+//   * upsamplers: IEEE-half activations AND weights.  tests/bf16_budget.py: bf16 rounding of the ups weights is the
+//     largest single error of the bf16 path (42.7 dB de-meaned SNR; hi+lo split activations with bf16 weights
+//     46.1 dB; half operands 54.3 dB) -- and half costs one MMA per step where the split cost two;
+//   * the <= 32-channel MRF stage (HBM-bound anyway): activations as hi + lo bf16 pairs on the per-layer path
+//     (+5..6 dB at random init), an IEEE-half c1 -> c2 intermediate and w2 image in the fused kernels.
+int finalize_plan(nvse_generator* g) {
   for (Layer& L : g->layers) {
-    const bool wanted = L.name != "conv_pre" && L.name != "conv_post" && tc_supported(L.Cin, L.Cout);
-    if (!wanted) continue;
-    if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
+    if (!wants_tc(L)) continue;
+    const size_t bytes = sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k);
+    if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, bytes));
+    if ((wants_f16_copy(L) || L.transposed) && !L.w_f16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_f16, bytes));
+    if (L.transposed) L.tc_f16 = true;
+    else L.tc_split = L.Cout <= 32 && tc_split_fits(L.Cin, L.Cout, (L.k - 1) * L.dilation);
+  }
+  return NVSE_OK;
+}
+
+int finalize_bf16(nvse_generator* g, cudaStream_t st) {
+  if (int rc = finalize_plan(g)) return rc;
+  for (Layer& L : g->layers) {
+    if (!wants_tc(L)) continue;
     if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_bf16), L.Cin, L.Cout, L.k, st)) return rc;
-    if (!L.transposed && L.Cout <= 32 && L.name.find(".convs2.") != std::string::npos) {
-      if (!L.w_f16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_f16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
+    if (L.w_f16)
       if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_f16), L.Cin, L.Cout, L.k, st, true)) return rc;
-    }
-    // Where bf16 rounding of the ACTIVATION operand costs the most SNR and the least time (the
-    // upsamplers: 3 % of the FLOPs; the <= 32-channel MRF stage: HBM-bound anyway) activations are
-    // fed as hi + lo bf16 pairs (tests/bf16_budget.py: +5..6 dB de-meaned SNR at random init).
-    if (L.transposed) {
-      // upsamplers: IEEE-half activations AND weights.  tests/bf16_budget.py: bf16 rounding of the ups weights
-      // is the largest single error of the bf16 path (42.7 dB de-meaned SNR; hi+lo split activations with bf16
-      // weights 46.1 dB; half operands 54.3 dB) -- and half costs one MMA per step where the split cost two.
-      L.tc_f16 = true;
-      if (!L.w_f16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_f16, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k)));
-      if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_f16), L.Cin, L.Cout, L.k, st, true)) return rc;
-    } else {
-      L.tc_split = L.Cout <= 32 && tc_split_fits(L.Cin, L.Cout, (L.k - 1) * L.dilation);
-    }
   }
   return NVSE_OK;
 }
@@ -386,6 +391,7 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     if (g->ev_join[q]) cudaEventDestroy(g->ev_join[q]);
     if (g->side[q]) cudaStreamDestroy(g->side[q]);
   }
+  destroy_weight_loader(g->loader);
   for (Layer& L : g->layers) {
     cudaFree(L.w);
     cudaFree(L.bias);

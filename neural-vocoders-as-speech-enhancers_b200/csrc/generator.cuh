@@ -27,12 +27,15 @@ struct Layer {
 
 }  // namespace nvse
 
+namespace nvse { struct WeightLoader; void destroy_weight_loader(WeightLoader*); }
+
 struct nvse_generator {
   nvse_generator_config cfg;
   std::vector<nvse::Layer> layers;
   std::unordered_map<std::string, int> index;
   bool finalized = false;
   bool train_ready = false;  // wT of every layer matches w
+  nvse::WeightLoader* loader = nullptr;  // tables of the batched weight load (weights.cu)
   // small-batch mode: the ResBlocks of a stage run concurrently on the caller's stream + two side streams
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
@@ -43,7 +46,8 @@ namespace nvse {
 
 int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st);
 
-int finalize_bf16(nvse_generator* g, cudaStream_t st);  // builds the tensor-core weight images
+int finalize_plan(nvse_generator* g);                    // allocates the tensor-core image buffers, sets the per-layer precision flags
+int finalize_bf16(nvse_generator* g, cudaStream_t st);  // finalize_plan + builds the tensor-core weight images
 int tc_abort_status(bool reset, unsigned int* flag);
 
 }  // namespace nvse

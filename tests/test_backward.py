@@ -388,3 +388,39 @@ def test_generator_backward_tensor_core_path(name):
     # bf16 operands through ~25 chained convolutions of the backward: a few per cent per tensor (tools/grad_diag.py),
     # the arithmetic of mixed-precision training; precision="fp32" is the exact path (tests above)
     assert worst <= 0.1 and cos >= 0.995
+
+
+@pytest.mark.gpu
+def test_batched_weight_load_matches_per_layer_load():
+    """nvse_generator_load_weights (two launches for all layers; taken when the parameters live on the GPU) and the
+    per-layer set_weight/finalize path (taken for a CPU-resident module) must build bit-identical weights: same
+    inference output in both precisions, same gradients."""
+    gold = synth.load_golden("grads_hifigan_train_f6")
+    meta = gold["meta"]
+    cfg = synth.CONFIGS[meta["cfg"]]
+    state = synth.make_state(cfg, meta["weight_seed"], meta["regime"])
+    mel = torch.from_numpy(gold["mel"]).cuda()
+    g_gpu = build_generator(cfg, state, "cuda")
+    g_cpu = build_generator(cfg, state, "cpu")     # parameters on the host -> staged and loaded layer by layer
+    for prec in ("fp32", "bf16"):
+        g_gpu.precision = g_cpu.precision = prec
+        with torch.no_grad():
+            assert torch.equal(g_gpu(mel), g_cpu(mel)), prec
+    with torch.no_grad():
+        l0 = lib_mod.launch_count()
+        g_gpu(mel)
+        l1 = lib_mod.launch_count()
+        g_gpu._engine.weights_key = None   # force a reload
+        g_gpu(mel)
+        l2 = lib_mod.launch_count()
+    assert (l2 - l1) - (l1 - l0) == 2      # the whole reload is two launches
+    dout = torch.from_numpy(gold["dout"]).cuda()
+    grads = []
+    for g in (g_gpu, g_cpu):
+        g.train()
+        g.precision = "bf16"
+        g.zero_grad(set_to_none=True)
+        (g(mel) * dout).sum().backward()
+        grads.append({k: p.grad.cpu() for k, p in g.named_parameters()})
+    for k in grads[0]:
+        assert torch.equal(grads[0][k], grads[1][k]), k

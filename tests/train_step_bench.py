@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Generator part of one training step at the reference's training shape (cfgs/hifigan_v1_config.json: batch 16,
 segment 8192 -> 32 frames; train_time_wi_inv.py:166-179,222-236): y_g = G(mel); L = 45 * L1(mel(y), mel(y_g));
-L.backward() -- through the CUDA forward/backward of this repo, and through stock PyTorch (the oracle port, i.e. what
+L.backward(); AdamW step -- through the CUDA forward/backward of this repo, and through stock PyTorch (the oracle port, i.e. what
 the reference's nn.Module dispatches: cuDNN + element-wise kernels) on the same GPU.  CUDA-event timed.
 usage: train_bench.py [batch=16] [frames=32] [steps=10]"""
 import json, os, sys
@@ -39,13 +39,16 @@ def timed(fn, steps):
 
 gen = build_generator(cfg, state, "cuda").train()
 y_mel = pkg.mel_spectrogram(y, *margs)
+LR = 1e-7  # the optimiser step is part of the step (train_time_wi_inv.py:236); tiny so that the timed steps stay comparable
+opt_ours = torch.optim.AdamW(gen.parameters(), LR, betas=(0.8, 0.99))
 
 
 def ours():
-    gen.zero_grad(set_to_none=True)
+    opt_ours.zero_grad(set_to_none=True)
     y_g = gen(mel_in)
     loss = F.l1_loss(y_mel, pkg.mel_spectrogram(y_g, *margs)) * 45
     loss.backward()
+    opt_ours.step()
     return loss
 
 
@@ -66,12 +69,15 @@ def mel_torch(w):
 y_mel_t = mel_torch(y)
 
 
+opt_stock = torch.optim.AdamW(list(leaves.values()), LR, betas=(0.8, 0.99))
+
+
 def stock():
-    for v in leaves.values():
-        v.grad = None
+    opt_stock.zero_grad(set_to_none=True)
     y_g = torch_port.hifigan_forward_autograd(torch_port.fold_state(leaves), cfg, mel_in)
     loss = F.l1_loss(y_mel_t, mel_torch(y_g)) * 45
     loss.backward()
+    opt_stock.step()
     return loss
 
 
