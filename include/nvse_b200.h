@@ -197,9 +197,9 @@ NVSE_API int nvse_conv_transpose1d_bf16(const float* x, const float* w, const fl
  * Supported: n_fft in {4..64} even, hop dividing n_fft. */
 NVSE_API int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, void* stream);
 
-/* ---- training path: backward of HiFiGAN.forward, fp32 ------------------
+/* ---- training path: backward of HiFiGAN.forward / iSTFTNet.forward -------
  * Replaces what loss_gen_all.backward() runs through the generator in train_time_wi_inv.py:222-236
- * (autograd over Models/hifigan.py:108-124).  Gradients are taken w.r.t. the FOLDED tensors loaded
+ * (autograd over Models/hifigan.py:108-124 / Models/istftnet.py:299-318).  Gradients are taken w.r.t. the FOLDED tensors loaded
  * with nvse_generator_set_weight; weight_norm's own backward is nvse_weight_norm_backward_f32.
  *
  * forward_train = the fp32 forward, keeping the input of every convolution on the caller-owned `tape`
@@ -244,6 +244,11 @@ NVSE_API int nvse_conv_transpose1d_backward_f32(const float* x, const float* w, 
  * dv[r] = g[r] / ||v[r]|| * (dw[r] - v[r] * <dw[r], v[r]> / ||v[r]||^2). */
 NVSE_API int nvse_weight_norm_backward_f32(const float* v, const float* g, const float* dw, float* dv, float* dg,
                                   int64_t rows, int64_t cols, void* stream);
+
+/* Backward of nvse_istft_head_f32 (autograd through exp / sin / torch.istft, istftnet.py:314-316,183-188):
+ * dout [B, hop*(Tp-1)] -> dz [B, Tp, n_fft+2].  n_fft in {4, 8, 16, 32}. */
+NVSE_API int nvse_istft_head_backward_f32(const float* z, const float* dout, float* dz, int64_t B, int64_t Tp, int n_fft,
+                                 int hop, void* stream);
 
 /* The tensor-core kernels bound every mbarrier wait (a protocol bug must never hang the GPU); a
  * tripped timeout sets a device flag and later tensor-core launches return without computing.

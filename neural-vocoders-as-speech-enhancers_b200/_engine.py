@@ -215,8 +215,6 @@ class GeneratorEngine:
     # ---- training (fp32) -------------------------------------------------------------
     def forward_train(self, module, x):
         """Forward that keeps every convolution input on an fp32 tape; returns (out, tape, precision)."""
-        if self.kind != _lib.GEN_HIFIGAN:
-            raise NotImplementedError("the B200 training path covers HiFiGAN; iSTFTNet's iSTFT head has no backward kernel yet")
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if not x.is_cuda and not torch.cuda.is_available():
@@ -262,7 +260,7 @@ class GeneratorEngine:
 
 
 class _GeneratorTrainFn(torch.autograd.Function):
-    """HiFiGAN.forward as one autograd node: ``apply(engine, module, mel, *module.named_parameters())``."""
+    """HiFiGAN.forward / iSTFTNet.forward as one autograd node: ``apply(engine, module, mel, *module.named_parameters())``."""
 
     @staticmethod
     def forward(ctx, engine, module, x, *params):

@@ -82,6 +82,7 @@ PROTOTYPES = {
     "nvse_conv1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _f, _i, _vp]),
     "nvse_conv_transpose1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_weight_norm_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "nvse_istft_head_backward_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
     "nvse_tc_abort_status": (_i, [_i, C.POINTER(_i)]),
     "nvse_debug_rb_trace": (_i, [C.POINTER(C.c_longlong)]),
 }

@@ -45,6 +45,11 @@ struct nvse_generator {
 namespace nvse {
 
 int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st);
+// dz rows have `pitch` >= n_fft + 2 floats (extra columns zeroed)
+int launch_istft_head_bwd(const float* z, const float* gout, float* dz, int64_t B, int64_t Tp, int n_fft, int hop, int pitch,
+                          cudaStream_t st);
+int launch_pad_reflect_left(const float* x, float* y, int64_t B, int64_t T, int C, cudaStream_t st);      // [B,T,C] -> [B,T+1,C]
+int launch_unpad_reflect_left(const float* dy, float* dx, int64_t B, int64_t T, int C, cudaStream_t st);  // the adjoint
 
 int finalize_plan(nvse_generator* g);                    // allocates the tensor-core image buffers, sets the per-layer precision flags
 int finalize_bf16(nvse_generator* g, cudaStream_t st);  // finalize_plan + builds the tensor-core weight images

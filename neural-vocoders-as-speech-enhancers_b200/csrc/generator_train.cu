@@ -28,6 +28,7 @@ struct TapePlan {
   std::vector<int64_t> xu, xs;                          // upsampler output / MRF output of stage i
   std::vector<std::vector<std::vector<int64_t>>> h;     // [i][j][m]: c1 output of pair m (ResBlock1)
   std::vector<std::vector<std::vector<int64_t>>> xin;   // [i][j][m]: input of pair m, m >= 1 (m = 0 reads xu)
+  int64_t xpad = -1, z = -1;                            // iSTFTNet: reflect-padded MRF output [B, T+1, C], conv_post output [B, T+1, n_fft+2]
   int64_t total = 0;
   int64_t max_act = 0;  // floats of the largest activation of the whole batch
 };
@@ -56,7 +57,12 @@ TapePlan make_tape(const nvse_generator* g, int64_t B, int64_t F) {
       }
     p.xs.push_back(take(n));
   }
-  p.max_act = std::max(p.max_act, B * T);
+  if (c.kind == NVSE_GEN_ISTFTNET) {
+    p.xpad = take(B * (T + 1) * (c.initial_channel >> p.nstage));
+    p.z = take(B * (T + 1) * (c.istft_n_fft + 2));
+    p.max_act = std::max(p.max_act, B * (T + 1) * 32);  // the 32-column padded gradient of z
+  }
+  p.max_act = std::max(p.max_act, B * T * (c.kind == NVSE_GEN_ISTFTNET ? c.istft_hop : 1));
   p.total = at;
   return p;
 }
@@ -189,7 +195,11 @@ size_t train_scratch_elems(const nvse_generator* g, int64_t B, int64_t F) {
       continue;
     }
     if (L.name.rfind("resblocks.", 0) == 0) T = p.T[std::atoi(L.name.c_str() + 10) / g->cfg.num_kernels];
-    if (L.name == "conv_post") T = p.T.back();
+    if (L.name == "conv_post") {
+      T = p.T.back() + (g->cfg.kind == NVSE_GEN_ISTFTNET ? 1 : 0);
+      m = std::max(m, wgrad_scratch_elems(L.Cin, 32, L.k, B, (int)T));  // iSTFTNet: gradient rows padded to 32 columns
+      m = std::max(m, colsum_scratch_elems(32, B * T));
+    }
     m = std::max(m, wgrad_scratch_elems(L.Cin, L.Cout, L.k, B, (int)T));
     m = std::max(m, colsum_scratch_elems(L.Cout, B * T));
   }
@@ -211,6 +221,7 @@ int prepare_train(nvse_generator* g, cudaStream_t st) {
 }
 
 constexpr int kBwdBuffers = 6;  // dA, dU, gT, gR, gS, dz
+constexpr int64_t kBwdExtraElems = 1 << 18;  // iSTFTNet conv_post: 32-row padded wT and the padded weight gradient
 
 }  // namespace
 
@@ -226,7 +237,7 @@ extern "C" size_t nvse_generator_tape_bytes(const nvse_generator* g, int64_t B, 
 extern "C" size_t nvse_generator_backward_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames) {
   if (!g || B < 0 || frames < 1) return 0;
   const TapePlan p = make_tape(g, B, frames);
-  return ((size_t)kBwdBuffers * (size_t)align64(p.max_act) + train_scratch_elems(g, B, frames)) * sizeof(float) + 256;
+  return ((size_t)kBwdBuffers * (size_t)align64(p.max_act) + (size_t)kBwdExtraElems + train_scratch_elems(g, B, frames)) * sizeof(float) + 256;
 }
 
 extern "C" int64_t nvse_generator_grad_elems(const nvse_generator* g) {
@@ -255,8 +266,6 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
                                             void* tape, size_t tape_bytes, int precision, void* stream) {
   NVSE_REQUIRE(g && mel && out && tape, NVSE_ERR_INVALID, "nvse_generator_forward_train: null argument");
   NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_forward_train: call nvse_generator_finalize first");
-  NVSE_REQUIRE(g->cfg.kind == NVSE_GEN_HIFIGAN, NVSE_ERR_UNSUPPORTED,
-               "the training path covers HiFiGAN; the iSTFT head has no backward kernel yet");
   NVSE_REQUIRE(B >= 1 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_forward_train: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
   NVSE_REQUIRE(tape_bytes >= nvse_generator_tape_bytes(g, B, frames), NVSE_ERR_INVALID, "tape too small");
   NVSE_REQUIRE(precision == NVSE_PRECISION_F32 || precision == NVSE_PRECISION_BF16, NVSE_ERR_INVALID, "bad precision %d", precision);
@@ -300,8 +309,14 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
     prev = xs;
     Tprev = T;
   }
-  // hifigan.py:120-122: leaky_relu (default slope 0.01) -> conv_post -> tanh
-  return conv_fwd(g->layer("conv_post"), prev, nullptr, out, B, Tprev, 0.01f, 1.0f, 0, 1, st);
+  const Layer& post = g->layer("conv_post");
+  if (c.kind == NVSE_GEN_HIFIGAN)  // hifigan.py:120-122: leaky_relu (default slope 0.01) -> conv_post -> tanh
+    return conv_fwd(post, prev, nullptr, out, B, Tprev, 0.01f, 1.0f, 0, 1, st);
+  // istftnet.py:311-318: leaky_relu (0.01) -> ReflectionPad1d((1, 0)) -> conv_post -> exp / sin -> iSTFT
+  NVSE_REQUIRE(post.Cout <= 32, NVSE_ERR_UNSUPPORTED, "iSTFTNet training: gen_istft_n_fft + 2 = %d > 32", post.Cout);
+  if (int rc = launch_pad_reflect_left(prev, tp + p.xpad, B, Tprev, post.Cin, st)) return rc;
+  if (int rc = conv_fwd(post, tp + p.xpad, nullptr, tp + p.z, B, Tprev + 1, 0.01f, 1.0f, 0, 0, st)) return rc;
+  return launch_istft_head(tp + p.z, out, B, Tprev + 1, c.istft_n_fft, c.istft_hop, st);
 }
 
 extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frames, const float* out, const float* dout,
@@ -309,8 +324,6 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
                                        size_t workspace_bytes, int precision, void* stream) {
   NVSE_REQUIRE(g && out && dout && tape && grads && workspace, NVSE_ERR_INVALID, "nvse_generator_backward: null argument");
   NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_backward: call nvse_generator_finalize first");
-  NVSE_REQUIRE(g->cfg.kind == NVSE_GEN_HIFIGAN, NVSE_ERR_UNSUPPORTED,
-               "the training path covers HiFiGAN; the iSTFT head has no backward kernel yet");
   NVSE_REQUIRE(B >= 1 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_backward: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
   NVSE_REQUIRE(tape_bytes >= nvse_generator_tape_bytes(g, B, frames), NVSE_ERR_INVALID, "tape too small");
   NVSE_REQUIRE(workspace_bytes >= nvse_generator_backward_workspace_bytes(g, B, frames), NVSE_ERR_INVALID, "workspace too small");
@@ -329,17 +342,59 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   float* gS = ws + 4 * be;   //                                         (pong)
   float* dz = ws + 5 * be;   // gradient w.r.t. the conv_post output
   const bool tc = precision == NVSE_PRECISION_BF16;
-  const GradSink sink{g, grads, ws + kBwdBuffers * be, B, st, tc ? 1 : 0};
+  const GradSink sink{g, grads, ws + kBwdBuffers * be + kBwdExtraElems, B, st, tc ? 1 : 0};
   const float slope = 0.1f;
   const float inv = 1.0f / (float)c.num_kernels;
 
-  // tanh, conv_post (hifigan.py:120-122)
   const int64_t Tl = p.T.back();
   const Layer& post = g->layer("conv_post");
   const float* xs_last = tp + p.xs.back();
-  if (int rc = launch_tanh_bwd(out, dout, dz, B * Tl * post.Cout, st)) return rc;
-  if (int rc = sink.conv(post, xs_last, 0.01f, dz, Tl, 1.0f)) return rc;
-  if (int rc = conv_dgrad(post, dz, xs_last, 0.01f, nullptr, dA, B, Tl, 1.0f, 0, st)) return rc;
+  if (c.kind == NVSE_GEN_HIFIGAN) {  // tanh, conv_post (hifigan.py:120-122)
+    if (int rc = launch_tanh_bwd(out, dout, dz, B * Tl * post.Cout, st)) return rc;
+    if (int rc = sink.conv(post, xs_last, 0.01f, dz, Tl, 1.0f)) return rc;
+    if (int rc = conv_dgrad(post, dz, xs_last, 0.01f, nullptr, dA, B, Tl, 1.0f, 0, st)) return rc;
+  } else {
+    // iSTFT head, conv_post over the reflect-padded rows (istftnet.py:311-318).  The gradient of z is kept with its
+    // n_fft + 2 columns padded to 32 (zeros): the data gradient then runs on the wide kernel (its K must be a multiple
+    // of 16) against a 32-row zero-padded wT, and the weight gradient comes out as the first Cout rows of a 32-row one.
+    NVSE_REQUIRE(post.Cout <= 32 && (int64_t)post.k * 32 * post.Cin + 32 <= kBwdExtraElems / 2, NVSE_ERR_UNSUPPORTED,
+                 "iSTFTNet training: conv_post %d -> %d unsupported", post.Cin, post.Cout);
+    const int64_t Tp = Tl + 1;
+    const float* xpad = tp + p.xpad;
+    float* extra = ws + kBwdBuffers * be;          // [k][32][Cin] padded wT, then [32][Cin][k] + [32] padded gradients
+    float* wT_pad = extra;
+    float* dw_pad = extra + kBwdExtraElems / 2;
+    float* db_pad = dw_pad + (int64_t)32 * post.Cin * post.k;
+    float* scratch = ws + kBwdBuffers * be + kBwdExtraElems;
+    if (int rc = launch_istft_head_bwd(tp + p.z, dout, dz, B, Tp, c.istft_n_fft, c.istft_hop, 32, st)) return rc;
+    NVSE_CUDA_CHECK(cudaMemsetAsync(wT_pad, 0, sizeof(float) * post.k * 32 * post.Cin, st));
+    NVSE_CUDA_CHECK(cudaMemcpy2DAsync(wT_pad, sizeof(float) * 32 * post.Cin, post.wT, sizeof(float) * post.Cout * post.Cin,
+                                      sizeof(float) * post.Cout * post.Cin, post.k, cudaMemcpyDeviceToDevice, st));
+    {
+      WgradArgs w{};
+      w.U = xpad; w.u_bstride = Tp * post.Cin; w.Tu = (int)Tp; w.Ca = post.Cin; w.u_slope = 0.01f;
+      w.V = dz; w.v_bstride = Tp * 32; w.Tv = (int)Tp; w.Cb = 32; w.v_slope = 1.0f;
+      w.u_stride = 1; w.ntaps = post.k;
+      for (int j = 0; j < post.k; ++j) w.off[j] = j - post.padding;
+      w.dst = dw_pad; w.scale = 1.0f; w.tc = 0;
+      if (int rc = launch_wgrad(w, B, scratch, st)) return rc;
+      if (int rc = launch_colsum(dz, B * Tp, 32, db_pad, 1.0f, scratch, st)) return rc;
+      NVSE_CUDA_CHECK(cudaMemcpyAsync(sink.dw(post), dw_pad, sizeof(float) * post.Cout * post.Cin * post.k, cudaMemcpyDeviceToDevice, st));
+      NVSE_CUDA_CHECK(cudaMemcpyAsync(sink.db(post), db_pad, sizeof(float) * post.Cout, cudaMemcpyDeviceToDevice, st));
+    }
+    {
+      ConvF32Args a{};
+      a.x = dz; a.x_bstride = Tp * 32; a.Tin = (int)Tp; a.Cin = 32;
+      a.w = wT_pad;
+      a.y = gT; a.y_bstride = Tp * post.Cin; a.Tout = (int)Tp; a.Cout = post.Cin;
+      a.taps.ntaps = post.k;
+      for (int j = 0; j < post.k; ++j) { a.taps.off[j] = post.padding - j; a.taps.widx[j] = j; }
+      a.out_mul = 1; a.Trows = (int)Tp; a.in_slope = 1.0f; a.out_scale = 1.0f;
+      a.mask = xpad; a.mask_slope = 0.01f;
+      if (int rc = launch_conv_f32(a, B, st)) return rc;
+    }
+    if (int rc = launch_unpad_reflect_left(gT, dA, B, Tl, post.Cin, st)) return rc;
+  }
 
   for (int i = c.num_upsamples - 1; i >= 0; --i) {
     const int64_t T = p.T[i];

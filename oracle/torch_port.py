@@ -92,12 +92,13 @@ def hifigan_forward(folded, cfg, mel):
 
 
 def hifigan_gradients(state, cfg, mel, dout):
-    """Gradients of ``(HiFiGAN(mel) * dout).sum()`` w.r.t. every tensor of a reference-format state dict
+    """Gradients of ``(G(mel) * dout).sum()`` (G = HiFiGAN or iSTFTNet, by ``cfg["model_name"]``) w.r.t. every tensor of a reference-format state dict
     (weight_g / weight_v / bias, or folded weight / bias) and w.r.t. ``mel``, by torch autograd over the port.
     -> (out, {name: grad}, dmel)"""
     leaves = {k: torch.as_tensor(v, dtype=torch.float32).clone().requires_grad_(True) for k, v in state.items()}
     mel = torch.as_tensor(mel, dtype=torch.float32).clone().requires_grad_(True)
-    out = hifigan_forward_autograd(fold_state(leaves), cfg, mel)
+    fwd = istftnet_forward_autograd if cfg.get("model_name") == "iSTFTNet" else hifigan_forward_autograd
+    out = fwd(fold_state(leaves), cfg, mel)
     (out * torch.as_tensor(dout, dtype=torch.float32)).sum().backward()
     return out.detach(), {k: v.grad for k, v in leaves.items()}, mel.grad
 
@@ -105,6 +106,11 @@ def hifigan_gradients(state, cfg, mel, dout):
 @torch.no_grad()
 def istftnet_forward(folded, cfg, mel):
     """Models/istftnet.py:299-318."""
+    return istftnet_forward_autograd(folded, cfg, mel)
+
+
+def istftnet_forward_autograd(folded, cfg, mel):
+    """Models/istftnet.py:299-318, differentiable (checker of the iSTFTNet backward kernels)."""
     x = _trunk(folded, cfg, mel)
     x = F.pad(F.leaky_relu(x), (1, 0), mode="reflect")
     x = F.conv1d(x, folded["conv_post.weight"], folded["conv_post.bias"], padding=3)

@@ -37,11 +37,13 @@ ISTFTNET_SMALL = dict(ISTFTNET, upsample_initial_channel=64)
 # training-path fixtures: every channel count a multiple of 16 (128, 64, 32, 16)
 HIFIGAN_TRAIN = dict(HIFIGAN_V1, upsample_initial_channel=256)
 HIFIGAN_TRAIN_RB2 = dict(HIFIGAN_SMALL_RB2, upsample_initial_channel=256)
+ISTFTNET_TRAIN = dict(ISTFTNET, upsample_initial_channel=256)   # 128, 64 channels
 
 CONFIGS = {
     "hifigan_v1": HIFIGAN_V1, "istftnet": ISTFTNET, "hifigan_small": HIFIGAN_SMALL,
     "hifigan_small_rb2": HIFIGAN_SMALL_RB2, "istftnet_small": ISTFTNET_SMALL,
     "hifigan_train": HIFIGAN_TRAIN, "hifigan_train_rb2": HIFIGAN_TRAIN_RB2,
+    "istftnet_train": ISTFTNET_TRAIN,
 }
 
 

@@ -17,7 +17,7 @@ import synth
 from util import lib_mod, pkg, stream_ptr, report, build_generator
 from oracle import torch_port
 
-GRAD_CASES = ["grads_hifigan_train_f6", "grads_hifigan_train_rb2_f5", "grads_hifigan_train_init_f4"]
+GRAD_CASES = ["grads_hifigan_train_f6", "grads_hifigan_train_rb2_f5", "grads_hifigan_train_init_f4", "grads_istftnet_train_f7"]
 
 
 def _summary_mismatch(grads, gold):
@@ -232,11 +232,22 @@ def test_training_step_reduces_loss():
 
 
 @pytest.mark.gpu
-def test_istftnet_training_is_rejected_loudly():
-    cfg = synth.CONFIGS["istftnet_small"]
-    gen = build_generator(cfg, synth.make_state(cfg, 9, "unit"), "cuda").train()
-    with pytest.raises(NotImplementedError):
-        gen(torch.zeros(1, 80, 4, device="cuda"))
+def test_istft_head_backward_layer():
+    """nvse_istft_head_backward_f32 against autograd through exp / sin / torch.istft (istftnet.py:314-316,183-188)."""
+    gold = synth.load_golden("istft_head_t37")
+    nb = gold["mag"].shape[1]
+    rng = np.random.default_rng(3)
+    z = torch.from_numpy(rng.normal(0, 0.7, size=(2, 2 * nb, 37)).astype(np.float32)).cuda().requires_grad_(True)
+    spec = torch.exp(z[:, :nb]) * torch.exp(1j * torch.sin(z[:, nb:]))
+    out = torch.istft(spec, 16, 4, 16, window=torch.hann_window(16, device="cuda"))
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    lib = lib_mod.load()
+    z_cl = z.detach().transpose(1, 2).contiguous()
+    dz = torch.full_like(z_cl, float("nan"))
+    lib_mod.check(lib.nvse_istft_head_backward_f32(lib_mod.ptr(z_cl), lib_mod.ptr(dout.contiguous()), lib_mod.ptr(dz), 2, 37, 16, 4, stream_ptr()))
+    torch.cuda.synchronize()
+    assert _close(dz.transpose(1, 2), z.grad, 2e-5)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -363,7 +374,7 @@ def test_conv1d_weight_gradient_tensor_core(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["grads_hifigan_train_f6", "grads_hifigan_train_rb2_f5"])
+@pytest.mark.parametrize("name", ["grads_hifigan_train_f6", "grads_hifigan_train_rb2_f5", "grads_istftnet_train_f7"])
 def test_generator_backward_tensor_core_path(name):
     """precision 'bf16' (the default): the MRF convolutions run on the tensor cores in the forward, the data gradients and
     the weight gradients (bf16 operands, fp32 accumulate).  Checked against the fp32 CUDA path and the fixture output."""
