@@ -159,6 +159,16 @@ static int workspace_buffers(const nvse_generator* g, int64_t B, int64_t frames,
   return small ? 12 : 4;
 }
 
+int ensure_side_streams(nvse_generator* g) {
+  if (g->ev_fork) return NVSE_OK;
+  NVSE_CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+  for (int q = 0; q < 2; ++q) {
+    NVSE_CUDA_CHECK(cudaStreamCreateWithFlags(&g->side[q], cudaStreamNonBlocking));
+    NVSE_CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_join[q], cudaEventDisableTiming));
+  }
+  return NVSE_OK;
+}
+
 static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B, int64_t F, float* out, float* ws,
                         int64_t buf_elems, int nbuf, cudaStream_t st) {
   const nvse_generator_config& c = g->cfg;
@@ -216,13 +226,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
     T = (T - 1) * up.stride - 2 * up.padding + up.k;
     const bool stage_concurrent = t32 && nbuf >= 12 && B * T <= kConcurrentRows;
     if (stage_concurrent) {
-      if (!g->ev_fork) {
-        NVSE_CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
-        for (int q = 0; q < 2; ++q) {
-          NVSE_CUDA_CHECK(cudaStreamCreateWithFlags(&g->side[q], cudaStreamNonBlocking));
-          NVSE_CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_join[q], cudaEventDisableTiming));
-        }
-      }
+      if (int rc = ensure_side_streams(g)) return rc;
       NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
     }
     const float inv = 1.0f / (float)c.num_kernels;  // hifigan.py:119

@@ -13,6 +13,7 @@
 #include "grad.cuh"
 #include "conv_tc.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace nvse {
@@ -28,6 +29,7 @@ struct TapePlan {
   std::vector<int64_t> xu, xs;                          // upsampler output / MRF output of stage i
   std::vector<std::vector<std::vector<int64_t>>> h;     // [i][j][m]: c1 output of pair m (ResBlock1)
   std::vector<std::vector<std::vector<int64_t>>> xin;   // [i][j][m]: input of pair m, m >= 1 (m = 0 reads xu)
+  int64_t tmp[2] = {-1, -1};                            // outputs of ResBlocks 1, 2 of a stage while they run concurrently
   int64_t xpad = -1, z = -1;                            // iSTFTNet: reflect-padded MRF output [B, T+1, C], conv_post output [B, T+1, n_fft+2]
   int64_t total = 0;
   int64_t max_act = 0;  // floats of the largest activation of the whole batch
@@ -56,6 +58,13 @@ TapePlan make_tape(const nvse_generator* g, int64_t B, int64_t F) {
         p.xin[i][j].push_back(m > 0 ? take(n) : -1);
       }
     p.xs.push_back(take(n));
+  }
+  {
+    int64_t big = 0, Tq = F;
+    for (int i = 0; i < p.nstage; ++i) big = std::max(big, B * p.T[i] * (c.initial_channel >> (i + 1)));
+    (void)Tq;
+    p.tmp[0] = take(big);
+    p.tmp[1] = take(big);
   }
   if (c.kind == NVSE_GEN_ISTFTNET) {
     p.xpad = take(B * (T + 1) * (c.initial_channel >> p.nstage));
@@ -220,7 +229,12 @@ int prepare_train(nvse_generator* g, cudaStream_t st) {
   return NVSE_OK;
 }
 
-constexpr int kBwdBuffers = 6;  // dA, dU, gT, gR, gS, dz
+constexpr int kBwdBuffers = 14;  // dA, dz, then per concurrent ResBlock j: dU_j, gT_j, gR_j, gS_j
+inline bool concurrent_ok(const nvse_generator_config& c) {
+  static const bool on = [] { const char* e = std::getenv("NVSE_CONCURRENT"); return !(e && e[0] == '0'); }();
+  return on && c.num_kernels >= 2 && c.num_kernels <= 3;
+}
+
 constexpr int64_t kBwdExtraElems = 1 << 18;  // iSTFTNet conv_post: 32-row padded wT and the padded weight gradient
 
 }  // namespace
@@ -237,7 +251,7 @@ extern "C" size_t nvse_generator_tape_bytes(const nvse_generator* g, int64_t B, 
 extern "C" size_t nvse_generator_backward_workspace_bytes(const nvse_generator* g, int64_t B, int64_t frames) {
   if (!g || B < 0 || frames < 1) return 0;
   const TapePlan p = make_tape(g, B, frames);
-  return ((size_t)kBwdBuffers * (size_t)align64(p.max_act) + (size_t)kBwdExtraElems + train_scratch_elems(g, B, frames)) * sizeof(float) + 256;
+  return ((size_t)kBwdBuffers * (size_t)align64(p.max_act) + (size_t)kBwdExtraElems + 3 * (size_t)align64((int64_t)train_scratch_elems(g, B, frames))) * sizeof(float) + 256;
 }
 
 extern "C" int64_t nvse_generator_grad_elems(const nvse_generator* g) {
@@ -287,24 +301,37 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
     float* xs = tp + p.xs[i];
     if (int rc = convT_fwd(up, prev, xu, B, Tprev, slope, st)) return rc;  // hifigan.py:111-112
     const int64_t T = p.T[i];
+    const bool conc = concurrent_ok(c);  // the ResBlocks of the MRF are independent: caller's stream + two side streams
+    if (conc) {
+      if (int rc = ensure_side_streams(g)) return rc;
+      NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
+    }
     for (int j = 0; j < c.num_kernels; ++j) {
       const std::string pj = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
+      cudaStream_t sj = (conc && j > 0) ? g->side[j - 1] : st;
+      if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
+      float* outj = (conc && j > 0) ? tp + p.tmp[j - 1] : xs;
       const float* src = xu;
       for (int m = 0; m < nd; ++m) {
         const bool last = (m == nd - 1);
-        float* dst = last ? xs : tp + p.xin[i][j][m + 1];
+        float* dst = last ? outj : tp + p.xin[i][j][m + 1];
         const float scale = last ? inv : 1.0f;
-        const int accum = last && j > 0;
+        const int accum = last && j > 0 && !conc;
         if (c.resblock_type == 1) {  // hifigan.py:43-50
           float* h = tp + p.h[i][j][m];
-          if (int rc = conv_fwd(g->layer(pj + ".convs1." + std::to_string(m)), src, nullptr, h, B, T, slope, 1.0f, 0, 0, st, tc)) return rc;
-          if (int rc = conv_fwd(g->layer(pj + ".convs2." + std::to_string(m)), h, src, dst, B, T, slope, scale, accum, 0, st, tc)) return rc;
+          if (int rc = conv_fwd(g->layer(pj + ".convs1." + std::to_string(m)), src, nullptr, h, B, T, slope, 1.0f, 0, 0, sj, tc)) return rc;
+          if (int rc = conv_fwd(g->layer(pj + ".convs2." + std::to_string(m)), h, src, dst, B, T, slope, scale, accum, 0, sj, tc)) return rc;
         } else {  // hifigan.py:71-76
-          if (int rc = conv_fwd(g->layer(pj + ".convs." + std::to_string(m)), src, src, dst, B, T, slope, scale, accum, 0, st, tc)) return rc;
+          if (int rc = conv_fwd(g->layer(pj + ".convs." + std::to_string(m)), src, src, dst, B, T, slope, scale, accum, 0, sj, tc)) return rc;
         }
         src = dst;
       }
+      if (conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
+    }
+    if (conc) {  // xs = (rb0 + rb1) + rb2: the summation order of the sequential path
+      for (int q = 1; q < c.num_kernels; ++q) NVSE_CUDA_CHECK(cudaStreamWaitEvent(st, g->ev_join[q - 1], 0));
+      if (int rc = launch_add3(xs, tp + p.tmp[0], c.num_kernels > 2 ? tp + p.tmp[1] : nullptr, B * T * (c.initial_channel >> (i + 1)), st)) return rc;
     }
     prev = xs;
     Tprev = T;
@@ -336,13 +363,19 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   if (int rc = prepare_train(g, st)) return rc;
   const int64_t be = align64(p.max_act);
   float* dA = ws;            // gradient w.r.t. the MRF output of the current stage (then w.r.t. the previous stage's)
-  float* dU = ws + be;       // gradient w.r.t. the upsampler output, summed over the ResBlocks
-  float* gT = ws + 2 * be;   // gradient w.r.t. the c1 output of the current pair
-  float* gR = ws + 3 * be;   // running gradient of the residual stream (ping)
-  float* gS = ws + 4 * be;   //                                         (pong)
-  float* dz = ws + 5 * be;   // gradient w.r.t. the conv_post output
+  float* dz = ws + be;       // gradient w.r.t. the conv_post output
+  // per concurrent ResBlock j: dU_j (gradient w.r.t. the upsampler output through block j), gT (w.r.t. the c1 output of the
+  // current pair), gR / gS (running gradient of the residual stream, ping / pong)
+  auto jbuf = [&](int j, int which) { return ws + (2 + 4 * j + which) * be; };
+  float* dU = jbuf(0, 0);
+  float* gT = jbuf(0, 1);
   const bool tc = precision == NVSE_PRECISION_BF16;
-  const GradSink sink{g, grads, ws + kBwdBuffers * be + kBwdExtraElems, B, st, tc ? 1 : 0};
+  float* scratch0 = ws + kBwdBuffers * be + kBwdExtraElems;
+  const int64_t scratch_stride = align64((int64_t)train_scratch_elems(g, B, frames));
+  const GradSink sink{g, grads, scratch0, B, st, tc ? 1 : 0};
+  const bool conc = concurrent_ok(c);
+  if (conc)
+    if (int rc = ensure_side_streams(g)) return rc;
   const float slope = 0.1f;
   const float inv = 1.0f / (float)c.num_kernels;
 
@@ -399,30 +432,44 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   for (int i = c.num_upsamples - 1; i >= 0; --i) {
     const int64_t T = p.T[i];
     const float* xu = tp + p.xu[i];
+    if (conc) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
     for (int j = 0; j < c.num_kernels; ++j) {
       const std::string pj = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
+      const int jb = conc ? j : 0;
+      cudaStream_t sj = (conc && j > 0) ? g->side[j - 1] : st;
+      if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
+      const GradSink sj_sink{g, grads, scratch0 + jb * scratch_stride, B, sj, tc ? 1 : 0};
+      float* dUj = jbuf(jb, 0);
+      float* gTj = jbuf(jb, 1);
+      float* gRj = jbuf(jb, 2);
+      float* gSj = jbuf(jb, 3);
       const float* gcur = dA;  // unscaled: the 1/num_kernels of the MRF average is applied where gradients leave the block
       for (int m = nd - 1; m >= 0; --m) {
         const float* x_m = m == 0 ? xu : tp + p.xin[i][j][m];
-        float* gnext = m == 0 ? dU : (gcur == gR ? gS : gR);
+        float* gnext = m == 0 ? dUj : (gcur == gRj ? gSj : gRj);
         const float oscale = m == 0 ? inv : 1.0f;
-        const int accum = m == 0 && j > 0;
+        const int accum = m == 0 && j > 0 && !conc;
         if (c.resblock_type == 1) {
           const Layer& c1 = g->layer(pj + ".convs1." + std::to_string(m));
           const Layer& c2 = g->layer(pj + ".convs2." + std::to_string(m));
           const float* h = tp + p.h[i][j][m];
-          if (int rc = conv_dgrad(c2, gcur, h, slope, nullptr, gT, B, T, 1.0f, 0, st, tc)) return rc;
-          if (int rc = sink.conv(c2, h, slope, gcur, T, inv)) return rc;
-          if (int rc = conv_dgrad(c1, gT, x_m, slope, gcur, gnext, B, T, oscale, accum, st, tc)) return rc;
-          if (int rc = sink.conv(c1, x_m, slope, gT, T, inv)) return rc;
+          if (int rc = conv_dgrad(c2, gcur, h, slope, nullptr, gTj, B, T, 1.0f, 0, sj, tc)) return rc;
+          if (int rc = sj_sink.conv(c2, h, slope, gcur, T, inv)) return rc;
+          if (int rc = conv_dgrad(c1, gTj, x_m, slope, gcur, gnext, B, T, oscale, accum, sj, tc)) return rc;
+          if (int rc = sj_sink.conv(c1, x_m, slope, gTj, T, inv)) return rc;
         } else {
           const Layer& cv = g->layer(pj + ".convs." + std::to_string(m));
-          if (int rc = conv_dgrad(cv, gcur, x_m, slope, gcur, gnext, B, T, oscale, accum, st, tc)) return rc;
-          if (int rc = sink.conv(cv, x_m, slope, gcur, T, inv)) return rc;
+          if (int rc = conv_dgrad(cv, gcur, x_m, slope, gcur, gnext, B, T, oscale, accum, sj, tc)) return rc;
+          if (int rc = sj_sink.conv(cv, x_m, slope, gcur, T, inv)) return rc;
         }
         gcur = gnext;
       }
+      if (conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
+    }
+    if (conc) {  // dU = (dU_0 + dU_1) + dU_2, the order of the sequential path
+      for (int q = 1; q < c.num_kernels; ++q) NVSE_CUDA_CHECK(cudaStreamWaitEvent(st, g->ev_join[q - 1], 0));
+      if (int rc = launch_add3(dU, jbuf(1, 0), c.num_kernels > 2 ? jbuf(2, 0) : nullptr, B * T * (c.initial_channel >> (i + 1)), st)) return rc;
     }
     // upsampler i (hifigan.py:111-112): input = lrelu(previous stage output, 0.1)
     const Layer& up = g->layer("ups." + std::to_string(i));
