@@ -240,6 +240,12 @@ NVSE_API int nvse_conv1d_backward_f32(const float* x, const float* w, const floa
 NVSE_API int nvse_conv_transpose1d_backward_f32(const float* x, const float* w, const float* dy, float* dx, float* dw,
                                        float* dbias, int64_t B, int64_t T, int Cin, int Cout, int k, int stride,
                                        int padding, float in_slope, void* stream);
+/* weight_norm backward of EVERY layer in one launch (after nvse_generator_load_weights; arrays as there).  For layer i
+ * with weight_g[i] != NULL:  dv is written at dv_flat + (offset of "<layer>.weight" in `grads`), dg at dg_flat + (rows of
+ * the layers before it; nvse_generator_total_rows floats in all).  Layers without weight norm are skipped. */
+NVSE_API int64_t nvse_generator_total_rows(const nvse_generator* g);
+NVSE_API int nvse_generator_weight_norm_backward(nvse_generator* g, const float* const* weight_v, const float* const* weight_g,
+                                        const float* grads, float* dv_flat, float* dg_flat, int n_layers, void* stream);
 /* Backward of nvse_weight_norm_fold_f32:  dg[r] = <dw[r], v[r]> / ||v[r]||,
  * dv[r] = g[r] / ||v[r]|| * (dw[r] - v[r] * <dw[r], v[r]> / ||v[r]||^2). */
 NVSE_API int nvse_weight_norm_backward_f32(const float* v, const float* g, const float* dw, float* dv, float* dg,

@@ -137,6 +137,7 @@ class GeneratorEngine:
             g_arr[i] = m.weight_g.data_ptr() if wn else None
             b_arr[i] = m.bias.data_ptr()
         _lib.check(lib.nvse_generator_load_weights(self.handle, w_arr, g_arr, b_arr, n, 1 if train else 0, stream))
+        self._batched = (w_arr, g_arr, [mods[name] for name in names])
         return True
 
     def _ensure(self, module, dev, train=False):
@@ -157,6 +158,7 @@ class GeneratorEngine:
             if self._load_batched(module, dev, train, lib, stream):
                 self.weights_key, self._train_loaded = key, train
                 return
+        self._batched = None
         keep = []  # keep staging tensors alive until the copies are enqueued (same stream -> safe after)
         with torch.cuda.device(dev), torch.no_grad():
             for name, m in self._conv_modules(module):
@@ -250,6 +252,7 @@ class GeneratorEngine:
             _lib.check(lib.nvse_generator_backward(self.handle, batch, frames, _lib.ptr(out), _lib.ptr(dout), _lib.ptr(tape),
                                                    tape.numel(), _lib.ptr(grads), _lib.ptr(dmel), _lib.ptr(ws), ws.numel(),
                                                    precision, stream))
+        self._grads_flat = grads
         views = {}
         off, n = C.c_int64(), C.c_int64()
         for name, m in self._conv_modules(module):
@@ -284,9 +287,29 @@ class _GeneratorTrainFn(torch.autograd.Function):
         ctx.tape = None
         grads = {}
         dev = out.device
+        batched = getattr(engine, "_batched", None)
         with torch.cuda.device(dev), torch.no_grad():
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            for name, m in engine._conv_modules(module):
+            if batched is not None:  # parameters live on the GPU: weight_norm backward of all layers in one launch
+                w_arr, g_arr, mods = batched
+                flat = engine._grads_flat
+                dv_flat = torch.empty_like(flat)
+                dg_flat = torch.empty(lib.nvse_generator_total_rows(engine.handle), dtype=torch.float32, device=dev)
+                _lib.check(lib.nvse_generator_weight_norm_backward(engine.handle, w_arr, g_arr, _lib.ptr(flat), _lib.ptr(dv_flat),
+                                                                   _lib.ptr(dg_flat), len(mods), stream))
+                row = 0
+                for name, m in zip(engine._layer_names(lib), mods):
+                    grads[f"{name}.bias"] = folded[f"{name}.bias"]
+                    dw = folded[f"{name}.weight"]
+                    rows = m.weight_v.shape[0] if hasattr(m, "weight_v") else m.weight.shape[0]
+                    if hasattr(m, "weight_g") and hasattr(m, "weight_v"):
+                        off = dw.storage_offset()
+                        grads[f"{name}.weight_v"] = dv_flat[off:off + dw.numel()].view(dw.shape)
+                        grads[f"{name}.weight_g"] = dg_flat[row:row + rows].view(m.weight_g.shape)
+                    else:
+                        grads[f"{name}.weight"] = dw
+                    row += rows
+            for name, m in (engine._conv_modules(module) if batched is None else ()):
                 grads[f"{name}.bias"] = folded[f"{name}.bias"]
                 dw = folded[f"{name}.weight"]
                 if hasattr(m, "weight_g") and hasattr(m, "weight_v"):  # weight_norm(dim=0): w = g * v / ||v||

@@ -79,6 +79,8 @@ PROTOTYPES = {
     "nvse_generator_grad_offset": (_i, [_vp, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     "nvse_generator_forward_train": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _i, _vp]),
     "nvse_generator_backward": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, _i, _vp]),
+    "nvse_generator_total_rows": (_i64, [_vp]),
+    "nvse_generator_weight_norm_backward": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _i, _vp]),
     "nvse_conv1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _f, _i, _vp]),
     "nvse_conv_transpose1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_weight_norm_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -26,9 +26,49 @@ struct LayerDev {
   int64_t cols;
 };
 
+struct WnBwdDev {
+  const float* v; const float* g; const float* dw;
+  float* dv; float* dg;
+  int64_t cols;
+};
+
 namespace {
 
 constexpr int kElemsPerBlock = 1024;
+
+__device__ __forceinline__ float wl_block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+
+// weight_norm backward of every layer in one launch: one CTA per row (same arithmetic as grad.cu's per-layer kernel)
+__global__ void __launch_bounds__(256) wn_bwd_all_kernel(const WnBwdDev* __restrict__ layers, const int* __restrict__ row_layer,
+                                                         const int* __restrict__ row_idx) {
+  __shared__ float red[8];
+  const WnBwdDev L = layers[row_layer[blockIdx.x]];
+  if (!L.g) return;
+  const int64_t r = row_idx[blockIdx.x];
+  const float* vr = L.v + r * L.cols;
+  const float* wr = L.dw + r * L.cols;
+  float ss = 0.0f, dot = 0.0f;
+  for (int64_t c = threadIdx.x; c < L.cols; c += blockDim.x) {
+    const float x = vr[c];
+    ss = fmaf(x, x, ss);
+    dot = fmaf(wr[c], x, dot);
+  }
+  ss = wl_block_sum(ss, red);
+  dot = wl_block_sum(dot, red);
+  const float nrm = sqrtf(ss), inv = 1.0f / nrm, gr = L.g[r];
+  if (threadIdx.x == 0) L.dg[r] = dot * inv;
+  const float s1 = gr * inv, s2 = dot * inv * inv;
+  for (int64_t c = threadIdx.x; c < L.cols; c += blockDim.x) L.dv[r * L.cols + c] = s1 * (wr[c] - vr[c] * s2);
+}
+
 
 __global__ void __launch_bounds__(256) load_scales_kernel(const LayerDev* __restrict__ layers, const int* __restrict__ row_layer,
                                                           const int* __restrict__ row_idx) {
@@ -90,10 +130,12 @@ struct WeightLoader {
   int* d_blk_layer = nullptr;
   int* d_blk_first = nullptr;
   float* d_scale = nullptr;
+  std::vector<WnBwdDev> wn_host;
+  WnBwdDev* d_wn = nullptr;
   int total_rows = 0, total_blocks = 0;
   bool with_train = false;
   ~WeightLoader() {
-    cudaFree(d_layers); cudaFree(d_row_layer); cudaFree(d_row_idx); cudaFree(d_blk_layer); cudaFree(d_blk_first); cudaFree(d_scale);
+    cudaFree(d_layers); cudaFree(d_row_layer); cudaFree(d_row_idx); cudaFree(d_blk_layer); cudaFree(d_blk_first); cudaFree(d_scale); cudaFree(d_wn);
   }
 };
 
@@ -136,7 +178,9 @@ static int prepare_loader(nvse_generator* g, bool with_train) {
   NVSE_CUDA_CHECK(cudaMemcpy(ld->d_row_idx, row_idx.data(), sizeof(int) * row_idx.size(), cudaMemcpyHostToDevice));
   NVSE_CUDA_CHECK(cudaMemcpy(ld->d_blk_layer, blk_layer.data(), sizeof(int) * blk_layer.size(), cudaMemcpyHostToDevice));
   NVSE_CUDA_CHECK(cudaMemcpy(ld->d_blk_first, blk_first.data(), sizeof(int) * blk_first.size(), cudaMemcpyHostToDevice));
+  NVSE_CUDA_CHECK(cudaMalloc(&ld->d_wn, sizeof(WnBwdDev) * g->layers.size()));
   ld->host.resize(g->layers.size());
+  ld->wn_host.resize(g->layers.size());
   return NVSE_OK;
 }
 
@@ -192,5 +236,41 @@ extern "C" int nvse_generator_layer_name(const nvse_generator* g, int index, cha
   const std::string& s = g->layers[index].name;
   NVSE_REQUIRE(s.size() + 1 <= capacity, NVSE_ERR_INVALID, "nvse_generator_layer_name: buffer too small");
   memcpy(out, s.c_str(), s.size() + 1);
+  return NVSE_OK;
+}
+
+extern "C" int64_t nvse_generator_total_rows(const nvse_generator* g) {
+  if (!g) return -1;
+  int64_t n = 0;
+  for (const Layer& L : g->layers) n += L.transposed ? L.Cin : L.Cout;
+  return n;
+}
+
+extern "C" int nvse_generator_weight_norm_backward(nvse_generator* g, const float* const* weight_v, const float* const* weight_g,
+                                                   const float* grads, float* dv_flat, float* dg_flat, int n_layers,
+                                                   void* stream) {
+  NVSE_REQUIRE(g && weight_v && weight_g && grads && dv_flat && dg_flat, NVSE_ERR_INVALID,
+               "nvse_generator_weight_norm_backward: null argument");
+  NVSE_REQUIRE(n_layers == (int)g->layers.size(), NVSE_ERR_INVALID, "nvse_generator_weight_norm_backward: expected %d layers",
+               (int)g->layers.size());
+  NVSE_REQUIRE(g->loader, NVSE_ERR_STATE, "nvse_generator_weight_norm_backward: load the weights with nvse_generator_load_weights first");
+  WeightLoader* ld = g->loader;
+  cudaStream_t st = as_stream(stream);
+  int64_t row_off = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    const Layer& L = g->layers[i];
+    const int rows = L.transposed ? L.Cin : L.Cout;
+    WnBwdDev& d = ld->wn_host[i];
+    d.v = weight_v[i]; d.g = weight_g[i];
+    d.dw = grads + L.grad_off;
+    d.dv = dv_flat + L.grad_off;
+    d.dg = dg_flat + row_off;
+    d.cols = (int64_t)L.Cin * L.Cout * L.k / rows;
+    NVSE_REQUIRE(!d.g || d.v, NVSE_ERR_INVALID, "layer '%s': weight_g without weight_v", L.name.c_str());
+    row_off += rows;
+  }
+  NVSE_CUDA_CHECK(cudaMemcpyAsync(ld->d_wn, ld->wn_host.data(), sizeof(WnBwdDev) * n_layers, cudaMemcpyHostToDevice, st));
+  wn_bwd_all_kernel<<<(unsigned)ld->total_rows, 256, 0, st>>>(ld->d_wn, ld->d_row_layer, ld->d_row_idx);
+  NVSE_LAUNCH_CHECK("wn_bwd_all_kernel");
   return NVSE_OK;
 }
