@@ -102,8 +102,8 @@ static int run_conv(const Layer& L, bool tc, const ConvIO& io, int64_t B, int64_
 // ConvTranspose1d as `stride` polyphase tap-list convolutions.  On the tensor-core
 // path up to 8 phases share one launch: the activation tile is staged once and the phases ping-pong
 // between two TMEM accumulators.
-static int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
-                              cudaStream_t st, bool x_t32 = false, bool y_t32 = false) {
+int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
+                       cudaStream_t st, bool x_t32, bool y_t32) {
   const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
   const int nph = (int)std::min<int64_t>(L.stride, Tout);
   if (tc && L.w_bf16) {

@@ -299,7 +299,7 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
     const Layer& up = g->layer("ups." + std::to_string(i));
     float* xu = tp + p.xu[i];
     float* xs = tp + p.xs[i];
-    if (int rc = convT_fwd(up, prev, xu, B, Tprev, slope, st)) return rc;  // hifigan.py:111-112
+    if (int rc = (tc ? run_conv_transpose(up, true, prev, B, Tprev, xu, slope, st) : convT_fwd(up, prev, xu, B, Tprev, slope, st))) return rc;  // hifigan.py:111-112
     const int64_t T = p.T[i];
     const bool conc = concurrent_ok(c);  // the ResBlocks of the MRF are independent: caller's stream + two side streams
     if (conc) {

@@ -24,16 +24,24 @@ mel_in = torch.from_numpy(synth.make_mel(B, FR, 1)).cuda()
 y = torch.from_numpy(synth.make_wave(B, FR * 256, 2)).cuda()
 
 
-def timed(fn, steps):
+HOST_MS = {}
+
+
+def timed(fn, steps, tag=None):
+    import time
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
+    t1 = time.perf_counter()   # host time to ENQUEUE the steps (no sync inside): >= device time means host-bound
     torch.cuda.synchronize()
+    if tag:
+        HOST_MS[tag] = (t1 - t0) * 1e3 / steps
     return e0.elapsed_time(e1) / steps
 
 
@@ -86,12 +94,13 @@ l_ours, l_stock = float(ours().detach()), float(stock().detach())
 res["loss_ours"], res["loss_stock_torch"] = l_ours, l_stock
 for prec in ("fp32", "bf16"):
     gen.precision = prec
-    res[f"ours_{prec}_ms"] = timed(ours, STEPS)
+    res[f"ours_{prec}_ms"] = timed(ours, STEPS, f"ours_{prec}")
     res[f"loss_ours_{prec}"] = float(ours().detach())
 for tf32 in (True, False):
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
-    res["stock_torch_ms_tf32" if tf32 else "stock_torch_ms_fp32"] = timed(stock, STEPS)
+    res["stock_torch_ms_tf32" if tf32 else "stock_torch_ms_fp32"] = timed(stock, STEPS, "stock_tf32" if tf32 else "stock_fp32")
+res["host_enqueue_ms_per_step"] = HOST_MS
 # where the time goes (per-launch CUDA events of the library's own profiler)
 lib_mod.profile_begin()
 ours()
