@@ -221,6 +221,16 @@ NVSE_API int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t frame
                             const void* tape, size_t tape_bytes, float* grads, float* dmel, void* workspace,
                             size_t workspace_bytes, int precision, void* stream);
 
+/* dataset.amp_pha_specturm (dataset.py:124-139): the STFT of the front-end (torch.stft(y, n_fft, hop, win, hann,
+ * center=True)) written out as log(|X| + 1e-7), atan2(Im, Re), Re, Im -- each [B, n_fft/2+1, frames]; any plane may be
+ * NULL.  The handle's mel basis is not used. */
+NVSE_API int nvse_frontend_stft_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride,
+                           float* log_amp, float* phase, float* real, float* imag, void* stream);
+/* dataset.inverse_mel (dataset.py:94-121): out[b, k, f] = sum_m inv_basis[k, m] * exp(mel[b, m, f]);
+ * inv_basis [n_bins, n_mels] = pinverse of the mel basis (device), mel [B, n_mels, frames], out [B, n_bins, frames]. */
+NVSE_API int nvse_inverse_mel_f32(const float* inv_basis, const float* mel, float* out, int64_t B, int n_bins, int n_mels,
+                         int64_t frames, void* stream);
+
 /* Backward of nvse_frontend_mel_f32 (the mel-L1 term of the generator loss differentiates
  * mel_spectrogram(y_g_hat), train_time_wi_inv.py:173-179,231-235): dmel [B, n_mels, frames] -> dy [B, T] (dense).
  * The spectra are recomputed from y (nothing is saved by the forward).  Bit-reproducible. */

@@ -388,6 +388,157 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) mel_frontend_bwd_kernel(con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dataset.amp_pha_specturm (reference dataset.py:124-139): the same packed STFT, with the complex spectrum
+// written out as log-amplitude, phase, real and imaginary planes [B, 513, F] instead of being reduced to mels
+// (the T-F vocoders' analysis front-end and STFT-consistency loss).
+// ------------------------------------------------------------------------------------------------
+struct StftParams {
+  FrontendParams f;
+  float* log_amp;  // each [B, 513, F] or null
+  float* phase;
+  float* real;
+  float* imag;
+};
+
+// One CTA = kWarpsPerCta frame pairs = 8 CONSECUTIVE frames of one utterance: the planes of the 8 frames are collected
+// in a shared tile [plane][bin][frame] and written out with 8 consecutive frames (32 B) per (plane, bin), so every store
+// fills whole sectors -- a lane writing its own bins directly would touch one float per 32-byte sector.  Two passes of
+// two planes each (log-amplitude + phase, then real + imaginary) over a tile that aliases the FFT scratch keep the CTA at
+// ~37 KB of shared memory (5-6 CTAs per SM): the kernel is latency-bound like the mel front-end.
+constexpr int kStftFrames = 2 * kWarpsPerCta;
+constexpr int kStftPitch = kStftFrames + 1;                 // conflict-free: lanes write consecutive bins
+constexpr int kStftTileFloats = 2 * kBins * kStftPitch;
+constexpr int kStftSmemFloats = kStftTileFloats > kWarpSmemFloats * kWarpsPerCta ? kStftTileFloats : kWarpSmemFloats * kWarpsPerCta;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) stft_amp_pha_kernel(const StftParams q, int groups_per_utt) {
+  extern __shared__ float smem[];
+  const FrontendParams& p = q.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = smem;                                   // [2][kBins][kStftPitch], aliases the FFT scratch
+  float* sre = smem + warp * kWarpSmemFloats;
+  float* sim = sre + 32 * kTransposeStride;
+  const int64_t b = blockIdx.x / groups_per_utt;
+  const int64_t f_base = (int64_t)(blockIdx.x % groups_per_utt) * kStftFrames;
+  const int64_t f0 = f_base + 2 * warp;
+  const bool active = f0 < p.F;  // warp-uniform
+  float re[32], im[32];
+  if (active) {
+    const bool has_b = (f0 + 1) < p.F;
+    const float* __restrict__ yrow = p.y + b * p.y_stride;
+    const int64_t sa = f0 * p.hop - kNfft / 2;
+    const int64_t sb = sa + p.hop;
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      const int n = lane + 32 * m;
+      const float w = __ldg(p.window + n);
+      re[m] = __ldg(yrow + reflect_index(sa + n, p.T)) * w;
+      im[m] = has_b ? __ldg(yrow + reflect_index(sb + n, p.T)) * w : 0.0f;
+    }
+    fft1024_warp(re, im, sre, sim, p.twiddle, lane);
+  }
+  const int src_lane = (32 - lane) & 31;
+  const int nf = (int)((p.F - f_base) < kStftFrames ? (p.F - f_base) : kStftFrames);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float* out0 = pass == 0 ? q.log_amp : q.real;
+    float* out1 = pass == 0 ? q.phase : q.imag;
+    if (!out0 && !out1) continue;  // uniform over the CTA
+    __syncthreads();  // the scratch (pass 0) / the previous pass's tile is no longer read
+    if (active) {
+      auto emit = [&](int k, float xr, float xi, int frame) {
+        float* t = tile + k * kStftPitch + 2 * warp + frame;
+        if (pass == 0) {
+          t[0] = logf(sqrtf(xr * xr + xi * xi) + 1e-7f);
+          t[kBins * kStftPitch] = atan2f(xi, xr);
+        } else {
+          t[0] = xr;
+          t[kBins * kStftPitch] = xi;
+        }
+      };
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+        float pr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], src_lane);
+        float pi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], src_lane);
+        if (lane == 0) {
+          pr = re[brev5((32 - k2) & 31)];
+          pi = im[brev5((32 - k2) & 31)];
+        }
+        const int k = lane + 32 * k2;
+        emit(k, 0.5f * (zr + pr), 0.5f * (zi - pi), 0);     // A = (Z[k] + conj Z[N-k]) / 2
+        emit(k, 0.5f * (zi + pi), -0.5f * (zr - pr), 1);    // B = (Z[k] - conj Z[N-k]) / 2i
+      }
+      if (lane == 0) {  // Nyquist bin: Z[512] = A[512] + i B[512], both real
+        emit(512, re[brev5(16)], 0.0f, 0);
+        emit(512, im[brev5(16)], 0.0f, 1);
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kBins * kStftFrames; e += kWarpsPerCta * 32) {
+      const int k = e / kStftFrames, fr = e % kStftFrames;
+      if (fr < nf) {
+        const int64_t o = (b * kBins + k) * p.F + f_base + fr;
+        if (out0) out0[o] = tile[k * kStftPitch + fr];
+        if (out1) out1[o] = tile[kBins * kStftPitch + k * kStftPitch + fr];
+      }
+    }
+  }
+}
+
+// dataset.inverse_mel (reference dataset.py:94-121): out[b, k, f] = sum_m inv_basis[k, m] * exp(mel[b, m, f]).
+// A small GEMM: one CTA computes 128 bins x 128 frames, each thread 8 bins x (4 + 4) frames (four LDS.128 per 64 FMAs; a
+// warp's stores cover 64 consecutive frames of two bins); exp(mel) is applied once while staging.
+constexpr int kInvBins = 128, kInvFrames = 128, kInvMelChunk = 16;
+__global__ void __launch_bounds__(256) inverse_mel_kernel(const float* __restrict__ inv_basis, const float* __restrict__ mel,
+                                                          float* __restrict__ out, int n_bins, int n_mels, int64_t F) {
+  __shared__ __align__(16) float Es[kInvMelChunk][kInvFrames];
+  __shared__ __align__(16) float Ws[kInvMelChunk][kInvBins + 4];  // +4: the transposing stores spread over the banks
+  const int64_t b = blockIdx.z, f0 = (int64_t)blockIdx.x * kInvFrames;
+  const int k0 = blockIdx.y * kInvBins;
+  const int fx = threadIdx.x & 15, ky = threadIdx.x >> 4;  // 16 x 16 threads
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  for (int m0 = 0; m0 < n_mels; m0 += kInvMelChunk) {
+    for (int e = threadIdx.x; e < kInvMelChunk * kInvFrames; e += 256) {
+      const int m = e / kInvFrames, f = e % kInvFrames;
+      Es[m][f] = (m0 + m < n_mels && f0 + f < F) ? expf(mel[(b * n_mels + m0 + m) * F + f0 + f]) : 0.0f;
+    }
+    for (int e = threadIdx.x; e < kInvMelChunk * kInvBins; e += 256) {
+      const int k = e / kInvMelChunk, m = e % kInvMelChunk;  // consecutive threads read consecutive m of a basis row
+      Ws[m][k] = (m0 + m < n_mels && k0 + k < n_bins) ? __ldg(inv_basis + (int64_t)(k0 + k) * n_mels + m0 + m) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < kInvMelChunk; ++m) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[m][ky * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[m][ky * 8 + 4]);
+      const float4 e0 = *reinterpret_cast<const float4*>(&Es[m][fx * 4]);
+      const float4 e1 = *reinterpret_cast<const float4*>(&Es[m][64 + fx * 4]);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], ev[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + ky * 8 + i;
+    if (k >= n_bins) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t f = f0 + (j < 4 ? fx * 4 + j : 64 + fx * 4 + (j - 4));
+      if (f < F) out[(b * n_bins + k) * F + f] = acc[i][j];
+    }
+  }
+}
+
 // dy[b][t] = sum over the padded positions that read sample t (itself and its reflections) of the frames covering them
 __global__ void __launch_bounds__(256) mel_overlap_add_kernel(const float* __restrict__ frames, float* __restrict__ dy, int64_t B,
                                                               int64_t T, int64_t F, int hop) {
@@ -598,5 +749,47 @@ extern "C" int nvse_frontend_mel_backward_f32(const nvse_frontend* fe, const flo
   const int64_t n = B * T;
   mel_overlap_add_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1 << 20), 256, 0, st>>>(q.frames, dy, B, T, p.F, fe->hop);
   NVSE_LAUNCH_CHECK("mel_overlap_add_kernel");
+  return NVSE_OK;
+}
+
+extern "C" int nvse_frontend_stft_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride,
+                                      float* log_amp, float* phase, float* real, float* imag, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(fe && y, NVSE_ERR_INVALID, "nvse_frontend_stft_f32: null argument");
+  NVSE_REQUIRE(B >= 0 && y_row_stride >= T, NVSE_ERR_INVALID, "nvse_frontend_stft_f32: bad B/stride");
+  NVSE_REQUIRE(T > fe->n_fft / 2, NVSE_ERR_INVALID, "nvse_frontend_stft_f32: reflect padding needs T > n_fft/2 (T=%lld, n_fft=%d)",
+               (long long)T, fe->n_fft);
+  if (B == 0) return NVSE_OK;
+  StftParams q;
+  FrontendParams& p = q.f;
+  p.y = y; p.y_stride = y_row_stride; p.T = T; p.B = B;
+  p.F = 1 + T / fe->hop; p.pairs = (p.F + 1) / 2; p.hop = fe->hop; p.n_mels = fe->n_mels;
+  p.window = fe->window; p.twiddle = fe->twiddle; p.wpack = fe->wpack; p.band_lo = fe->band_lo; p.band_len = fe->band_len;
+  p.out = nullptr;
+  q.log_amp = log_amp; q.phase = phase; q.real = real; q.imag = imag;
+  const int groups_per_utt = (int)((p.F + kStftFrames - 1) / kStftFrames);
+  const int64_t ctas = B * groups_per_utt;
+  NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_stft_f32: problem too large for one launch");
+  const size_t smem = sizeof(float) * kStftSmemFloats;
+  NVSE_CUDA_CHECK(cudaFuncSetAttribute(stft_amp_pha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int planes = (log_amp ? 1 : 0) + (phase ? 1 : 0) + (real ? 1 : 0) + (imag ? 1 : 0);
+  ProfScope prof("stft_amp_pha", 1, planes, 0.0, 4.0 * (double)B * (double)T + 4.0 * planes * (double)B * kBins * (double)p.F, as_stream(stream));
+  stft_amp_pha_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, as_stream(stream)>>>(q, groups_per_utt);
+  NVSE_LAUNCH_CHECK("stft_amp_pha_kernel");
+  return NVSE_OK;
+}
+
+extern "C" int nvse_inverse_mel_f32(const float* inv_basis, const float* mel, float* out, int64_t B, int n_bins, int n_mels,
+                                    int64_t frames, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(inv_basis && mel && out, NVSE_ERR_INVALID, "nvse_inverse_mel_f32: null argument");
+  NVSE_REQUIRE(B >= 0 && B <= 65535 && n_bins >= 1 && n_mels >= 1 && n_mels <= 1024 && frames >= 0, NVSE_ERR_INVALID,
+               "nvse_inverse_mel_f32: bad shape");
+  if (B == 0 || frames == 0) return NVSE_OK;
+  dim3 grid((unsigned)((frames + kInvFrames - 1) / kInvFrames), (unsigned)((n_bins + kInvBins - 1) / kInvBins), (unsigned)B);
+  ProfScope prof("inverse_mel", n_mels, n_bins, 2.0 * (double)B * frames * n_bins * n_mels,
+                 4.0 * (double)B * frames * (n_bins + n_mels), as_stream(stream));
+  inverse_mel_kernel<<<grid, 256, 0, as_stream(stream)>>>(inv_basis, mel, out, n_bins, n_mels, frames);
+  NVSE_LAUNCH_CHECK("inverse_mel_kernel");
   return NVSE_OK;
 }

@@ -105,6 +105,76 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     return out if out.device == out_device else out.to(out_device)
 
 
+def spectral_de_normalize_torch(magnitudes):
+    """dataset.py:39-41 (kept for callers)."""
+    return torch.exp(magnitudes)
+
+
+def inverse_mel(mel, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, in_dataset=False):
+    """Reference ``dataset.inverse_mel`` (dataset.py:94-121): ``pinv(mel_basis) @ exp(mel)`` -> ``[B, n_fft//2+1, F]``
+    (or ``[n_fft//2+1, F]`` for 2-D input), with the reference's ``inv_mel_window`` / ``mel_window`` caches."""
+    global inv_mel_window, mel_window
+    if mel.dim() not in (2, 3):
+        raise RuntimeError(f"inverse_mel expects [B, num_mels, F] or [num_mels, F], got {tuple(mel.shape)}")
+    out_device = torch.device("cpu") if in_dataset else mel.device
+    ps = param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, out_device)
+    if ps in inv_mel_window:
+        inv_basis = inv_mel_window[ps]
+    else:
+        if ps in mel_window:
+            mel_basis, _ = mel_window[ps]
+        else:
+            mel_basis = torch.from_numpy(slaney_mel_basis(sampling_rate, n_fft, num_mels, fmin, fmax)).float().to(out_device)
+            mel_window[ps] = (mel_basis, torch.hann_window(win_size).to(out_device))
+        inv_basis = mel_basis.pinverse()          # once per parameter set, like dataset.py:118
+        inv_mel_window[ps] = inv_basis
+    dev = _cuda_device_for(mel)
+    squeeze = mel.dim() == 2
+    md = mel.detach().to(dev, torch.float32)
+    if squeeze:
+        md = md.unsqueeze(0)
+    md = md.contiguous()
+    batch, n_mels, frames = md.shape
+    if n_mels != inv_basis.shape[1]:
+        raise RuntimeError(f"inverse_mel: mel has {n_mels} bands, the basis {inv_basis.shape[1]}")
+    ib = inv_basis.to(dev, torch.float32).contiguous()
+    out = torch.empty((batch, ib.shape[0], frames), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.load().nvse_inverse_mel_f32(_lib.ptr(ib), _lib.ptr(md), _lib.ptr(out), batch, ib.shape[0], n_mels,
+                                                    frames, stream))
+    if squeeze:
+        out = out[0]
+    return out if out.device == out_device else out.to(out_device)
+
+
+def amp_pha_specturm(y, n_fft, hop_size, win_size):
+    """Reference ``dataset.amp_pha_specturm`` (dataset.py:124-139; the spelling is the reference's):
+    ``(log(|X| + 1e-7), atan2(Im X, Re X), Re X, Im X)`` of ``torch.stft(y, center=True)``, each ``[B, n_fft//2+1, F]``."""
+    if y.dim() not in (1, 2):
+        raise RuntimeError(f"amp_pha_specturm expects a 1-D or 2-D waveform tensor, got {tuple(y.shape)}")
+    dev = _cuda_device_for(y)
+    fe = _frontends.get(("stft", n_fft, 1, 0, 0, win_size, hop_size, dev.index))
+    if fe is None:  # a front-end handle without a mel basis (one zero filter): window + twiddles only
+        fe = _frontend("stft", n_fft, 1, hop_size, win_size, 0, 0, torch.zeros(1, n_fft // 2 + 1), torch.hann_window(win_size), dev)
+    squeeze = y.dim() == 1
+    yd = y.detach().to(dev, torch.float32)
+    if squeeze:
+        yd = yd.unsqueeze(0)
+    if yd.stride(-1) != 1:
+        yd = yd.contiguous()
+    batch, samples = yd.shape
+    frames = 1 + samples // hop_size
+    outs = [torch.empty((batch, n_fft // 2 + 1, frames), dtype=torch.float32, device=dev) for _ in range(4)]
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.load().nvse_frontend_stft_f32(fe, _lib.ptr(yd), batch, samples, yd.stride(0) if batch > 1 else samples,
+                                                      *[_lib.ptr(o) for o in outs], stream))
+    if squeeze:
+        outs = [o[0] for o in outs]
+    return tuple(o if o.device == y.device else o.to(y.device) for o in outs)
+
+
 class _MelFn(torch.autograd.Function):
     """mel_spectrogram as an autograd node: the CUDA forward above, and the CUDA backward
     (nvse_frontend_mel_backward_f32: recomputed spectra -> d|X| -> packed inverse FFT -> overlap-add)."""

@@ -105,6 +105,35 @@ def stft_magnitude(y, n_fft, hop, win, window=None):
     return mag[0] if squeeze else mag
 
 
+def stft_complex(y, n_fft, hop, win):
+    """torch.stft(y, n_fft, hop, win, hann, center=True, return_complex=True) -> complex128 ``[B, n_fft//2+1, F]``."""
+    y = np.asarray(y, dtype=np.float64)
+    squeeze = y.ndim == 1
+    if squeeze:
+        y = y[None]
+    window = hann_periodic(win)
+    if win < n_fft:
+        lp = (n_fft - win) // 2
+        window = np.pad(window, (lp, n_fft - win - lp))
+    yp = reflect_pad(y, n_fft // 2)
+    n_frames = 1 + y.shape[-1] // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
+    spec = np.fft.rfft(yp[:, idx] * window, axis=-1).transpose(0, 2, 1)
+    return spec[0] if squeeze else spec
+
+
+def amp_pha_spectrum(y, n_fft, hop, win):
+    """dataset.py:124-139 (``amp_pha_specturm``): (log(|X| + 1e-7), atan2(Im, Re), Re, Im)."""
+    spec = stft_complex(y, n_fft, hop, win)
+    return np.log(np.abs(spec) + 1e-7), np.arctan2(spec.imag, spec.real), spec.real, spec.imag
+
+
+def inverse_mel(mel, inv_basis):
+    """dataset.py:94-121: ``inv_basis @ exp(mel)`` with ``inv_basis = pinverse(mel_basis)`` supplied by the caller
+    (the reference takes it from ``torch.Tensor.pinverse``; the checker does not re-derive a pseudo-inverse)."""
+    return np.matmul(np.asarray(inv_basis, dtype=np.float64), np.exp(np.asarray(mel, dtype=np.float64)))
+
+
 def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax,
                     center=True, mel_basis=None):
     """dataset.py:53-91: log(clamp(mel_basis @ |STFT|, 1e-5)).  float32 result.
