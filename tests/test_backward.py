@@ -435,3 +435,51 @@ def test_batched_weight_load_matches_per_layer_load():
         grads.append({k: p.grad.cpu() for k, p in g.named_parameters()})
     for k in grads[0]:
         assert torch.equal(grads[0][k], grads[1][k]), k
+
+
+@pytest.mark.gpu
+def test_training_abi_rejects_bad_arguments():
+    """Error behaviour of the training entry points: non-zero return + nvse_last_error(), never a crash."""
+    import ctypes as C
+    lib = lib_mod.load()
+    cfg = synth.CONFIGS["hifigan_train"]
+    gen = build_generator(cfg, synth.make_state(cfg, 3, "unit"), "cuda").train()
+    gen.precision = "fp32"
+    x = torch.from_numpy(synth.make_mel(1, 4, 0)).cuda()
+    out = gen(x)                               # creates and loads the handle
+    h = gen._engine.handle
+    st = stream_ptr()
+    tape = torch.empty(lib.nvse_generator_tape_bytes(h, 1, 4), dtype=torch.uint8, device="cuda")
+    o = torch.empty_like(out)
+    with pytest.raises(lib_mod.NvseError, match="tape too small"):
+        lib_mod.check(lib.nvse_generator_forward_train(h, lib_mod.ptr(x), 1, 4, lib_mod.ptr(o), lib_mod.ptr(tape), 1024, 0, st))
+    with pytest.raises(lib_mod.NvseError, match="bad precision"):
+        lib_mod.check(lib.nvse_generator_forward_train(h, lib_mod.ptr(x), 1, 4, lib_mod.ptr(o), lib_mod.ptr(tape), tape.numel(), 7, st))
+    with pytest.raises(lib_mod.NvseError, match="bad B"):
+        lib_mod.check(lib.nvse_generator_forward_train(h, lib_mod.ptr(x), 0, 4, lib_mod.ptr(o), lib_mod.ptr(tape), tape.numel(), 0, st))
+    grads = torch.empty(lib.nvse_generator_grad_elems(h), device="cuda")
+    ws = torch.empty(64, dtype=torch.uint8, device="cuda")
+    with pytest.raises(lib_mod.NvseError, match="workspace too small"):
+        lib_mod.check(lib.nvse_generator_backward(h, 1, 4, lib_mod.ptr(o), lib_mod.ptr(o), lib_mod.ptr(tape), tape.numel(),
+                                                  lib_mod.ptr(grads), None, lib_mod.ptr(ws), ws.numel(), 0, st))
+    off, n = C.c_int64(), C.c_int64()
+    with pytest.raises(lib_mod.NvseError, match="unknown tensor name"):
+        lib_mod.check(lib.nvse_generator_grad_offset(h, b"ups.9.weight", C.byref(off), C.byref(n)))
+    lib_mod.check(lib.nvse_generator_grad_offset(h, b"conv_post.bias", C.byref(off), C.byref(n)))
+    assert n.value == 1 and off.value + 1 == lib.nvse_generator_grad_elems(h)
+    nl = lib.nvse_generator_num_layers(h)
+    arr = (C.c_void_p * nl)()
+    with pytest.raises(lib_mod.NvseError, match="expected"):
+        lib_mod.check(lib.nvse_generator_load_weights(h, arr, arr, arr, nl - 1, 1, st))
+    with pytest.raises(lib_mod.NvseError, match="missing its weight or bias"):
+        lib_mod.check(lib.nvse_generator_load_weights(h, arr, arr, arr, nl, 1, st))
+    # a rejected load leaves the handle as it was: the previous weights still answer
+    lib_mod.check(lib.nvse_generator_forward_train(h, lib_mod.ptr(x), 1, 4, lib_mod.ptr(o), lib_mod.ptr(tape), tape.numel(), 0, st))
+    torch.cuda.synchronize()
+    assert torch.equal(o, out.detach())
+    # layer-level: even kernel sizes and k > 16 are refused
+    t = torch.zeros(1, 8, 16, device="cuda")
+    w = torch.zeros(16, 16, 4, device="cuda")
+    with pytest.raises(lib_mod.NvseError, match="odd k"):
+        lib_mod.check(lib.nvse_conv1d_backward_f32(lib_mod.ptr(t), lib_mod.ptr(w), lib_mod.ptr(t), None, lib_mod.ptr(t), None, None,
+                                                   1, 8, 16, 16, 4, 1, 0.1, 0, st))
