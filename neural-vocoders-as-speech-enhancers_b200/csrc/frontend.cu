@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) stft_amp_pha_kernel(cons
 // A small GEMM: one CTA computes 128 bins x 128 frames, each thread 8 bins x (4 + 4) frames (four LDS.128 per 64 FMAs; a
 // warp's stores cover 64 consecutive frames of two bins); exp(mel) is applied once while staging.
 constexpr int kInvBins = 128, kInvFrames = 128, kInvMelChunk = 16;
+static_assert(kInvBins == kInvFrames, "one fetch loop stages both operands");
 __global__ void __launch_bounds__(256) inverse_mel_kernel(const float* __restrict__ inv_basis, const float* __restrict__ mel,
                                                           float* __restrict__ out, int n_bins, int n_mels, int64_t F) {
   __shared__ __align__(16) float Es[kInvMelChunk][kInvFrames];
@@ -502,16 +503,29 @@ __global__ void __launch_bounds__(256) inverse_mel_kernel(const float* __restric
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-  for (int m0 = 0; m0 < n_mels; m0 += kInvMelChunk) {
-    for (int e = threadIdx.x; e < kInvMelChunk * kInvFrames; e += 256) {
+  // software pipeline: the next chunk's global loads are in flight (in registers) while this chunk is multiplied
+  constexpr int kPerThread = kInvMelChunk * kInvFrames / 256;  // = kInvMelChunk * kInvBins / 256
+  float pe[kPerThread], pw[kPerThread];
+  auto fetch = [&](int m0) {
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      const int e = threadIdx.x + u * 256;
       const int m = e / kInvFrames, f = e % kInvFrames;
-      Es[m][f] = (m0 + m < n_mels && f0 + f < F) ? expf(mel[(b * n_mels + m0 + m) * F + f0 + f]) : 0.0f;
+      pe[u] = (m0 + m < n_mels && f0 + f < F) ? mel[(b * n_mels + m0 + m) * F + f0 + f] : -INFINITY;  // exp(-inf) = 0
+      const int k = e / kInvMelChunk, mw = e % kInvMelChunk;  // consecutive threads read consecutive m of a basis row
+      pw[u] = (m0 + mw < n_mels && k0 + k < n_bins) ? __ldg(inv_basis + (int64_t)(k0 + k) * n_mels + m0 + mw) : 0.0f;
     }
-    for (int e = threadIdx.x; e < kInvMelChunk * kInvBins; e += 256) {
-      const int k = e / kInvMelChunk, m = e % kInvMelChunk;  // consecutive threads read consecutive m of a basis row
-      Ws[m][k] = (m0 + m < n_mels && k0 + k < n_bins) ? __ldg(inv_basis + (int64_t)(k0 + k) * n_mels + m0 + m) : 0.0f;
+  };
+  fetch(0);
+  for (int m0 = 0; m0 < n_mels; m0 += kInvMelChunk) {
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      const int e = threadIdx.x + u * 256;
+      Es[e / kInvFrames][e % kInvFrames] = expf(pe[u]);
+      Ws[e % kInvMelChunk][e / kInvMelChunk] = pw[u];
     }
     __syncthreads();
+    if (m0 + kInvMelChunk < n_mels) fetch(m0 + kInvMelChunk);
 #pragma unroll
     for (int m = 0; m < kInvMelChunk; ++m) {
       const float4 w0 = *reinterpret_cast<const float4*>(&Ws[m][ky * 8]);
