@@ -60,9 +60,8 @@ TapePlan make_tape(const nvse_generator* g, int64_t B, int64_t F) {
     p.xs.push_back(take(n));
   }
   {
-    int64_t big = 0, Tq = F;
+    int64_t big = 0;
     for (int i = 0; i < p.nstage; ++i) big = std::max(big, B * p.T[i] * (c.initial_channel >> (i + 1)));
-    (void)Tq;
     p.tmp[0] = take(big);
     p.tmp[1] = take(big);
   }
