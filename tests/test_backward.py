@@ -483,3 +483,39 @@ def test_training_abi_rejects_bad_arguments():
     with pytest.raises(lib_mod.NvseError, match="odd k"):
         lib_mod.check(lib.nvse_conv1d_backward_f32(lib_mod.ptr(t), lib_mod.ptr(w), lib_mod.ptr(t), None, lib_mod.ptr(t), None, None,
                                                    1, 8, 16, 16, 4, 1, 0.1, 0, st))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_key,frames,batch", [("hifigan_train", 1, 1), ("hifigan_train", 2, 3), ("istftnet_train", 2, 1)])
+def test_generator_backward_tiny_inputs(cfg_key, frames, batch):
+    """One or two mel frames (every layer shorter than its receptive field), both precisions."""
+    cfg = synth.CONFIGS[cfg_key]
+    state = synth.make_state(cfg, 17, "unit")
+    mel = synth.make_mel(batch, frames, 18)
+    out_len = frames * 256
+    dout = synth.make_dout(batch, out_len, 19)
+    _, ref, dmel_ref = torch_port.hifigan_gradients(state, cfg, mel, dout)
+    out, grads, dmel, _ = _module_grads(cfg, state, mel, dout, precision="fp32")
+    assert out.shape == (batch, out_len)
+    assert _close(dmel.cpu(), dmel_ref, 2e-4)
+    for k, gr in ref.items():
+        assert _close(grads[k].cpu(), gr, 2e-4), k
+    _, g16, _, _ = _module_grads(cfg, state, mel, dout, precision="bf16")
+    assert not lib_mod.tc_abort_status()
+    for k, gr in ref.items():
+        assert torch.isfinite(g16[k]).all(), k
+        assert float(F.cosine_similarity(g16[k].cpu().flatten(), gr.flatten(), dim=0)) >= 0.99, k
+
+
+@pytest.mark.gpu
+def test_mel_backward_1d_input_and_in_dataset_flag():
+    a = synth.HIFIGAN_V1
+    y = synth.make_wave(1, 3000, 5)[0]
+    dmel = np.random.default_rng(6).normal(size=(80, 1 + 3000 // 256)).astype(np.float32)
+    _, ref = _mel_grad_oracle(y[None], a["fmax"], dmel[None])
+    yt = torch.from_numpy(y).cuda().requires_grad_(True)
+    mel = pkg.mel_spectrogram(yt, a["n_fft"], a["num_mels"], a["sampling_rate"], a["hop_size"], a["win_size"], a["fmin"], a["fmax"])
+    assert mel.shape == dmel.shape
+    (mel * torch.from_numpy(dmel).cuda()).sum().backward()
+    assert yt.grad.shape == yt.shape
+    assert float((yt.grad.cpu().double() - ref[0]).abs().max()) <= 2e-5 * float(ref.abs().max())
