@@ -15,6 +15,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 namespace nvse {
 
@@ -234,6 +235,24 @@ inline bool concurrent_ok(const nvse_generator_config& c) {
   return on && c.num_kernels >= 2 && c.num_kernels <= 3;
 }
 
+// (block j, pair m) steps of one MRF.  Sequential: block by block (the blocks accumulate into one buffer in order).
+// Concurrent: pair by pair across the blocks, so that all three streams get work from the first enqueued launches on
+// (the host enqueues ~5 us per launch: block-major order would start stream 2 a millisecond late).
+inline std::vector<std::pair<int, int>> mrf_schedule(const nvse_generator_config& c, bool conc, bool backward) {
+  std::vector<std::pair<int, int>> steps;
+  int max_nd = 0;
+  for (int j = 0; j < c.num_kernels; ++j) max_nd = std::max(max_nd, c.num_dilations[j]);
+  if (!conc) {
+    for (int j = 0; j < c.num_kernels; ++j)
+      for (int q = 0; q < c.num_dilations[j]; ++q) steps.emplace_back(j, backward ? c.num_dilations[j] - 1 - q : q);
+  } else {
+    for (int q = 0; q < max_nd; ++q)
+      for (int j = 0; j < c.num_kernels; ++j)
+        if (q < c.num_dilations[j]) steps.emplace_back(j, backward ? c.num_dilations[j] - 1 - q : q);
+  }
+  return steps;
+}
+
 constexpr int64_t kBwdExtraElems = 1 << 18;  // iSTFTNet conv_post: 32-row padded wT and the padded weight gradient
 
 }  // namespace
@@ -305,28 +324,31 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
       if (int rc = ensure_side_streams(g)) return rc;
       NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
     }
-    for (int j = 0; j < c.num_kernels; ++j) {
+    const float* srcs[NVSE_MAX_KERNELS];
+    for (const auto& jm : mrf_schedule(c, conc, false)) {  // concurrent: pair by pair across the blocks, so every stream has work early
+      const int j = jm.first, m = jm.second;
       const std::string pj = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
       cudaStream_t sj = (conc && j > 0) ? g->side[j - 1] : st;
-      if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
-      float* outj = (conc && j > 0) ? tp + p.tmp[j - 1] : xs;
-      const float* src = xu;
-      for (int m = 0; m < nd; ++m) {
-        const bool last = (m == nd - 1);
-        float* dst = last ? outj : tp + p.xin[i][j][m + 1];
-        const float scale = last ? inv : 1.0f;
-        const int accum = last && j > 0 && !conc;
-        if (c.resblock_type == 1) {  // hifigan.py:43-50
-          float* h = tp + p.h[i][j][m];
-          if (int rc = conv_fwd(g->layer(pj + ".convs1." + std::to_string(m)), src, nullptr, h, B, T, slope, 1.0f, 0, 0, sj, tc)) return rc;
-          if (int rc = conv_fwd(g->layer(pj + ".convs2." + std::to_string(m)), h, src, dst, B, T, slope, scale, accum, 0, sj, tc)) return rc;
-        } else {  // hifigan.py:71-76
-          if (int rc = conv_fwd(g->layer(pj + ".convs." + std::to_string(m)), src, src, dst, B, T, slope, scale, accum, 0, sj, tc)) return rc;
-        }
-        src = dst;
+      if (m == 0) {
+        if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
+        srcs[j] = xu;
       }
-      if (conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
+      float* outj = (conc && j > 0) ? tp + p.tmp[j - 1] : xs;
+      const float* src = srcs[j];
+      const bool last = (m == nd - 1);
+      float* dst = last ? outj : tp + p.xin[i][j][m + 1];
+      const float scale = last ? inv : 1.0f;
+      const int accum = last && j > 0 && !conc;
+      if (c.resblock_type == 1) {  // hifigan.py:43-50
+        float* h = tp + p.h[i][j][m];
+        if (int rc = conv_fwd(g->layer(pj + ".convs1." + std::to_string(m)), src, nullptr, h, B, T, slope, 1.0f, 0, 0, sj, tc)) return rc;
+        if (int rc = conv_fwd(g->layer(pj + ".convs2." + std::to_string(m)), h, src, dst, B, T, slope, scale, accum, 0, sj, tc)) return rc;
+      } else {  // hifigan.py:71-76
+        if (int rc = conv_fwd(g->layer(pj + ".convs." + std::to_string(m)), src, src, dst, B, T, slope, scale, accum, 0, sj, tc)) return rc;
+      }
+      srcs[j] = dst;
+      if (last && conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
     }
     if (conc) {  // xs = (rb0 + rb1) + rb2: the summation order of the sequential path
       for (int q = 1; q < c.num_kernels; ++q) NVSE_CUDA_CHECK(cudaStreamWaitEvent(st, g->ev_join[q - 1], 0));
@@ -432,39 +454,42 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
     const int64_t T = p.T[i];
     const float* xu = tp + p.xu[i];
     if (conc) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
-    for (int j = 0; j < c.num_kernels; ++j) {
+    const float* gcurs[NVSE_MAX_KERNELS];
+    for (const auto& jm : mrf_schedule(c, conc, true)) {
+      const int j = jm.first, m = jm.second;
       const std::string pj = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
       const int jb = conc ? j : 0;
       cudaStream_t sj = (conc && j > 0) ? g->side[j - 1] : st;
-      if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
+      if (m == nd - 1) {
+        if (conc && j > 0) NVSE_CUDA_CHECK(cudaStreamWaitEvent(sj, g->ev_fork, 0));
+        gcurs[j] = dA;  // unscaled: the 1/num_kernels of the MRF average is applied where gradients leave the block
+      }
       const GradSink sj_sink{g, grads, scratch0 + jb * scratch_stride, B, sj, tc ? 1 : 0};
       float* dUj = jbuf(jb, 0);
       float* gTj = jbuf(jb, 1);
       float* gRj = jbuf(jb, 2);
       float* gSj = jbuf(jb, 3);
-      const float* gcur = dA;  // unscaled: the 1/num_kernels of the MRF average is applied where gradients leave the block
-      for (int m = nd - 1; m >= 0; --m) {
-        const float* x_m = m == 0 ? xu : tp + p.xin[i][j][m];
-        float* gnext = m == 0 ? dUj : (gcur == gRj ? gSj : gRj);
-        const float oscale = m == 0 ? inv : 1.0f;
-        const int accum = m == 0 && j > 0 && !conc;
-        if (c.resblock_type == 1) {
-          const Layer& c1 = g->layer(pj + ".convs1." + std::to_string(m));
-          const Layer& c2 = g->layer(pj + ".convs2." + std::to_string(m));
-          const float* h = tp + p.h[i][j][m];
-          if (int rc = conv_dgrad(c2, gcur, h, slope, nullptr, gTj, B, T, 1.0f, 0, sj, tc)) return rc;
-          if (int rc = sj_sink.conv(c2, h, slope, gcur, T, inv)) return rc;
-          if (int rc = conv_dgrad(c1, gTj, x_m, slope, gcur, gnext, B, T, oscale, accum, sj, tc)) return rc;
-          if (int rc = sj_sink.conv(c1, x_m, slope, gTj, T, inv)) return rc;
-        } else {
-          const Layer& cv = g->layer(pj + ".convs." + std::to_string(m));
-          if (int rc = conv_dgrad(cv, gcur, x_m, slope, gcur, gnext, B, T, oscale, accum, sj, tc)) return rc;
-          if (int rc = sj_sink.conv(cv, x_m, slope, gcur, T, inv)) return rc;
-        }
-        gcur = gnext;
+      const float* gcur = gcurs[j];
+      const float* x_m = m == 0 ? xu : tp + p.xin[i][j][m];
+      float* gnext = m == 0 ? dUj : (gcur == gRj ? gSj : gRj);
+      const float oscale = m == 0 ? inv : 1.0f;
+      const int accum = m == 0 && j > 0 && !conc;
+      if (c.resblock_type == 1) {
+        const Layer& c1 = g->layer(pj + ".convs1." + std::to_string(m));
+        const Layer& c2 = g->layer(pj + ".convs2." + std::to_string(m));
+        const float* h = tp + p.h[i][j][m];
+        if (int rc = conv_dgrad(c2, gcur, h, slope, nullptr, gTj, B, T, 1.0f, 0, sj, tc)) return rc;
+        if (int rc = sj_sink.conv(c2, h, slope, gcur, T, inv)) return rc;
+        if (int rc = conv_dgrad(c1, gTj, x_m, slope, gcur, gnext, B, T, oscale, accum, sj, tc)) return rc;
+        if (int rc = sj_sink.conv(c1, x_m, slope, gTj, T, inv)) return rc;
+      } else {
+        const Layer& cv = g->layer(pj + ".convs." + std::to_string(m));
+        if (int rc = conv_dgrad(cv, gcur, x_m, slope, gcur, gnext, B, T, oscale, accum, sj, tc)) return rc;
+        if (int rc = sj_sink.conv(cv, x_m, slope, gcur, T, inv)) return rc;
       }
-      if (conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
+      gcurs[j] = gnext;
+      if (m == 0 && conc && j > 0) NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[j - 1], sj));
     }
     if (conc) {  // dU = (dU_0 + dU_1) + dU_2, the order of the sequential path
       for (int q = 1; q < c.num_kernels; ++q) NVSE_CUDA_CHECK(cudaStreamWaitEvent(st, g->ev_join[q - 1], 0));
