@@ -499,8 +499,18 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
     const Layer& up = g->layer("ups." + std::to_string(i));
     const float* prev = i == 0 ? tp + p.x_pre : tp + p.xs[i - 1];
     const int64_t Tprev = i == 0 ? frames : p.T[i - 1];
-    if (int rc = sink.convT(up, prev, slope, dU, Tprev)) return rc;
-    if (int rc = convT_dgrad(up, dU, prev, slope, dA, B, Tprev, st)) return rc;
+    if (conc) {  // the upsampler's weight gradient (side stream) overlaps its data gradient: both only read dU
+      const GradSink side_sink{g, grads, scratch0 + scratch_stride, B, g->side[0], tc ? 1 : 0};
+      NVSE_CUDA_CHECK(cudaEventRecord(g->ev_fork, st));
+      NVSE_CUDA_CHECK(cudaStreamWaitEvent(g->side[0], g->ev_fork, 0));
+      if (int rc = side_sink.convT(up, prev, slope, dU, Tprev)) return rc;
+      NVSE_CUDA_CHECK(cudaEventRecord(g->ev_join[0], g->side[0]));
+      if (int rc = convT_dgrad(up, dU, prev, slope, dA, B, Tprev, st)) return rc;
+      NVSE_CUDA_CHECK(cudaStreamWaitEvent(st, g->ev_join[0], 0));  // dU is rewritten by the next stage
+    } else {
+      if (int rc = sink.convT(up, prev, slope, dU, Tprev)) return rc;
+      if (int rc = convT_dgrad(up, dU, prev, slope, dA, B, Tprev, st)) return rc;
+    }
   }
   // conv_pre (hifigan.py:109): no activation in front
   const Layer& pre = g->layer("conv_pre");
