@@ -312,7 +312,10 @@ def main():
                           key=lambda r: -r["ms_per_step"]),
     }
     if world == 1:
-        line["train_step"] = train_step(pkg, synth, cfg, dev)
+        try:  # a secondary number must never cost the headline line
+            line["train_step"] = train_step(pkg, synth, cfg, dev)
+        except Exception as e:  # noqa: BLE001
+            line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference(args, args.cpu_utts, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port",
