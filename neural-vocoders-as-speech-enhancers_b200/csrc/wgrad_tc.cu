@@ -14,6 +14,8 @@
 #include "grad.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
+
 namespace nvse {
 
 namespace {
@@ -27,7 +29,7 @@ struct WgTcKernelArgs {
   WgradArgs a;
   int min_off, span;
   int ru_pad, rv_pad;     // staged rows of the U / V tile, padded to an odd count (conflict-free staging stores)
-  int tg, ngroups;        // taps per CTA (tg * Cb <= 512 TMEM columns), tap groups
+  int tg, ngroups;        // taps per CTA (tg * Cb <= 256 TMEM columns: two CTAs share an SM's 512), tap groups
   int chunks_per_b;       // row chunks per utterance
   long long nchunks;      // B * chunks_per_b
   int cps;                // chunks per split (blockIdx.y)
@@ -69,7 +71,7 @@ __device__ __forceinline__ void wg_stage(uint8_t* tile, int rows_pad, int nrows,
 
 // R = V rows (K) per chunk.  grid: (ca tiles * tap groups, splits)
 template <int R>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcKernelArgs k) {
+__global__ void __launch_bounds__(kWgThreads, 2) wgrad_tc_kernel(const __grid_constant__ WgTcKernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const WgradArgs& a = k.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,10 +184,17 @@ WgTcPlan wg_tc_plan(int Ca, int Cb, int ntaps, const int* off, int u_stride, int
     for (int j = 1; j < ntaps; ++j) { lo = std::min(lo, off[j]); hi = std::max(hi, off[j]); }
   }
   p.min_off = lo; p.span = hi - lo;
-  p.R = Cb > 128 ? 128 : 256;
+  static const int env_r = [] { const char* e = std::getenv("NVSE_WG_R"); return e ? std::atoi(e) : 0; }();
+  static const int env_cols = [] { const char* e = std::getenv("NVSE_WG_TMEM"); return e ? std::atoi(e) : 0; }();
+  // measured (tools/wg_ab.sh, training step of HiFi-GAN V1): 128-row chunks + <= 256 TMEM columns per CTA -- two CTAs per
+  // SM, each staging while the other multiplies -- beat 256 rows / 512 columns (one CTA per SM) by 10 % of the
+  // wgrad time although every operand tile is then staged for twice as many tap groups
+  p.R = 128;
+  if (env_r == 128 || env_r == 256) p.R = (Cb > 128) ? 128 : env_r;
   p.ru_pad = (p.R + p.span) | 1;
   p.rv_pad = p.R | 1;
-  p.tg = std::min(ntaps, 512 / Cb);
+  const int cols = (env_cols == 256 || env_cols == 512) ? env_cols : 256;
+  p.tg = std::max(1, std::min(ntaps, cols / Cb));
   p.ngroups = (ntaps + p.tg - 1) / p.tg;
   p.chunks_per_b = (Tv + p.R - 1) / p.R;
   p.nchunks = (long long)B * p.chunks_per_b;
