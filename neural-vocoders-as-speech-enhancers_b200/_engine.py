@@ -84,27 +84,23 @@ class GeneratorEngine:
                 yield name, m
 
     def _key(self, module, dev):
-        """Identity of the weights the handle holds: (data_ptr, version) of every parameter.  Walking
-        ``named_parameters()`` costs ~0.5 ms per call (more than a batch-1 forward on the GPU), so the
-        list of Parameter objects is cached; it is rebuilt when the module's structure changed
-        (``remove_weight_norm`` / re-parametrisation swap Parameter objects: detected through the total
-        parameter count of the conv modules) and, as a backstop, every 256 calls."""
+        """Identity of the weights the handle holds: (data_ptr, version) of every parameter of every conv module, read
+        from the modules' CURRENT ``_parameters`` (so in-place updates, ``remove_weight_norm`` and re-assigned Parameter
+        objects are all seen).  ``named_parameters()`` over the module tree costs ~0.5 ms per call (more than a batch-1
+        forward on the GPU), so the list of conv modules is cached and only re-collected every 256 calls (a sub-module
+        swapped for a new one is the one change this can miss for that long; writes through ``p.data`` bypass autograd's
+        version counter by design and are not seen either -- set ``module._engine.weights_key = None`` after such a write)."""
         self._calls = getattr(self, "_calls", 0) + 1
-        plist = getattr(self, "_plist", None)
         convs = getattr(self, "_convs", None)
-        if convs is not None and (self._calls & 255) != 0:
-            n = 0
-            for m in convs:
-                n += len(m._parameters)
-            if n != self._nparam:
-                plist = None
-        else:
-            plist = None
-        if plist is None:
-            self._convs = [m for _, m in self._conv_modules(module)]
-            self._nparam = sum(len(m._parameters) for m in self._convs)
-            plist = self._plist = list(module.parameters())
-        return (dev.index,) + tuple([(p.data_ptr(), p._version) for p in plist])
+        if convs is None or (self._calls & 255) == 0:
+            convs = self._convs = [m for _, m in self._conv_modules(module)]
+        key = [dev.index]
+        for m in convs:
+            for p in m._parameters.values():
+                if p is not None:
+                    key.append(p.data_ptr())
+                    key.append(p._version)
+        return tuple(key)
 
     def _layer_names(self, lib):
         names = getattr(self, "_names", None)

@@ -553,3 +553,20 @@ def test_tiny_inputs_through_the_fused_t32_path(frames, batch):
         assert float((o32 - ref).abs().max()) <= 1e-4
         assert np_oracle.snr_db(ref.cpu().numpy(), o16.cpu().numpy()) >= 40.0
     assert not lib_mod.tc_abort_status()
+
+
+@pytest.mark.gpu
+def test_reassigned_parameter_is_picked_up():
+    """Replacing a Parameter OBJECT (not just its data) must reload the handle on the next call."""
+    cfg = synth.CONFIGS["hifigan_small"]
+    gen = build_generator(cfg, synth.make_state(cfg, 5, "unit"), "cuda", remove_wn=True)
+    gen.precision = "fp32"
+    mel = torch.from_numpy(synth.make_mel(1, 6, 3)).cuda()
+    with torch.no_grad():
+        y0 = gen(mel)
+        gen.conv_post.bias = torch.nn.Parameter(gen.conv_post.bias.detach() + 0.25)   # same shape, new object
+        y1 = gen(mel)
+        gen.conv_post.bias -= 0.25                                                    # in-place under no_grad: version bump only
+        y2 = gen(mel)
+    assert not torch.equal(y0, y1) and float((y1 - y0).abs().max()) > 1e-2
+    assert float((y2 - y0).abs().max()) < 1e-6 and float((y2 - y1).abs().max()) > 1e-2   # (b + 0.25) - 0.25 rounds
