@@ -1,3 +1,5 @@
+# Same-box A/B of the tensor-core weight-gradient kernel (chunk rows R, TMEM columns per CTA) on the training step:
+#   tools/wg_ab.sh   (on the GPU box; prints step time and the wgrad_tc totals per configuration, sequential and concurrent)
 for cfg in "256 512" "128 512" "128 256" "256 256"; do
   set -- $cfg
   echo "== R=$1 TMEM=$2"
