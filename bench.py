@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--cpu-utts", type=int, default=2, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-utts", type=int, default=0,
+                    help="strong scaling: a FIXED pool of this many utterances (cfg5: 1024) split with shard_range over the ranks; "
+                         "0 = weak scaling (every rank its own --utts-per-gpu shard)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary legs (cfg1 / cfg2 / eager competitor / train step)")
     return ap.parse_args()
 
 
@@ -97,24 +101,73 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_reference(args, n_utts, steps, warmup):
-    """The reference's CPU path (oracle port: same torch.stft / oneDNN conv calls, fp32, all host
-    threads), one utterance at a time like infers/inference_hifigan.py:67-84."""
+REF_STAGE = os.path.join(ROOT, "baseline", "_ref")
+
+
+def load_reference_modules():
+    """The reference's OWN dataset.py / Models/hifigan.py, loaded by file path from baseline/_ref (a plain copy of the
+    reference files staged by __graft_entry__.build(); the reference has no setup.py to pip-install).  librosa is not in
+    this image: tests/shims supplies librosa.filters.mel (= oracle.np_oracle.mel_filterbank).  None when not staged."""
+    import importlib.util
+    if not os.path.isfile(os.path.join(REF_STAGE, "Models", "hifigan.py")):
+        return None
+    shims = os.path.join(ROOT, "tests", "shims")
+    if shims not in sys.path:
+        sys.path.append(shims)
+    mods = {}
+    for name, rel in (("_bench_ref_dataset", "dataset.py"), ("_bench_ref_hifigan", os.path.join("Models", "hifigan.py"))):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_STAGE, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["_bench_ref_dataset"], mods["_bench_ref_hifigan"]
+
+
+def reference_generator(hifigan_mod, cfg, device="cpu"):
+    """Models.HiFiGAN(h) of the reference with the bench's synthetic state dict, eval(), weight norm removed."""
+    import contextlib
     import synth
-    from oracle import torch_port
+    gen = hifigan_mod.HiFiGAN(synth.AttrDict(cfg))
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state(cfg, 1234, "init").items()})
+    gen = gen.to(device).eval()
+    with contextlib.redirect_stdout(sys.stderr):
+        gen.remove_weight_norm()
+    return gen
+
+
+def cpu_reference(args, n_utts, steps, warmup, seconds=None):
+    """The reference's CPU path, one utterance at a time like infers/inference_hifigan.py:67-84, fp32, all host threads:
+    the reference's own modules when baseline/_ref is staged (kind "reference"), else the oracle port (same torch.stft /
+    oneDNN conv calls; kind "port")."""
+    import synth
     cfg = synth.HIFIGAN_V1
     torch.set_num_threads(os.cpu_count() or 1)
-    folded = torch_port.fold_state(synth.make_state(cfg, 1234, "init"))
-    T = int(args.seconds * SR)
+    T = int((seconds or args.seconds) * SR)
     wav = torch.from_numpy(synth.make_wave(n_utts, T, 0))
+    margs = (cfg["n_fft"], cfg["num_mels"], cfg["sampling_rate"], cfg["hop_size"], cfg["win_size"], cfg["fmin"], cfg["fmax"])
+    ref = load_reference_modules()
+    if ref is not None:
+        ds, hg = ref
+        gen = reference_generator(hg, cfg)
+        kind = "reference"
 
-    def step():
-        n = 0
-        for u in range(n_utts):
-            mel = torch_port.mel_spectrogram(wav[u:u + 1], cfg["n_fft"], cfg["num_mels"], cfg["sampling_rate"],
-                                             cfg["hop_size"], cfg["win_size"], cfg["fmin"], cfg["fmax"])
-            n += torch_port.hifigan_forward(folded, cfg, mel).shape[-1]
-        return n
+        @torch.no_grad()
+        def step():
+            n = 0
+            for u in range(n_utts):
+                n += gen(ds.mel_spectrogram(wav[u:u + 1], *margs)).shape[-1]
+            return n
+    else:
+        from oracle import torch_port
+        folded = torch_port.fold_state(synth.make_state(cfg, 1234, "init"))
+        kind = "port"
+
+        def step():
+            n = 0
+            for u in range(n_utts):
+                n += torch_port.hifigan_forward(folded, cfg, torch_port.mel_spectrogram(wav[u:u + 1], *margs)).shape[-1]
+            return n
 
     for _ in range(warmup):
         step()
@@ -123,7 +176,7 @@ def cpu_reference(args, n_utts, steps, warmup):
     for _ in range(steps):
         samples += step()
     dt = time.perf_counter() - t0
-    return samples / SR / dt, dt / steps, torch.get_num_threads()
+    return samples / SR / dt, dt / steps, torch.get_num_threads(), kind
 
 
 def train_step(pkg, synth, cfg, dev, batch=16, frames=32, steps=5):
@@ -164,24 +217,131 @@ def train_step(pkg, synth, cfg, dev, batch=16, frames=32, steps=5):
     return out
 
 
+def cfg1_gpu(voc, synth, dev, reps=30):
+    """cfg1 of BASELINE.json on the GPU through the public host-to-host call: batch 1, 2 s -> mel -> HiFi-GAN V1 -> wav."""
+    wav = torch.from_numpy(synth.make_wave(1, 2 * SR, 3)).pin_memory()
+    out = None
+    for _ in range(5):
+        out = voc.run_host(wav, out)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        voc.run_host(wav, out)
+        torch.cuda.current_stream(dev).synchronize()
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return {"config": "cfg1: HiFi-GAN V1, batch 1, 2 s (173 frames -> 44288 samples), pinned host wav -> pinned host wav, wall clock incl. sync",
+            "ms": med * 1e3, "value": out.shape[-1] / SR / med, "unit": "audio-sec/sec"}
+
+
+def cfg2_frontend(voc, synth, cfg, dev, pk):
+    """cfg2 of BASELINE.json: mel_spectrogram alone on 64 x 4 s, warm (working set L2-resident, back to back) and cold (a
+    256 MB write between launches evicts L2), plus a ~1 GB steady-state size; algorithmic bytes = 4BT + 4*B*80*F."""
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for name, B, secs, reps in (("cfg2_64x4s", 64, 4.0, 50), ("steady_2048x4s", 2048, 4.0, 10)):
+        T = int(secs * SR)
+        wav = torch.from_numpy(synth.make_wave(8, T, 9)).to(dev).repeat(B // 8, 1).contiguous()
+        nbytes = 4.0 * B * T + 4.0 * B * 80 * (1 + T // cfg["hop_size"])
+        for _ in range(3):
+            voc.mel(wav)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            voc.mel(wav)
+        e1.record()
+        torch.cuda.synchronize()
+        warm = e0.elapsed_time(e1) / reps
+        cold = []
+        for _ in range(min(reps, 20)):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            voc.mel(wav)
+            b.record()
+            torch.cuda.synchronize()
+            cold.append(a.elapsed_time(b))
+        cold_ms = statistics.median(cold)
+        out[name] = {"bytes": nbytes, "warm_us": warm * 1e3, "warm_gbs": nbytes / warm / 1e6, "warm_frac_hbm": nbytes / warm / 1e6 / pk["hbm_gbs"],
+                     "cold_us": cold_ms * 1e3, "cold_gbs": nbytes / cold_ms / 1e6, "cold_frac_hbm": nbytes / cold_ms / 1e6 / pk["hbm_gbs"]}
+        del wav
+    out["note"] = "CUDA events around each launch; cold = L2 flushed by a 256 MB fill before every launch; peak = measured copy bandwidth"
+    return out
+
+
+def eager_competitor(args, synth, cfg, dev, wav_dev):
+    """BASELINE.md 3's on-box competitor: the reference's modules under stock PyTorch eager on the SAME B200 (cuFFT /
+    cuDNN / cuBLAS), one micro-batch of the workload, fp32 as shipped (PyTorch's default lets cuDNN use TF32) and under
+    torch.autocast(bf16)."""
+    ref = load_reference_modules()
+    n = min(args.micro_batch, wav_dev.shape[0])
+    wav = wav_dev[:n]
+    margs = (cfg["n_fft"], cfg["num_mels"], cfg["sampling_rate"], cfg["hop_size"], cfg["win_size"], cfg["fmin"], cfg["fmax"])
+    if ref is not None:
+        ds, hg = ref
+        gen = reference_generator(hg, cfg, dev)
+        fwd, kind = (lambda: gen(ds.mel_spectrogram(wav, *margs))), "reference modules (baseline/_ref)"
+    else:
+        from oracle import torch_port
+        folded = {k: v.to(dev) for k, v in torch_port.fold_state(synth.make_state(cfg, 1234, "init")).items()}
+        torch_port._basis_cache.clear()
+
+        def fwd():
+            basis = torch.from_numpy(__import__("oracle.np_oracle", fromlist=["x"]).mel_filterbank(cfg["sampling_rate"], cfg["n_fft"], cfg["num_mels"], cfg["fmin"], cfg["fmax"])).to(dev)
+            spec = torch.stft(wav, cfg["n_fft"], hop_length=cfg["hop_size"], win_length=cfg["win_size"], window=torch.hann_window(cfg["win_size"], device=dev),
+                              center=True, return_complex=True)
+            return torch_port.hifigan_forward(folded, cfg, torch.log(torch.clamp(basis @ spec.abs(), min=1e-5)))
+        kind = "oracle port"
+    res = {"impl": kind, "sample": f"{n} x {args.seconds:g} s utterances per step (one micro-batch), wav on the device -> wav on the device"}
+    for label, ctx in (("fp32_tf32_default", None), ("autocast_bf16", torch.bfloat16)):
+        def run():
+            with torch.no_grad():
+                if ctx is None:
+                    return fwd()
+                with torch.autocast("cuda", dtype=ctx):
+                    return fwd()
+        for _ in range(2):
+            y = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            y = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        res[label] = {"ms": ms, "value": n * y.shape[-1] / SR / (ms * 1e-3), "unit": "audio-sec/sec"}
+        del y
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = (f"cfg5 shard: {args.utts_per_gpu} x {args.seconds:g} s utterances per GPU "
-                f"({args.utts_per_gpu * max(world, args.gpus)} over {max(world, args.gpus)} GPUs), micro-batch {args.micro_batch}")
+    nranks = max(world, args.gpus)
+    if args.total_utts > 0:  # strong scaling: the fixed cfg5 pool split per utterance (shard.shard_range)
+        workload = (f"cfg5 pool: {args.total_utts} x {args.seconds:g} s utterances in total, split contiguously over {nranks} GPUs "
+                    f"({-(-args.total_utts // nranks)} per GPU at most), micro-batch {args.micro_batch}")
+    else:
+        workload = (f"cfg5 shard: {args.utts_per_gpu} x {args.seconds:g} s utterances per GPU "
+                    f"({args.utts_per_gpu * nranks} over {nranks} GPUs), micro-batch {args.micro_batch}")
+    scaling = "strong" if args.total_utts > 0 else "weak"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        v, sec, cores = cpu_reference(args, args.cpu_utts, args.steps, args.warmup)
-        sample = f"{args.cpu_utts} x {args.seconds:g} s utterances per step, batch 1 each, fp32, torch CPU ({cores} threads)"
+        v, sec, cores, kind = cpu_reference(args, args.cpu_utts, args.steps, args.warmup)
+        sample = (f"{args.cpu_utts} x {args.seconds:g} s utterances per step, batch 1 each, fp32, torch CPU ({cores} threads), "
+                  + ("the reference's own dataset.mel_spectrogram + Models.HiFiGAN (baseline/_ref)" if kind == "reference"
+                     else "oracle port of the reference's calls (baseline/_ref not staged)"))
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": "audio-sec/sec", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "audio-sec/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -227,6 +387,10 @@ def main():
     voc = pkg.Vocoder(gen, h, micro_batch=args.micro_batch, device=dev)
 
     U, T = args.utts_per_gpu, int(args.seconds * SR)
+    if args.total_utts > 0:
+        U = len(pkg.shard_range(args.total_utts, world, rank))
+        if U == 0:
+            raise SystemExit(f"--total-utts {args.total_utts} leaves rank {rank} of {world} without work")
     # every rank vocodes its own shard of the global utterance list (per-utterance sharding)
     wav_host = torch.from_numpy(synth.make_wave(U, T, 1000 + rank)).pin_memory()
     wav_dev = wav_host.to(dev)
@@ -234,7 +398,8 @@ def main():
     t_out = frames * 256
     out_dev = torch.empty((U, t_out), dtype=torch.float32, device=dev)
     out_host = torch.empty((U, t_out), dtype=torch.float32).pin_memory()
-    audio_sec_per_step = U * t_out / SR
+    audio_sec_per_step = U * t_out / SR                     # this rank
+    total_audio_sec_per_step = (args.total_utts if args.total_utts > 0 else U * world) * t_out / SR   # whole job
 
     def timed(fn, steps):
         barrier()
@@ -278,9 +443,33 @@ def main():
     if pkg._lib.tc_abort_status():
         raise SystemExit("tensor-core kernel tripped its bounded wait; results invalid")
 
+    # The timed output is CHECKED: the first micro-batch of what the timed steps left in out_dev against the fp32
+    # CUDA-core path of the same module on the same input (itself within 1e-4 of the reference, tests/test_gpu_parity.py);
+    # de-meaned SNR as Metrics/snr.py:25-31, the gate of the 16-bit path is >= 40 dB.
+    def snr_db(ref, deg):
+        ref = ref.double() - ref.double().mean(dim=-1, keepdim=True)
+        deg = deg.double() - deg.double().mean(dim=-1, keepdim=True)
+        return float((10 * torch.log10(ref.pow(2).sum(-1) / (ref - deg).pow(2).sum(-1).clamp_min(1e-30))).min())
+
+    n_chk = min(U, args.micro_batch)
+    with torch.no_grad():
+        gen.precision = "fp32"
+        ref32 = gen(voc.mel(wav_dev[:n_chk]))
+        gen.precision = args.precision
+    parity = {"parity_snr_db": snr_db(ref32, out_dev[:n_chk]), "checked": f"{n_chk} utterances of the timed output vs the fp32 path",
+              "gate_db": 40.0, "max_abs_err": float((ref32 - out_dev[:n_chk]).abs().max())}
+    del ref32
+    if not parity["parity_snr_db"] >= (40.0 if args.precision == "bf16" else 80.0):
+        raise SystemExit(f"timed output fails the parity gate: {parity}")
+
     for _ in range(max(1, args.warmup // 2)):
         host_step()
     ms_e2e = timed(host_step, args.steps)
+    if pkg._lib.tc_abort_status():
+        raise SystemExit("tensor-core kernel tripped its bounded wait during the host leg; results invalid")
+    parity["e2e_vs_device_max_abs"] = float((out_host[:n_chk].to(dev) - out_dev[:n_chk]).abs().max())
+    if parity["e2e_vs_device_max_abs"] != 0.0:
+        raise SystemExit(f"host-buffer path and device-resident path disagree: {parity}")
 
     # per-kernel event timing over the same K steps (separate pass so the events do not perturb `value`)
     pkg._lib.profile_begin()
@@ -289,8 +478,8 @@ def main():
     torch.cuda.synchronize()
     prof = pkg._lib.profile_end()
 
-    value = world * audio_sec_per_step * args.steps / (ms_total / 1e3)
-    e2e = world * audio_sec_per_step * args.steps / (ms_e2e / 1e3)
+    value = total_audio_sec_per_step * args.steps / (ms_total / 1e3)
+    e2e = total_audio_sec_per_step * args.steps / (ms_e2e / 1e3)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -315,15 +504,16 @@ def main():
     fe_gbs = sum(k["bytes"] for k in fe) / (sum(k["ms"] for k in fe) * 1e-3) / 1e9 if fe else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": "audio-sec/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": args.precision, "data": "synthetic",
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic", "parity": parity,
         "config": {"workload": workload, "weights": "random-init (reference-like N(0,0.01), seed 1234), weight_norm folded",
                    "l2": "inputs larger than L2 (113 MB waveforms, GB-scale activations per step)",
                    "operands": "16-bit tensor-core path: bf16 MRF convs, IEEE-half upsamplers and C<=32 second convs, fp32 accumulate, "
                                "fp32 residual stream / conv_pre / conv_post" if args.precision == "bf16" else "fp32 CUDA-core path",
-                   "frames_per_utt": frames, "flop_per_step_per_gpu": FLOP_PER_FRAME * frames * U},
+                   "frames_per_utt": frames, "utts_this_rank": U, "flop_per_step_per_gpu": FLOP_PER_FRAME * frames * U},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "audio-sec/sec", "h2d_bytes_per_step": int(U * T * 4), "d2h_bytes_per_step": int(U * t_out * 4),
+                "bytes_note": "per rank",
                 "ms_per_step": ms_e2e / args.steps, "api": "Vocoder.run_host: pinned host wav -> mel_spectrogram -> HiFiGAN -> pinned host wav"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "resblock_tc_kernel + pair_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs: fused MRF ResBlocks + upsamplers)",
@@ -340,15 +530,24 @@ def main():
                             "gbs": k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] else 0.0} for k in prof),
                           key=lambda r: -r["ms_per_step"]),
     }
-    if world == 1:
-        try:  # a secondary number must never cost the headline line
-            line["train_step"] = train_step(pkg, synth, cfg, dev)
-        except Exception as e:  # noqa: BLE001
-            line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    extras = world == 1 and not args.no_extras
+    if extras:  # secondary numbers: none of them may cost the headline line
+        for key, fn in (("cfg1_gpu", lambda: cfg1_gpu(voc, synth, dev)), ("cfg2_frontend", lambda: cfg2_frontend(voc, synth, cfg, dev, pk)),
+                        ("eager_b200", lambda: eager_competitor(args, synth, cfg, dev, wav_dev)),
+                        ("train_step", lambda: train_step(pkg, synth, cfg, dev))):
+            try:
+                line[key] = fn()
+            except Exception as e:  # noqa: BLE001
+                line[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference(args, args.cpu_utts, 3, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": "port",
+        v, sec, cores, kind = cpu_reference(args, args.cpu_utts, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "audio-sec/sec", "cores": cores, "kind": kind,
                                 "sample": f"{args.cpu_utts} x {args.seconds:g} s utterances x 3 steps, batch 1 each, fp32 torch CPU"}
+        if extras:
+            v1, sec1, _, _ = cpu_reference(args, 1, 5, 1, seconds=2.0)
+            line["cfg1_cpu"] = {"value": v1, "unit": "audio-sec/sec", "ms": sec1 * 1e3, "cores": cores, "kind": kind,
+                                "config": "cfg1: HiFi-GAN V1, batch 1, 2 s waveform -> mel -> waveform, fp32 torch CPU"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -103,9 +103,22 @@ class _GeneratorBase(nn.Module):
         self.conv_post = _wn(nn.Conv1d(ch, post_channels, 7, 1, padding=3))
         _redraw_like_reference(self.ups)
         _redraw_like_reference(self.conv_post)
-        # "bf16" (tcgen05 tensor cores, default) or "fp32"; also NVSE_B200_PRECISION in the environment
+        # inference: "bf16" (tcgen05 tensor cores, default) or "fp32"; also NVSE_B200_PRECISION in the environment
         self.precision = None
+        # training: fp32 like the reference unless set to "bf16" (or NVSE_B200_TRAIN_PRECISION / an explicit .precision)
+        self.train_precision = None
         self._engine = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_engine())
+
+    def invalidate_engine(self):
+        """The native handle re-reads every parameter at the next call (see GeneratorEngine.invalidate)."""
+        if self._engine is not None:
+            self._engine.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): parameters may be re-created
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate_engine()
+        return out
 
     def forward(self, x):
         """mel ``[B, 80, frames]`` -> waveform ``[B, samples]`` on ``x.device``."""
@@ -121,6 +134,7 @@ class _GeneratorBase(nn.Module):
             block.remove_weight_norm()
         _strip_wn(self.conv_pre)
         _strip_wn(self.conv_post)
+        self.invalidate_engine()
 
     def __getstate__(self):  # the native handle is process-local
         state = self.__dict__.copy()

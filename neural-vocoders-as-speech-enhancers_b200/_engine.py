@@ -22,6 +22,20 @@ def resolve_precision(name=None):
         raise ValueError(f"unknown precision {name!r}; use 'fp32' or 'bf16'") from None
 
 
+def resolve_train_precision(module):
+    """Precision of the TRAINING path (forward with a tape + CUDA backward).  The reference trains in fp32
+    (train_time_wi_inv.py has no autocast), so an unmodified training script gets the fp32 kernels: the tensor-core
+    backward (bf16 operands; per-tensor gradients 3-7.5 % relative L2 off fp32) is an explicit opt-in --
+    ``module.train_precision = "bf16"``, ``NVSE_B200_TRAIN_PRECISION=bf16``, or a ``module.precision`` the caller set
+    by hand.  The inference switch ``NVSE_B200_PRECISION`` does not touch training."""
+    name = (getattr(module, "train_precision", None) or os.environ.get("NVSE_B200_TRAIN_PRECISION")
+            or getattr(module, "precision", None) or "fp32")
+    try:
+        return _PRECISIONS[str(name).lower()]
+    except KeyError:
+        raise ValueError(f"unknown training precision {name!r}; use 'fp32' or 'bf16'") from None
+
+
 def make_config(h, kind):
     """cfgs/*.json hyper-parameters (as read at hifigan.py:87-102, istftnet.py:275-297)
     -> struct nvse_generator_config."""
@@ -76,6 +90,15 @@ class GeneratorEngine:
     def __del__(self):
         self.close()
 
+    def invalidate(self):
+        """Forget which weights the handle holds (and the cached list of conv modules): the next forward re-reads every
+        parameter.  Called by the module after ``load_state_dict``, ``remove_weight_norm`` and ``.to()``; call it by hand
+        after writing through ``p.data`` or swapping a sub-module, which neither autograd's version counters nor the
+        hooks can see."""
+        self.weights_key = None
+        self._convs = None
+        self._batched = None
+
     # ---- weights ---------------------------------------------------------------------
     @staticmethod
     def _conv_modules(module):
@@ -87,12 +110,12 @@ class GeneratorEngine:
         """Identity of the weights the handle holds: (data_ptr, version) of every parameter of every conv module, read
         from the modules' CURRENT ``_parameters`` (so in-place updates, ``remove_weight_norm`` and re-assigned Parameter
         objects are all seen).  ``named_parameters()`` over the module tree costs ~0.5 ms per call (more than a batch-1
-        forward on the GPU), so the list of conv modules is cached and only re-collected every 256 calls (a sub-module
-        swapped for a new one is the one change this can miss for that long; writes through ``p.data`` bypass autograd's
-        version counter by design and are not seen either -- set ``module._engine.weights_key = None`` after such a write)."""
+        forward on the GPU), so the list of conv modules is cached and only re-collected every 64 calls (a sub-module
+        swapped for a new one is the one change this can miss, for at most 64 calls; writes through ``p.data`` bypass
+        autograd's version counter by design and are not seen either -- call ``invalidate()`` after either)."""
         self._calls = getattr(self, "_calls", 0) + 1
         convs = getattr(self, "_convs", None)
-        if convs is None or (self._calls & 255) == 0:
+        if convs is None or (self._calls & 63) == 0:
             convs = self._convs = [m for _, m in self._conv_modules(module)]
         key = [dev.index]
         for m in convs:
@@ -183,7 +206,8 @@ class GeneratorEngine:
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters()))):
-            # training step (train_time_wi_inv.py:173-236): fp32 forward with a tape + the CUDA backward
+            # training step (train_time_wi_inv.py:173-236): forward with a tape + the CUDA backward, fp32 unless the
+            # caller opted in to the tensor-core training path (resolve_train_precision)
             return _GeneratorTrainFn.apply(self, module, x, *[p for _, p in module.named_parameters()])
         if x.is_cuda:
             dev = x.device
@@ -210,9 +234,11 @@ class GeneratorEngine:
                                                   _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
         return out if x.is_cuda else out.to(x.device)
 
-    # ---- training (fp32) -------------------------------------------------------------
+    # ---- training ---------------------------------------------------------------------
     def forward_train(self, module, x):
-        """Forward that keeps every convolution input on an fp32 tape; returns (out, tape, precision)."""
+        """Forward that keeps every convolution input on an fp32 tape; returns (out, tape, precision).  The arithmetic is
+        fp32 CUDA cores by default, tensor cores (bf16 operands, fp32 accumulate / tape / master weights) when opted in
+        (resolve_train_precision)."""
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if not x.is_cuda and not torch.cuda.is_available():
@@ -228,7 +254,7 @@ class GeneratorEngine:
         tape = torch.empty(lib.nvse_generator_tape_bytes(self.handle, batch, frames), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            prec = resolve_precision(getattr(module, "precision", None))
+            prec = resolve_train_precision(module)
             _lib.check(lib.nvse_generator_forward_train(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
                                                         _lib.ptr(tape), tape.numel(), prec, stream))
         return out, tape, prec

@@ -41,6 +41,9 @@ extern std::atomic<uint64_t> g_launches;
     if (!(cond)) return ::nvse::fail(code, __VA_ARGS__);  \
   } while (0)
 
+// SM count of the CURRENT device (cached per device index: one process may drive several GPUs)
+int device_sm_count();
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Optional per-launch timing (nvse_profile_begin / nvse_profile_end): when enabled every launch

@@ -445,7 +445,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   dim3 grid((unsigned)((a.Trows + kTileM * ntile - 1) / (kTileM * ntile)), (unsigned)B);
   // Small grids (the batch-1 case): one phase per CTA, the phases of a tile on different SMs -- each CTA then
   // streams 1 / nphase of the weights, which is what a few-CTA ConvTranspose1d launch is bound by.
-  static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+  const int sm_count = device_sm_count();
   if (nphase > 1 && (int64_t)grid.x * grid.y * nphase <= 2 * sm_count) {
     k.ph_per_cta = 1;
     grid.z = (unsigned)nphase;
@@ -476,15 +476,6 @@ int launch_conv_tc(const ConvTcArgs& a, int64_t B, cudaStream_t st) {
   return launch_conv_tc_phases(a, &a.taps, &a.out_add, 1, B, st);
 }
 
-int tc_abort_status(bool reset, unsigned int* flag) {
-  unsigned int v = 0;
-  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));
-  if (reset && v) {
-    const unsigned int z = 0;
-    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));
-  }
-  *flag = v;
-  return NVSE_OK;
-}
+NVSE_TC_ABORT_IMPL(tc)
 
 }  // namespace nvse

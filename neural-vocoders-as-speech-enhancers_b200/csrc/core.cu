@@ -198,6 +198,21 @@ int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, 
 
 }  // namespace nvse
 
+namespace nvse {
+int device_sm_count() {
+  static std::atomic<int> cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+}  // namespace nvse
+
 extern "C" int nvse_abi_version(void) { return NVSE_ABI_VERSION; }
 extern "C" const char* nvse_last_error(void) { return nvse::last_error_slot().c_str(); }
 extern "C" uint64_t nvse_launch_count(void) { return nvse::g_launches.load(); }

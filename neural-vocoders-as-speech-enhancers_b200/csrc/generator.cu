@@ -472,6 +472,7 @@ extern "C" int nvse_generator_forward(nvse_generator* g, const float* mel, int64
   NVSE_REQUIRE(B >= 0 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_forward: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
   NVSE_REQUIRE(precision == NVSE_PRECISION_F32 || precision == NVSE_PRECISION_BF16, NVSE_ERR_INVALID, "bad precision %d", precision);
   if (B == 0) return NVSE_OK;
+  if (int rc = tc_abort_poll(as_stream(stream))) return rc;  // a timed-out kernel of an earlier call is an error, not garbage
   const size_t need = nvse_generator_workspace_bytes(g, B, frames, precision);
   NVSE_REQUIRE(workspace && workspace_bytes >= need, NVSE_ERR_INVALID, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   NVSE_REQUIRE(max_activation_elems(g, frames) * 4 < (int64_t)1 << 40, NVSE_ERR_INVALID, "utterance too long");

@@ -58,5 +58,12 @@ int ensure_side_streams(nvse_generator* g);  // g->side[], ev_fork, ev_join[]: t
 int finalize_plan(nvse_generator* g);                    // allocates the tensor-core image buffers, sets the per-layer precision flags
 int finalize_bf16(nvse_generator* g, cudaStream_t st);  // finalize_plan + builds the tensor-core weight images
 int tc_abort_status(bool reset, unsigned int* flag);
+int tc_abort_bind(unsigned int* host_word_dev);
+int tc_abort_clear(cudaStream_t st);
+// tc_abort.cu: bind this device to the shared host word; poll it on entry of a product call (NVSE_ERR_STATE if a
+// kernel of an earlier call timed out; the flags are cleared so later calls run)
+int tc_abort_bind_device();
+int tc_abort_poll(cudaStream_t st);
+void tc_abort_host_clear();
 
 }  // namespace nvse

@@ -305,6 +305,7 @@ extern "C" int nvse_generator_forward_train(nvse_generator* g, const float* mel,
   const TapePlan p = make_tape(g, B, frames);
   float* tp = reinterpret_cast<float*>((reinterpret_cast<size_t>(tape) + 255) / 256 * 256);
   cudaStream_t st = as_stream(stream);
+  if (int rc = tc_abort_poll(st)) return rc;
   const float slope = 0.1f;  // LRELU_SLOPE, hifigan.py:7
   const bool tc = precision == NVSE_PRECISION_BF16;
 
@@ -381,6 +382,7 @@ extern "C" int nvse_generator_backward(nvse_generator* g, int64_t B, int64_t fra
   const float* tp = reinterpret_cast<const float*>((reinterpret_cast<size_t>(tape) + 255) / 256 * 256);
   float* ws = reinterpret_cast<float*>((reinterpret_cast<size_t>(workspace) + 255) / 256 * 256);
   cudaStream_t st = as_stream(stream);
+  if (int rc = tc_abort_poll(st)) return rc;
   if (int rc = prepare_train(g, st)) return rc;
   const int64_t be = align64(p.max_act);
   float* dA = ws;            // gradient w.r.t. the MRF output of the current stage (then w.r.t. the previous stage's)

@@ -34,6 +34,8 @@ bool wgrad_tc_supported(int Ca, int Cb, int ntaps, const int* off, int u_stride,
 size_t wgrad_tc_scratch_elems(int Ca, int Cb, int ntaps, int64_t B, int Tv);
 int launch_wgrad_tc(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t st);
 int wgrad_abort_status(bool reset, unsigned int* flag);
+int wgrad_abort_bind(unsigned int* host_word_dev);
+int wgrad_abort_clear(cudaStream_t st);
 
 // dst[c] = scale * sum over rows of V[row][c]   (bias gradient; V dense [rows, C]);  scratch: colsum_scratch_elems floats
 size_t colsum_scratch_elems(int C, int64_t rows);

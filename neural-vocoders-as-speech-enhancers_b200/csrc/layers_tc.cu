@@ -146,5 +146,6 @@ extern "C" int nvse_tc_abort_status(int reset, int* flag) {
   if (int rc = pair_abort_status(reset != 0, &v3)) return rc;
   if (int rc = wgrad_abort_status(reset != 0, &v4)) return rc;
   *flag = (int)(v | v2 | v3 | v4);
+  if (reset) tc_abort_host_clear();
   return NVSE_OK;
 }

@@ -386,7 +386,7 @@ int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   const int64_t n_items = (int64_t)k.tiles_per_seq * B;
   NVSE_REQUIRE(n_items < (int64_t)1 << 30, NVSE_ERR_INVALID, "pipelined pair kernel: too many tiles");
   k.n_items = (int)n_items;
-  static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+  const int sm_count = device_sm_count();
   const unsigned grid = (unsigned)std::min<int64_t>(n_items, sm_count);
   const double rows = (double)B * a.T;
   ProfScope prof("pair_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0, rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
@@ -401,15 +401,6 @@ int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   return NVSE_OK;
 }
 
-int pair_abort_status(bool reset, unsigned int* flag) {
-  unsigned int v = 0;
-  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));
-  if (reset && v) {
-    const unsigned int z = 0;
-    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));
-  }
-  *flag = v;
-  return NVSE_OK;
-}
+NVSE_TC_ABORT_IMPL(pair)
 
 }  // namespace nvse

@@ -841,7 +841,7 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   if (k.a.bstride == 0) k.a.bstride = (a.t32 ? t32_rows(a.T) : (int64_t)a.T) * a.C;
   k.trace = nullptr;
   k.trace = trace_buffer();
-  static const int sm_count = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+  const int sm_count = device_sm_count();
   k.sm_count = sm_count;
   k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.P0 = p.P0; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
   dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
@@ -870,16 +870,7 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
 
 long long* rb_trace_buffer() { return trace_buffer(); }
 
-int rb_abort_status(bool reset, unsigned int* flag) {
-  unsigned int v = 0;
-  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));
-  if (reset && v) {
-    const unsigned int z = 0;
-    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));
-  }
-  *flag = v;
-  return NVSE_OK;
-}
+NVSE_TC_ABORT_IMPL(rb)
 
 }  // namespace nvse
 

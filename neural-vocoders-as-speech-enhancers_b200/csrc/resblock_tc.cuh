@@ -39,11 +39,15 @@ bool rb_supported(int C, int k, const int* dil, int npairs);
 double rb_cost_per_row(int C, int k, const int* dil, int npairs);
 int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st);
 int rb_abort_status(bool reset, unsigned int* flag);
+int rb_abort_bind(unsigned int* host_word_dev);
+int rb_abort_clear(cudaStream_t st);
 long long* rb_trace_buffer();  // debug stamps (NVSE_RB_TRACE), null when off
 
 // pair_tc.cu: persistent, software-pipelined single pair (C = 128), T32 layout only
 bool pair_supported(int C, int k, int dil);
 int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st);
 int pair_abort_status(bool reset, unsigned int* flag);
+int pair_abort_bind(unsigned int* host_word_dev);
+int pair_abort_clear(cudaStream_t st);
 
 }  // namespace nvse

@@ -13,6 +13,10 @@ constexpr long long kTimeoutCycles = 400000000LL;  // ~0.2 s: no legitimate wait
 // set when a bounded wait times out; one copy per translation unit that includes this header
 // (conv_tc.cu, resblock_tc.cu); nvse_tc_abort_status reports the OR of the copies
 static __device__ unsigned int g_tc_abort = 0;
+// device pointer of ONE pinned, mapped host word shared by every translation unit and device (tc_abort.cu): a timeout
+// also raises it, so that the host sees the failure with a plain memory read at the next library call -- no
+// synchronising cudaMemcpyFromSymbol on the product path.  Null until tc_abort_bind() ran for this device.
+static __device__ unsigned int* g_tc_abort_host = nullptr;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,6 +49,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     if ((++spins & 0xffu) == 0) {
       if (clock64() - start > kTimeoutCycles || *(volatile unsigned int*)&g_tc_abort) {
         atomicExch(&g_tc_abort, 1u);
+        if (g_tc_abort_host) {
+          *(volatile unsigned int*)g_tc_abort_host = 1u;
+          __threadfence_system();
+        }
         return false;
       }
     }
@@ -185,4 +193,28 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace tc
+
+// Host side of the per-translation-unit flag: `prefix`_abort_status (read, optionally reset; synchronous -- tests and
+// bench.py), `prefix`_abort_bind (point this TU's copy at the mapped host word), `prefix`_abort_clear (stream-ordered reset).
+#define NVSE_TC_ABORT_IMPL(prefix)                                                                    \
+  int prefix##_abort_status(bool reset, unsigned int* flag) {                                         \
+    unsigned int v = 0;                                                                               \
+    NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));                             \
+    if (reset && v) {                                                                                 \
+      const unsigned int z = 0;                                                                       \
+      NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));                             \
+    }                                                                                                 \
+    *flag = v;                                                                                        \
+    return NVSE_OK;                                                                                   \
+  }                                                                                                   \
+  int prefix##_abort_bind(unsigned int* host_word_dev) {                                              \
+    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort_host, &host_word_dev, sizeof(host_word_dev)));  \
+    return NVSE_OK;                                                                                   \
+  }                                                                                                   \
+  int prefix##_abort_clear(cudaStream_t st) {                                                         \
+    static const unsigned int z = 0;                                                                  \
+    NVSE_CUDA_CHECK(cudaMemcpyToSymbolAsync(tc::g_tc_abort, &z, sizeof(z), 0, cudaMemcpyHostToDevice, st)); \
+    return NVSE_OK;                                                                                   \
+  }
+
 }  // namespace nvse

@@ -243,15 +243,6 @@ int launch_wgrad_tc(const WgradArgs& a, int64_t B, float* scratch, cudaStream_t 
   return launch_wgrad_reduce(scratch, p.nsplit, a.ntaps, a.Ca, a.Cb, a.dst, a.scale, st);
 }
 
-int wgrad_abort_status(bool reset, unsigned int* flag) {
-  unsigned int v = 0;
-  NVSE_CUDA_CHECK(cudaMemcpyFromSymbol(&v, tc::g_tc_abort, sizeof(v)));
-  if (reset && v) {
-    const unsigned int z = 0;
-    NVSE_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_abort, &z, sizeof(z)));
-  }
-  *flag = v;
-  return NVSE_OK;
-}
+NVSE_TC_ABORT_IMPL(wgrad)
 
 }  // namespace nvse

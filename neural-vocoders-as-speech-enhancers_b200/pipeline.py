@@ -88,6 +88,15 @@ class Vocoder:
                 y.record_stream(self._d2h)
                 out_host[s:s + y.shape[0]].copy_(y, non_blocking=True)
         cur.wait_stream(self._d2h)
+        if out_host is None:  # no utterances: an empty result of the right width, like the device-resident path
+            h = self.h
+            n_out = 1
+            for u in h.upsample_rates:
+                n_out *= int(u)
+            if hasattr(h, "gen_istft_hop_size"):
+                n_out *= int(h.gen_istft_hop_size)
+            frames = 1 + wav_host.shape[-1] // int(h.hop_size) if wav_host.dim() == 2 else 0
+            out_host = torch.empty((0, frames * n_out), dtype=torch.int16 if pcm16 else torch.float32)
         return out_host
 
     @torch.no_grad()

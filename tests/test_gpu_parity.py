@@ -428,6 +428,45 @@ def test_full_size_cfg3_fp32_vs_bf16_and_torch():
     assert snr >= 40.0
 
 
+@pytest.mark.parametrize("name,B,F", [("cfg3 at its real batch", 32, 690), ("cfg5 micro-batch (the benchmarked shape)", 32, 862),
+                                      ("cfg1", 1, 173), ("training segment", 16, 65)])
+def test_benchmark_shapes_wav_to_wav(name, B, F):
+    """The shapes BASELINE.json quotes, end to end through the public API (wav -> mel_spectrogram -> HiFiGAN -> wav):
+    mel vs torch.stft-based fp32 ops, fp32 path vs PyTorch fp32 ops on the GPU (max-abs <= 1e-4), 16-bit tensor-core
+    path vs the same (de-meaned SNR >= 40 dB, Metrics/snr.py:25-31), per utterance."""
+    from oracle import torch_port
+    cfg = synth.HIFIGAN_V1
+    state = synth.make_state(cfg, 1234, "init")
+    gen = build_generator(cfg, state, DEV, True)
+    T = (F - 1) * 256 + 17   # F = 1 + T // 256 frames
+    wav = torch.from_numpy(synth.make_wave(B, T, 77)).to(DEV)
+    folded = {k: v.to(DEV) for k, v in torch_port.fold_state(state).items()}
+    basis = torch.from_numpy(np_oracle.mel_filterbank(cfg["sampling_rate"], cfg["n_fft"], cfg["num_mels"], cfg["fmin"], cfg["fmax"])).to(DEV)
+    with torch.no_grad():
+        spec = torch.stft(wav, cfg["n_fft"], hop_length=cfg["hop_size"], win_length=cfg["win_size"],
+                          window=torch.hann_window(cfg["win_size"], device=DEV), center=True, return_complex=True)
+        mel_ref = torch.log(torch.clamp(basis @ spec.abs(), min=1e-5))
+        del spec
+        mel = _mel(wav)
+        assert tuple(mel.shape) == (B, 80, F)
+        mm = synth.mel_mismatch(mel.cpu().numpy(), mel_ref.cpu().numpy(), rtol=1e-4, atol=2e-6)
+        ref = torch_port.hifigan_forward(folded, cfg, mel)
+        gen.precision = "fp32"
+        e32 = float((gen(mel) - ref).abs().max())
+        gen.precision = "bf16"
+        o16 = gen(mel)
+    assert tuple(o16.shape) == (B, 256 * F)
+    r, o = ref.double(), o16.double()
+    r, o = r - r.mean(-1, keepdim=True), o - o.mean(-1, keepdim=True)
+    snr = float((10 * torch.log10(r.pow(2).sum(-1) / (r - o).pow(2).sum(-1))).min())
+    report(f"{name} ({B} x {F} frames, wav -> wav): mel mismatch ratio {mm:.3f} (<=1 at rtol 1e-4), fp32 max-abs {e32:.2e} (<=1e-4), "
+           f"16-bit path worst-utterance SNR {snr:.1f} dB (>=40)")
+    assert mm <= 1.0
+    assert e32 <= 1e-4
+    assert snr >= 40.0
+    assert not lib_mod.tc_abort_status()
+
+
 @pytest.mark.parametrize("seed", [1234, 7, 99])
 def test_full_size_cfg4_istftnet_fp32_vs_bf16_and_torch(seed):
     """BASELINE cfg4 shape at reduced batch (iSTFTNet, 4 x 8 s, F = 690) and the seeds SURVEY 8(d) names:
