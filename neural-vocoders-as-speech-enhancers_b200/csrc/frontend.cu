@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace nvse {
@@ -208,6 +209,193 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, NVSE_FE_MINB) mel_frontend_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Forward kernel, second generation ("staged"): what nvse_frontend_mel_f32 launches.
+//
+// A persistent CTA of 4 warps walks over groups of 8 CONSECUTIVE frames of one utterance (one frame pair per warp):
+//   * the 7 * hop + 1024 samples a group covers are staged in shared memory ONCE, by cp.async, while the previous
+//     group is being transformed (the sample buffer is free again as soon as every warp holds its frames in
+//     registers): frames overlap by 75 %, so every sample is read from L2/HBM once instead of four times and no warp
+//     has a global load on its critical path.  Groups that touch the reflect padding are staged with plain loads;
+//   * the packed 1024-point FFT is the one above, with the 32 x 32 transpose done on (re, im) pairs (64-bit shared
+//     memory accesses, half the instructions);
+//   * the factor 1/2 of the two-real-FFTs-in-one separation is folded into the window (exact: a power of two),
+//     magnitudes use sqrt.approx (1 ulp; the mel sums are checked at 2e-5 relative), and only the bins that carry a
+//     non-zero mel weight are separated at all (fmax 8000 at 22.05 kHz: 372 of 513 -> 12 of 16 passes);
+//   * the banded mel projection runs CTA-wide, one thread per mel row over all 8 frames of the group (a weight is
+//     loaded once per 8 frames; a per-warp projection iterates to the longest band of its lanes three times over);
+//   * the 80 x 8 log-mel tile goes through shared memory so that every global store instruction writes runs of
+//     8 consecutive frames (whole 32-byte sectors where the row is aligned) instead of 2.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFe2Warps = 4;
+constexpr int kFe2Threads = kFe2Warps * 32;
+constexpr int kFe2Frames = 2 * kFe2Warps;
+constexpr int kTr2 = 33;                   // float2 row pitch of the transpose tile: conflict-free for 64-bit accesses both ways
+constexpr int kFe2Scratch = 32 * kTr2;     // float2 per warp: transpose tile, then the (|A|, |B|) magnitudes of its two frames
+constexpr int kFe2OutOff = 520;            // float2 offset inside warp 0's scratch of the [n_mels][8] output tile (above its 513 magnitudes)
+constexpr int kFe2MaxMels = (kFe2Scratch - kFe2OutOff) * 2 / kFe2Frames;  // 134
+
+struct Frontend2Params {
+  FrontendParams f;
+  const float* window_half;  // 0.5 * window
+  int64_t groups;            // ceil(F / 8) frame groups per utterance
+  int64_t total;             // B * groups
+  int nsmp;                  // staged samples per group: 7 * hop + 1024
+  int nsmp_pad;              // rounded up to a multiple of 4 floats
+  int nyquist;               // bin 512 carries mel weight
+  const int4* items;         // mel projection work items: (mel row, first tap, taps, slices of the row | slice index << 8)
+  int nitems;                // padded so that the slices of a row never straddle a warp
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// samples of group g -> ssmp (asynchronously where the group lies inside the utterance and is 16-byte aligned)
+__device__ __forceinline__ void fe2_stage(const Frontend2Params& q, int64_t g, float* ssmp, int tid) {
+  const FrontendParams& p = q.f;
+  const int64_t b = g / q.groups;
+  const int64_t f0 = (g - b * q.groups) * kFe2Frames;
+  const int nf = (int)((p.F - f0) < kFe2Frames ? (p.F - f0) : kFe2Frames);
+  const float* __restrict__ yrow = p.y + b * p.y_stride;
+  const int64_t s0 = f0 * p.hop - kNfft / 2;  // un-padded sample index of staged sample 0
+  if (s0 >= 0 && s0 + q.nsmp <= p.T && ((reinterpret_cast<uintptr_t>(yrow + s0) & 15) == 0)) {
+    for (int i = tid * 4; i + 3 < q.nsmp; i += kFe2Threads * 4) cp_async16(ssmp + i, yrow + s0 + i);
+    for (int i = (q.nsmp & ~3) + tid; i < q.nsmp; i += kFe2Threads) ssmp[i] = __ldg(yrow + s0 + i);
+  } else {
+    const int need = (nf - 1) * p.hop + kNfft;  // samples the existing frames cover; the rest is never stored
+    for (int i = tid; i < q.nsmp; i += kFe2Threads) ssmp[i] = i < need ? __ldg(yrow + reflect_index(s0 + i, p.T)) : 0.0f;
+  }
+}
+
+// K2N: passes of 32 bins that are separated (compile-time: the loop holds warp shuffles and register-indexed arrays)
+template <int K2N>
+__global__ void __launch_bounds__(kFe2Threads, 4) mel_frontend2_kernel(const Frontend2Params q) {
+  extern __shared__ __align__(16) float smem[];
+  const FrontendParams& p = q.f;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* ssmp = smem;
+  float2* scr = reinterpret_cast<float2*>(smem + q.nsmp_pad);  // [4 warps][kFe2Scratch]
+  float2* sz = scr + warp * kFe2Scratch;
+  float* sout = reinterpret_cast<float*>(scr + kFe2OutOff);   // [n_mels][8], inside warp 0's scratch
+
+  int64_t g = blockIdx.x;
+  if (g < q.total) fe2_stage(q, g, ssmp, tid);
+  for (; g < q.total; g += gridDim.x) {
+    const int64_t b = g / q.groups;
+    const int64_t f0 = (g - b * q.groups) * kFe2Frames;
+    const int nf = (int)((p.F - f0) < kFe2Frames ? (p.F - f0) : kFe2Frames);  // frames of this group that exist
+    cp_async_wait_all();
+    __syncthreads();  // samples of this group are in place; the previous group's output tile has been stored
+
+    // Frame b of the last pair of an odd-length utterance does not exist: its samples are staged as zeros (or are
+    // real samples further on), it is transformed like any other and never stored.  Pairs beyond the utterance
+    // (fa >= nf) are transformed as well -- the warp would otherwise idle at the barriers below.
+    const int fa = 2 * warp;
+    float re[32], im[32];
+    {
+      const float* sa = ssmp + fa * p.hop + lane;
+      const float* sb = sa + p.hop;
+      const float* wh = q.window_half + lane;
+#pragma unroll
+      for (int m = 0; m < 32; ++m) {
+        const float w = __ldg(wh + 32 * m);
+        re[m] = sa[32 * m] * w;
+        im[m] = sb[32 * m] * w;
+      }
+    }
+    __syncthreads();  // every warp holds its frames: the sample buffer is free for the next group
+    if (g + gridDim.x < q.total) fe2_stage(q, g + gridDim.x, ssmp, tid);
+
+    fft32_dif(re, im);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+      const int r = brev5(k1);
+      const float2 t = __ldg(p.twiddle + k1 * 32 + lane);
+      sz[k1 * kTr2 + lane] = make_float2(re[r] * t.x - im[r] * t.y, re[r] * t.y + im[r] * t.x);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const float2 v = sz[lane * kTr2 + l];
+      re[l] = v.x;
+      im[l] = v.y;
+    }
+    __syncwarp();
+    fft32_dif(re, im);  // Z[lane + 32*k2] (already halved through the window) is at register brev5(k2)
+
+    // |A[k]|, |B[k]| for the bins that carry mel weight, as (a, b) pairs
+    const int src_lane = (32 - lane) & 31;
+#pragma unroll
+    for (int k2 = 0; k2 < K2N; ++k2) {
+      const float zr = re[brev5(k2)], zi = im[brev5(k2)];
+      float pr = __shfl_sync(0xffffffffu, re[brev5(31 - k2)], src_lane);
+      float pi = __shfl_sync(0xffffffffu, im[brev5(31 - k2)], src_lane);
+      if (lane == 0) {
+        pr = re[brev5((32 - k2) & 31)];
+        pi = im[brev5((32 - k2) & 31)];
+      }
+      const float ar = zr + pr, ai = zi - pi;
+      const float br = zr - pr, bi = zi + pi;
+      sz[lane + 32 * k2] = make_float2(sqrt_approx(fmaf(ar, ar, ai * ai)), sqrt_approx(fmaf(br, br, bi * bi)));
+    }
+    if (q.nyquist && lane == 0) sz[512] = make_float2(2.0f * fabsf(re[brev5(16)]), 2.0f * fabsf(im[brev5(16)]));
+    __syncthreads();  // the magnitudes of all 8 frames are in the four scratch tiles
+
+    // Banded mel projection + log-clamp, all 8 frames at once.  The bands are 3 .. 27 bins long, so a row is cut into
+    // 1, 2 or 4 slices of about equal length on adjacent lanes (work items, built at create time so that every
+    // thread gets at most ~10 taps); the slices of a row are summed with two xor-shuffle rounds.
+    for (int it = tid; it < q.nitems; it += kFe2Threads) {
+      const int4 item = __ldg(q.items + it);
+      const int m = item.x, cnt = item.z, nsl = item.w & 0xff, sl = item.w >> 8;
+      float acc[kFe2Frames];
+#pragma unroll
+      for (int j = 0; j < kFe2Frames; ++j) acc[j] = 0.0f;
+      if (m >= 0) {
+        const float2* mg = scr + __ldg(p.band_lo + m) + item.y;
+        const float* wp = p.wpack + (int64_t)item.y * p.n_mels + m;
+        for (int t = 0; t < cnt; ++t) {
+          const float w = __ldg(wp + (int64_t)t * p.n_mels);
+#pragma unroll
+          for (int wq = 0; wq < kFe2Warps; ++wq) {
+            const float2 v = mg[wq * kFe2Scratch + t];
+            acc[2 * wq] = fmaf(w, v.x, acc[2 * wq]);
+            acc[2 * wq + 1] = fmaf(w, v.y, acc[2 * wq + 1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 1; off <= 2; off <<= 1) {
+#pragma unroll
+        for (int j = 0; j < kFe2Frames; ++j) {
+          const float o = __shfl_xor_sync(0xffffffffu, acc[j], off);
+          if (nsl > off) acc[j] += o;
+        }
+      }
+      if (m >= 0 && sl == 0) {
+        float4* o = reinterpret_cast<float4*>(sout + m * kFe2Frames);
+        o[0] = make_float4(__logf(fmaxf(acc[0], 1e-5f)), __logf(fmaxf(acc[1], 1e-5f)), __logf(fmaxf(acc[2], 1e-5f)), __logf(fmaxf(acc[3], 1e-5f)));
+        o[1] = make_float4(__logf(fmaxf(acc[4], 1e-5f)), __logf(fmaxf(acc[5], 1e-5f)), __logf(fmaxf(acc[6], 1e-5f)), __logf(fmaxf(acc[7], 1e-5f)));
+      }
+    }
+    __syncthreads();  // output tile complete
+
+    // coalesced store of the [n_mels][8] tile: 8 consecutive lanes write 8 consecutive frames of one mel row
+    float* obase = p.out + b * p.n_mels * p.F + f0;
+    for (int e = tid; e < p.n_mels * kFe2Frames; e += kFe2Threads) {
+      const int m = e >> 3, j = e & 7;
+      if (j < nf) obase[(int64_t)m * p.F + j] = sout[e];
+    }
+  }
+  cp_async_wait_all();
+}
 
 // ------------------------------------------------------------------------------------------------
 // Backward of the front-end (the mel-L1 term of the generator loss back-propagates through
@@ -585,6 +773,10 @@ __global__ void __launch_bounds__(256) mel_overlap_add_kernel(const float* __res
 struct nvse_frontend {
   int n_fft, hop, n_mels, max_band;
   float* window = nullptr;
+  float* window_half = nullptr;  // 0.5 * window: the staged forward kernel folds the FFT-separation factor into it
+  int k2n = 16, nyquist = 1;     // which bins carry mel weight (staged forward kernel)
+  int4* items = nullptr;         // mel projection work items of the staged forward kernel
+  int nitems = 0;
   float2* twiddle = nullptr;
   float* wpack = nullptr;
   int* band_lo = nullptr;
@@ -656,6 +848,48 @@ extern "C" int nvse_frontend_create(int n_fft, int hop, int n_mels, const float*
     }                                                                                          \
   } while (0)
   FE_TRY(cudaMalloc(&fe->window, sizeof(float) * kNfft));
+  {
+    std::vector<float> wh(kNfft);
+    for (int i = 0; i < kNfft; ++i) wh[i] = 0.5f * window_host[i];
+    FE_TRY(cudaMalloc(&fe->window_half, sizeof(float) * kNfft));
+    FE_TRY(cudaMemcpy(fe->window_half, wh.data(), sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+    int top = 0;  // one past the highest bin below the Nyquist bin with a non-zero weight in any filter
+    bool nyq = false;
+    for (int m = 0; m < n_mels; ++m) {
+      if (len[m] > 0 && lo[m] + len[m] - 1 == kBins - 1) nyq = true;
+      for (int k = 0; k < kBins - 1; ++k)
+        if (mel_basis_host[(size_t)m * kBins + k] != 0.0f && k + 1 > top) top = k + 1;
+    }
+    fe->k2n = std::min(16, std::max(1, (top + 31) / 32));
+    fe->nyquist = nyq ? 1 : 0;
+    // work items of the mel projection: the smallest chunk size for which every row, cut into 1 / 2 / 4 slices of at most
+    // that many taps on an aligned group of lanes, fits the 128 threads of a CTA in one round
+    std::vector<int4> items;
+    for (int chunk = 4; chunk <= kBins; ++chunk) {
+      items.clear();
+      bool ok = true;
+      for (int m = 0; m < n_mels && ok; ++m) {
+        const int need = std::max(1, (len[m] + chunk - 1) / chunk);
+        const int nsl = need <= 1 ? 1 : (need <= 2 ? 2 : 4);
+        if (need > 4) { ok = false; break; }
+        while (items.size() % nsl) items.push_back(make_int4(-1, 0, 0, 1));  // aligned group of lanes
+        const int per = (len[m] + nsl - 1) / nsl;
+        for (int sidx = 0; sidx < nsl; ++sidx) {
+          const int t0 = std::min(len[m], sidx * per), cnt = std::max(0, std::min(per, len[m] - t0));
+          items.push_back(make_int4(m, t0, cnt, nsl | (sidx << 8)));
+        }
+      }
+      if (ok && (int)items.size() <= 128) break;
+      if (chunk == kBins) {  // does not fit one round even uncut (n_mels > 128): several rounds of whole rows
+        items.clear();
+        for (int m = 0; m < n_mels; ++m) items.push_back(make_int4(m, 0, len[m], 1));
+      }
+    }
+    while (items.size() % 32) items.push_back(make_int4(-1, 0, 0, 1));  // whole warps: the shuffles need every lane
+    fe->nitems = (int)items.size();
+    FE_TRY(cudaMalloc(&fe->items, sizeof(int4) * items.size()));
+    FE_TRY(cudaMemcpy(fe->items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice));
+  }
   FE_TRY(cudaMalloc(&fe->twiddle, sizeof(float2) * tw.size()));
   FE_TRY(cudaMalloc(&fe->wpack, sizeof(float) * wpack.size()));
   FE_TRY(cudaMalloc(&fe->band_lo, sizeof(int) * n_mels));
@@ -677,6 +911,8 @@ extern "C" int nvse_frontend_create(int n_fft, int hop, int n_mels, const float*
 extern "C" int nvse_frontend_destroy(nvse_frontend* fe) {
   if (!fe) return NVSE_OK;
   cudaFree(fe->window);
+  cudaFree(fe->window_half);
+  cudaFree(fe->items);
   cudaFree(fe->twiddle);
   cudaFree(fe->wpack);
   cudaFree(fe->band_lo);
@@ -716,14 +952,40 @@ extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, in
   p.band_lo = fe->band_lo;
   p.band_len = fe->band_len;
   p.out = out;
+  // algorithmic bytes (SURVEY.md 8d): waveform in + log-mel out
+  ProfScope prof("mel_frontend", 1, fe->n_mels, 0.0, 4.0 * (double)B * (double)T + 4.0 * (double)B * fe->n_mels * (double)p.F,
+                 as_stream(stream));
+  static const bool legacy = [] { const char* e = std::getenv("NVSE_FE_LEGACY"); return e && e[0] == '1'; }();
+  Frontend2Params q;
+  q.f = p;
+  q.window_half = fe->window_half;
+  q.groups = (p.F + kFe2Frames - 1) / kFe2Frames;
+  q.total = B * q.groups;
+  q.nsmp = (kFe2Frames - 1) * fe->hop + kNfft;
+  q.nsmp_pad = (q.nsmp + 3) & ~3;
+  q.nyquist = fe->nyquist;
+  q.items = fe->items;
+  q.nitems = fe->nitems;
+  const size_t smem2 = sizeof(float) * ((size_t)q.nsmp_pad + (size_t)kFe2Warps * 2 * kFe2Scratch);
+  if (!legacy && smem2 <= 100 * 1024 && fe->n_mels <= kFe2MaxMels) {  // the staged kernel (persistent CTAs, 8 consecutive frames per step)
+    static const int ctas_per_sm = [] { const char* e = std::getenv("NVSE_FE_CTAS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 4; }();
+    const int64_t ctas = std::min<int64_t>(q.total, (int64_t)device_sm_count() * ctas_per_sm);
+    if (fe->k2n <= 12) {  // fmax 8000 at 22.05 kHz: bins >= 372 carry no mel weight
+      NVSE_CUDA_CHECK(cudaFuncSetAttribute(mel_frontend2_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      mel_frontend2_kernel<12><<<(unsigned)ctas, kFe2Threads, smem2, as_stream(stream)>>>(q);
+    } else {
+      NVSE_CUDA_CHECK(cudaFuncSetAttribute(mel_frontend2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      mel_frontend2_kernel<16><<<(unsigned)ctas, kFe2Threads, smem2, as_stream(stream)>>>(q);
+    }
+    NVSE_LAUNCH_CHECK("mel_frontend2_kernel");
+    return NVSE_OK;
+  }
+  // very large hops: one warp per frame pair straight from global memory
   const int64_t tasks = B * p.pairs;
   const int64_t ctas = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;
   NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: problem too large for one launch");
   const size_t smem = sizeof(float) * kWarpSmemFloats * kWarpsPerCta;
   NVSE_CUDA_CHECK(cudaFuncSetAttribute(mel_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // algorithmic bytes (SURVEY.md 8d): waveform in + log-mel out
-  ProfScope prof("mel_frontend", 1, fe->n_mels, 0.0, 4.0 * (double)B * (double)T + 4.0 * (double)B * fe->n_mels * (double)p.F,
-                 as_stream(stream));
   mel_frontend_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, as_stream(stream)>>>(p);
   NVSE_LAUNCH_CHECK("mel_frontend_kernel");
   return NVSE_OK;
