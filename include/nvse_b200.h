@@ -231,6 +231,14 @@ NVSE_API int nvse_frontend_stft_f32(const nvse_frontend* fe, const float* y, int
 NVSE_API int nvse_inverse_mel_f32(const float* inv_basis, const float* mel, float* out, int64_t B, int n_bins, int n_mels,
                          int64_t frames, void* stream);
 
+/* Inverse STFT at n_fft = 1024, the head of the reference's T-F vocoders (Models/apnet.py:155, Models/freeV.py:178,
+ * Models/bsrnn.py:210): torch.istft(complex(real, imag), n_fft, hop, win, window, center=True) with the handle's window
+ * and hop.  real / imag [B, n_fft/2+1, frames] -> out [B, hop * (frames - 1)].  scratch: caller-owned, at least
+ * nvse_frontend_istft_scratch_bytes (the windowed frames before the overlap-add).  Bit-reproducible. */
+NVSE_API size_t nvse_frontend_istft_scratch_bytes(const nvse_frontend* fe, int64_t B, int64_t frames);
+NVSE_API int nvse_frontend_istft_f32(const nvse_frontend* fe, const float* real, const float* imag, int64_t B, int64_t frames,
+                            float* out, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Backward of nvse_frontend_mel_f32 (the mel-L1 term of the generator loss differentiates
  * mel_spectrogram(y_g_hat), train_time_wi_inv.py:173-179,231-235): dmel [B, n_mels, frames] -> dy [B, T] (dense).
  * The spectra are recomputed from y (nothing is saved by the forward).  Bit-reproducible. */

@@ -197,38 +197,46 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
 // ------------------------------------------------------------------------------------------
 constexpr int POST_ROWS = 256;
 
+// CIN is compile-time so that the staging pass issues all CIN / 4 independent 16-byte loads of a row before the first
+// store: with one load in flight per thread the kernel ran at 1.7 TB/s on a pure streaming job (BENCH_r01).
+template <int CIN>
 __global__ void __launch_bounds__(POST_ROWS) conv_post1_t32_kernel(const ConvF32Args a, int min_off, int span) {
   extern __shared__ __align__(16) float sm[];
-  const int pitch = a.Cin + 4, c4n = a.Cin >> 2, nrows = POST_ROWS + span;
+  constexpr int pitch = CIN + 4, c4n = CIN >> 2;
+  const int nrows = POST_ROWS + span;
   float* xs = sm;                   // [nrows][pitch]
   float* ws = sm + nrows * pitch;   // [ntaps][Cin]
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.y;
   const int t0 = blockIdx.x * POST_ROWS;
   const float* __restrict__ xb = a.x + b * a.x_bstride;
-  for (int e = tid; e < a.taps.ntaps * a.Cin; e += POST_ROWS) {
-    const int tap = e / a.Cin, c = e - tap * a.Cin;
-    ws[e] = a.w[(int64_t)a.taps.widx[tap] * a.Cin + c];
+  for (int e = tid; e < a.taps.ntaps * CIN; e += POST_ROWS) {
+    const int tap = e / CIN, c = e - tap * CIN;
+    ws[e] = a.w[(int64_t)a.taps.widx[tap] * CIN + c];
   }
-  for (int c4 = 0; c4 < c4n; ++c4)
-    for (int r = tid; r < nrows; r += POST_ROWS) {
-      const int t = t0 + min_off + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t >= 0 && t < a.Tin) {
-        v = __ldg(reinterpret_cast<const float4*>(xb + t32_off(t, 4 * c4, a.Cin)));
-        v.x = lrelu(v.x, a.in_slope); v.y = lrelu(v.y, a.in_slope); v.z = lrelu(v.z, a.in_slope); v.w = lrelu(v.w, a.in_slope);
-      }
-      *reinterpret_cast<float4*>(xs + r * pitch + 4 * c4) = v;
+  for (int r = tid; r < nrows; r += POST_ROWS) {
+    const int t = t0 + min_off + r;
+    float4 v[c4n];
+    const bool in = t >= 0 && t < a.Tin;
+    const float4* src = reinterpret_cast<const float4*>(xb + t32_off(in ? t : 0, 0, CIN));
+#pragma unroll
+    for (int c4 = 0; c4 < c4n; ++c4) v[c4] = in ? __ldg(src + 32 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // T32: 4-channel groups 128 floats apart
+#pragma unroll
+    for (int c4 = 0; c4 < c4n; ++c4) {
+      float4 q = v[c4];
+      q.x = lrelu(q.x, a.in_slope); q.y = lrelu(q.y, a.in_slope); q.z = lrelu(q.z, a.in_slope); q.w = lrelu(q.w, a.in_slope);
+      *reinterpret_cast<float4*>(xs + r * pitch + 4 * c4) = q;
     }
+  }
   __syncthreads();
   const int t = t0 + tid;
   if (t >= a.Trows) return;
   float acc = a.bias ? a.bias[0] : 0.0f;
   for (int tap = 0; tap < a.taps.ntaps; ++tap) {
     const float4* xr = reinterpret_cast<const float4*>(xs + (tid + a.taps.off[tap] - min_off) * pitch);
-    const float4* wr = reinterpret_cast<const float4*>(ws + tap * a.Cin);
+    const float4* wr = reinterpret_cast<const float4*>(ws + tap * CIN);
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-#pragma unroll 8
+#pragma unroll
     for (int c4 = 0; c4 < c4n; ++c4) {
       const float4 xv = xr[c4], wv = wr[c4];
       p0 = fmaf(xv.x, wv.x, p0); p1 = fmaf(xv.y, wv.y, p1); p2 = fmaf(xv.z, wv.z, p2); p3 = fmaf(xv.w, wv.w, p3);
@@ -291,11 +299,17 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
     NVSE_REQUIRE(a.in_stride <= 1, NVSE_ERR_UNSUPPORTED, "thin conv: strided input rows are not supported");
     NVSE_REQUIRE(max_off - min_off <= THIN_MAX_SPAN, NVSE_ERR_UNSUPPORTED, "thin conv: tap span %d too wide", max_off - min_off);
     const int span = max_off - min_off;
-    if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 && a.Cin <= 128) {
+    if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 &&
+        (a.Cin == 16 || a.Cin == 32 || a.Cin == 64)) {
       const size_t smem = sizeof(float) * ((size_t)(POST_ROWS + span) * (a.Cin + 4) + (size_t)a.taps.ntaps * a.Cin);
-      NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_post1_t32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((unsigned)((a.Trows + POST_ROWS - 1) / POST_ROWS), (unsigned)B);
-      conv_post1_t32_kernel<<<grid, POST_ROWS, smem, st>>>(a, min_off, span);
+#define POST_LAUNCH(CV)                                                                                                          \
+  if (a.Cin == CV) {                                                                                                             \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_post1_t32_kernel<CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    conv_post1_t32_kernel<CV><<<grid, POST_ROWS, smem, st>>>(a, min_off, span);                                                  \
+  }
+      POST_LAUNCH(16) POST_LAUNCH(32) POST_LAUNCH(64)
+#undef POST_LAUNCH
       NVSE_LAUNCH_CHECK("conv_post1_t32_kernel");
       return NVSE_OK;
     }

@@ -434,7 +434,8 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   NVSE_REQUIRE(act_bytes + 2 * stage_bytes + tail <= budget, NVSE_ERR_UNSUPPORTED,
                "tensor-core conv: tile needs %zu B of shared memory", act_bytes + 2 * stage_bytes + tail);
   const int n_iters = total_taps * (a.Cin / k.kc);
-  int stages = (int)std::min<size_t>((budget - act_bytes - tail) / stage_bytes, (size_t)4);
+  static const int max_stages = [] { const char* e = std::getenv("NVSE_TC_STAGES"); const int v = e ? std::atoi(e) : 0; return v >= 2 && v <= kMaxStages ? v : 4; }();
+  int stages = (int)std::min<size_t>((budget - act_bytes - tail) / stage_bytes, (size_t)max_stages);
   stages = std::max(2, std::min(stages, std::max(2, n_iters)));
   // more resident CTAs per SM beat a deeper weight ring: one CTA's staging / epilogue overlaps another's MMAs
   // (only where that is attainable: a tile that is > 56 KB by itself keeps its 4-stage ring)

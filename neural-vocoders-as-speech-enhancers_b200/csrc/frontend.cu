@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, NVSE_FE_MINB) mel_frontend_
 //   * the 7 * hop + 1024 samples a group covers are staged in shared memory ONCE, by cp.async, while the previous
 //     group is being transformed (the sample buffer is free again as soon as every warp holds its frames in
 //     registers): frames overlap by 75 %, so every sample is read from L2/HBM once instead of four times and no warp
-//     has a global load on its critical path.  Groups that touch the reflect padding are staged with plain loads;
+//     has a global load on its critical path.  Groups that touch the reflect padding are staged element by element;
 //   * the packed 1024-point FFT is the one above, with the 32 x 32 transpose done on (re, im) pairs (64-bit shared
 //     memory accesses, half the instructions);
 //   * the factor 1/2 of the two-real-FFTs-in-one separation is folded into the window (exact: a power of two),
@@ -256,9 +256,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// samples of group g -> ssmp (asynchronously where the group lies inside the utterance and is 16-byte aligned)
+// samples of group g -> ssmp, asynchronously: 16-byte copies where the group lies inside the utterance and is aligned,
+// 4-byte copies through the reflect index otherwise
 __device__ __forceinline__ void fe2_stage(const Frontend2Params& q, int64_t g, float* ssmp, int tid) {
   const FrontendParams& p = q.f;
   const int64_t b = g / q.groups;
@@ -271,7 +275,10 @@ __device__ __forceinline__ void fe2_stage(const Frontend2Params& q, int64_t g, f
     for (int i = (q.nsmp & ~3) + tid; i < q.nsmp; i += kFe2Threads) ssmp[i] = __ldg(yrow + s0 + i);
   } else {
     const int need = (nf - 1) * p.hop + kNfft;  // samples the existing frames cover; the rest is never stored
-    for (int i = tid; i < q.nsmp; i += kFe2Threads) ssmp[i] = i < need ? __ldg(yrow + reflect_index(s0 + i, p.T)) : 0.0f;
+    for (int i = tid; i < q.nsmp; i += kFe2Threads) {  // element-wise, still asynchronous
+      if (i < need) cp_async4(ssmp + i, yrow + reflect_index(s0 + i, p.T));
+      else ssmp[i] = 0.0f;
+    }
   }
 }
 
@@ -766,6 +773,118 @@ __global__ void __launch_bounds__(256) mel_overlap_add_kernel(const float* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Inverse STFT at n_fft = 1024, the head of the reference's T-F vocoders (Models/apnet.py:155, freeV.py:178,
+// bsrnn.py:210: torch.istft(spec, n_fft, hop, win, window=hann, center=True)):
+//   frame f:  s_f = irfft(spec[:, :, f]) (1/N scaling, imaginary parts of bins 0 and N/2 ignored),  * window
+//   y[t]   =  sum_f s_f[t + N/2 - f hop] / sum_f window[t + N/2 - f hop]^2,   t in [0, hop (F - 1))
+// Kernel 1: a CTA of 4 warps takes 8 consecutive frames; the [513 x 8] tile of the two planes is staged in shared
+// memory (frames are the fastest axis of [B, 513, F], so 8 consecutive lanes read 32 contiguous bytes), each warp
+// turns ONE frame pair into one packed 1024-point transform -- Z = A + i B with A, B the Hermitian extensions of the
+// two spectra, s_a + i s_b = conj(FFT(conj Z)) / N -- and writes the two windowed frames to a scratch [B, F, 1024].
+// Kernel 2 gathers the (at most ceil(N / hop)) overlapping frames of every output sample in frame order and divides
+// by the window envelope: bit-reproducible, no atomics.
+// ------------------------------------------------------------------------------------------------
+struct IstftParams {
+  const float* re;     // [B, 513, F]
+  const float* im;
+  int64_t B, F;
+  int hop;
+  const float* window;    // [1024]
+  const float2* twiddle;  // forward twiddles of fft1024_warp
+  float* frames;          // scratch [B, F, 1024]
+  float* out;             // [B, hop * (F - 1)]
+};
+
+constexpr int kIsWarps = 4, kIsFrames = 2 * kIsWarps;
+
+__global__ void __launch_bounds__(kIsWarps * 32) istft1024_frames_kernel(const IstftParams q) {
+  extern __shared__ __align__(16) float smem[];
+  float* tre = smem;                       // [513][8]
+  float* tim = tre + kBins * kIsFrames;    // [513][8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sre = tim + kBins * kIsFrames + warp * kWarpSmemFloats;
+  float* sim = sre + 32 * kTransposeStride;
+  const int64_t groups = (q.F + kIsFrames - 1) / kIsFrames;
+  const int64_t b = blockIdx.x / groups;
+  const int64_t f0 = (blockIdx.x - b * groups) * kIsFrames;
+  const int nf = (int)((q.F - f0) < kIsFrames ? (q.F - f0) : kIsFrames);
+  const float* __restrict__ gre = q.re + b * kBins * q.F + f0;
+  const float* __restrict__ gim = q.im + b * kBins * q.F + f0;
+  for (int e = tid; e < kBins * kIsFrames; e += kIsWarps * 32) {
+    const int k = e >> 3, j = e & 7;
+    const bool in = j < nf;
+    tre[e] = in ? __ldg(gre + (int64_t)k * q.F + j) : 0.0f;
+    tim[e] = in ? __ldg(gim + (int64_t)k * q.F + j) : 0.0f;
+  }
+  __syncthreads();
+  const int fa = 2 * warp;
+  if (fa >= nf) return;
+  const bool has_b = fa + 1 < nf;
+
+  // input of the forward FFT: conj(Z[k]) at index k = lane + 32 m in register m
+  float re[32], im[32];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {  // k <= 511:  Z = A[k] + i B[k] = (Ar - Bi) + i (Ai + Br)
+    const int k = lane + 32 * m;
+    const float2 r = *reinterpret_cast<const float2*>(tre + k * kIsFrames + fa);  // (Ar, Br)
+    const float2 i = *reinterpret_cast<const float2*>(tim + k * kIsFrames + fa);  // (Ai, Bi)
+    if (m == 0 && lane == 0) {  // DC: the imaginary parts are ignored (C2R)
+      re[m] = r.x;
+      im[m] = -r.y;
+    } else {
+      re[m] = r.x - i.y;
+      im[m] = -(i.x + r.y);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m < 32; ++m) {  // k >= 512:  Z = conj A[N-k] + i conj B[N-k] = (Ar + Bi) + i (Br - Ai)
+    const int kk = kNfft - (lane + 32 * m);  // 1 .. 512
+    const float2 r = *reinterpret_cast<const float2*>(tre + kk * kIsFrames + fa);
+    const float2 i = *reinterpret_cast<const float2*>(tim + kk * kIsFrames + fa);
+    if (m == 16 && lane == 0) {  // Nyquist: real
+      re[m] = r.x;
+      im[m] = -r.y;
+    } else {
+      re[m] = r.x + i.y;
+      im[m] = -(r.y - i.x);
+    }
+  }
+  fft1024_warp(re, im, sre, sim, q.twiddle, lane);  // X[n], n = lane + 32 k2, at register brev5(k2);  s_a + i s_b = conj(X) / N
+
+  float* fo = q.frames + (b * q.F + f0 + fa) * kNfft;
+  constexpr float inv_n = 1.0f / (float)kNfft;
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) {
+    const int n = lane + 32 * k2;
+    const float w = __ldg(q.window + n) * inv_n;
+    fo[n] = w * re[brev5(k2)];
+    if (has_b) fo[kNfft + n] = -w * im[brev5(k2)];
+  }
+}
+
+__global__ void __launch_bounds__(256) istft1024_ola_kernel(const IstftParams q, int64_t Tout) {
+  const int64_t n = q.B * Tout;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = e / Tout, t = e - b * Tout;
+    const int64_t pos = t + kNfft / 2;  // position in the un-trimmed overlap-add buffer
+    int64_t f_lo = (pos - (kNfft - 1) + q.hop - 1) / q.hop;
+    if (pos - (kNfft - 1) < 0) f_lo = 0;
+    int64_t f_hi = pos / q.hop;
+    if (f_hi > q.F - 1) f_hi = q.F - 1;
+    const float* fb = q.frames + b * q.F * kNfft;
+    float acc = 0.0f, env = 0.0f;
+    for (int64_t f = f_lo; f <= f_hi; ++f) {
+      const int64_t i = pos - f * q.hop;
+      const float w = __ldg(q.window + i);
+      acc += fb[f * kNfft + i];
+      env = fmaf(w, w, env);
+    }
+    q.out[e] = acc / env;
+  }
+}
+
 }  // namespace
 
 }  // namespace nvse
@@ -1067,5 +1186,44 @@ extern "C" int nvse_inverse_mel_f32(const float* inv_basis, const float* mel, fl
                  4.0 * (double)B * frames * (n_bins + n_mels), as_stream(stream));
   inverse_mel_kernel<<<grid, 256, 0, as_stream(stream)>>>(inv_basis, mel, out, n_bins, n_mels, frames);
   NVSE_LAUNCH_CHECK("inverse_mel_kernel");
+  return NVSE_OK;
+}
+
+
+extern "C" size_t nvse_frontend_istft_scratch_bytes(const nvse_frontend* fe, int64_t B, int64_t frames) {
+  if (!fe || B < 0 || frames < 0) return 0;
+  return (size_t)B * (size_t)frames * nvse::kNfft * sizeof(float) + 256;
+}
+
+extern "C" int nvse_frontend_istft_f32(const nvse_frontend* fe, const float* real, const float* imag, int64_t B, int64_t frames,
+                                       float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace nvse;
+  NVSE_REQUIRE(fe && real && imag && out && scratch, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: null argument");
+  NVSE_REQUIRE(B >= 0 && frames >= 1, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
+  NVSE_REQUIRE(fe->hop <= kNfft, NVSE_ERR_UNSUPPORTED, "nvse_frontend_istft_f32: hop %d > n_fft leaves gaps (torch.istft rejects it: zero envelope)", fe->hop);
+  NVSE_REQUIRE(scratch_bytes >= nvse_frontend_istft_scratch_bytes(fe, B, frames), NVSE_ERR_INVALID, "nvse_frontend_istft_f32: scratch too small");
+  const int64_t Tout = (int64_t)fe->hop * (frames - 1);
+  if (B == 0 || Tout == 0) return NVSE_OK;
+  cudaStream_t st = as_stream(stream);
+  IstftParams q;
+  q.re = real; q.im = imag; q.B = B; q.F = frames; q.hop = fe->hop;
+  q.window = fe->window; q.twiddle = fe->twiddle;
+  q.frames = reinterpret_cast<float*>((reinterpret_cast<size_t>(scratch) + 255) / 256 * 256);
+  q.out = out;
+  const int64_t ctas = B * ((frames + kIsFrames - 1) / kIsFrames);
+  NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: problem too large for one launch");
+  const size_t smem = sizeof(float) * (2 * (size_t)kBins * kIsFrames + (size_t)kIsWarps * kWarpSmemFloats);
+  NVSE_CUDA_CHECK(cudaFuncSetAttribute(istft1024_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope prof("istft1024_frames", 513, 1, 0.0, 8.0 * (double)B * kBins * (double)frames + 4.0 * (double)B * (double)frames * kNfft, st);
+    istft1024_frames_kernel<<<(unsigned)ctas, kIsWarps * 32, smem, st>>>(q);
+    NVSE_LAUNCH_CHECK("istft1024_frames_kernel");
+  }
+  {
+    ProfScope prof("istft1024_ola", 1, 1, 0.0, 4.0 * (double)B * (double)Tout * (1.0 + (double)kNfft / fe->hop), st);
+    const unsigned grid = (unsigned)std::min<int64_t>((B * Tout + 255) / 256, 148 * 16);
+    istft1024_ola_kernel<<<grid, 256, 0, st>>>(q, Tout);
+    NVSE_LAUNCH_CHECK("istft1024_ola_kernel");
+  }
   return NVSE_OK;
 }

@@ -175,6 +175,46 @@ def amp_pha_specturm(y, n_fft, hop_size, win_size):
     return tuple(o if o.device == y.device else o.to(y.device) for o in outs)
 
 
+def istft(spec, n_fft, hop_length=None, win_length=None, window=None, center=True):
+    """The inverse STFT the reference's T-F vocoders end in (Models/apnet.py:155, Models/freeV.py:178, Models/bsrnn.py:210):
+    ``torch.istft(spec, n_fft, hop_length=hop, win_length=win, window=torch.hann_window(win), center=True)`` for a
+    complex ``spec`` of shape ``[B, n_fft//2+1, F]`` (or ``[n_fft//2+1, F]``) -> ``[B, hop * (F - 1)]`` float32.
+    Same argument order as ``torch.istft``, so the call sites change one name.  n_fft = 1024 (this build's FFT size),
+    ``center=True`` only; ``window`` defaults to the periodic Hann window those call sites pass."""
+    if not center:
+        raise NotImplementedError("istft: the reference only calls torch.istft with center=True")
+    if not torch.is_complex(spec) or spec.dim() not in (2, 3):
+        raise RuntimeError(f"istft expects a complex [B, n_fft//2+1, F] or [n_fft//2+1, F] tensor, got {spec.dtype} {tuple(spec.shape)}")
+    hop_length = n_fft // 4 if hop_length is None else int(hop_length)
+    win_length = n_fft if win_length is None else int(win_length)
+    if spec.shape[-2] != n_fft // 2 + 1:
+        raise RuntimeError(f"istft: expected {n_fft // 2 + 1} frequency bins, got {spec.shape[-2]}")
+    dev = _cuda_device_for(spec)
+    win = torch.hann_window(win_length) if window is None else window.detach().to("cpu", torch.float32)
+    key = ("istft", n_fft, 1, hash(win.numpy().tobytes()), 0, win_length, hop_length, dev.index)
+    fe = _frontends.get(key)
+    if fe is None:  # a front-end handle without a mel basis: window + twiddles only
+        _frontend("istft", n_fft, 1, hop_length, win_length, hash(win.numpy().tobytes()), 0, torch.zeros(1, n_fft // 2 + 1), win, dev)
+        fe = _frontends[key]
+    squeeze = spec.dim() == 2
+    sd = spec.detach().to(dev)
+    if squeeze:
+        sd = sd.unsqueeze(0)
+    re = sd.real.to(torch.float32).contiguous()
+    im = sd.imag.to(torch.float32).contiguous()
+    batch, _, frames = re.shape
+    out = torch.empty((batch, hop_length * (frames - 1)), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    scratch = torch.empty(lib.nvse_frontend_istft_scratch_bytes(fe, batch, frames), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.nvse_frontend_istft_f32(fe, _lib.ptr(re), _lib.ptr(im), batch, frames, _lib.ptr(out), _lib.ptr(scratch),
+                                               scratch.numel(), stream))
+    if squeeze:
+        out = out[0]
+    return out if out.device == spec.device else out.to(spec.device)
+
+
 class _MelFn(torch.autograd.Function):
     """mel_spectrogram as an autograd node: the CUDA forward above, and the CUDA backward
     (nvse_frontend_mel_backward_f32: recomputed spectra -> d|X| -> packed inverse FFT -> overlap-add)."""

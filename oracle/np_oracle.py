@@ -128,6 +128,31 @@ def amp_pha_spectrum(y, n_fft, hop, win):
     return np.log(np.abs(spec) + 1e-7), np.arctan2(spec.imag, spec.real), spec.real, spec.imag
 
 
+def istft(spec, n_fft, hop, win):
+    """torch.istft(spec, n_fft, hop, win, window=hann_window(win), center=True) -- the head of the reference's T-F vocoders
+    (Models/apnet.py:155, Models/freeV.py:178, Models/bsrnn.py:210): per-frame irfft (1/n_fft), times the window,
+    overlap-add, divided by the overlap-added squared window, n_fft//2 samples trimmed on both sides -> ``[B, hop*(F-1)]``."""
+    spec = np.asarray(spec, dtype=np.complex128)
+    squeeze = spec.ndim == 2
+    if squeeze:
+        spec = spec[None]
+    window = hann_periodic(win)
+    if win < n_fft:
+        lp = (n_fft - win) // 2
+        window = np.pad(window, (lp, n_fft - win - lp))
+    B, _, F = spec.shape
+    frames = np.fft.irfft(spec.transpose(0, 2, 1), n=n_fft, axis=-1) * window  # [B, F, n_fft]
+    total = n_fft + hop * (F - 1)
+    y = np.zeros((B, total))
+    env = np.zeros(total)
+    for f in range(F):
+        y[:, f * hop:f * hop + n_fft] += frames[:, f]
+        env[f * hop:f * hop + n_fft] += window ** 2
+    lo, hi = n_fft // 2, n_fft // 2 + hop * (F - 1)
+    out = y[:, lo:hi] / env[lo:hi]
+    return out[0] if squeeze else out
+
+
 def inverse_mel(mel, inv_basis):
     """dataset.py:94-121: ``inv_basis @ exp(mel)`` with ``inv_basis = pinverse(mel_basis)`` supplied by the caller
     (the reference takes it from ``torch.Tensor.pinverse``; the checker does not re-derive a pseudo-inverse)."""
