@@ -140,6 +140,12 @@ NVSE_API size_t nvse_generator_workspace_bytes(const nvse_generator* g, int64_t 
  * fp32 residual stream, fp32 conv_pre / conv_post). */
 NVSE_API int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
                            void* workspace, size_t workspace_bytes, int precision, void* stream);
+/* The same forward with the waveform delivered as PCM_16 (int16 [B, out_samples]) instead of float: the quantisation of
+ * sf.write(..., 'PCM_16') (infers/inference_hifigan.py:93-95: round(x * 32767), clipped) fused into the last kernel
+ * where that kernel is conv_post of the tensor-core plan, one extra pass otherwise.  Bit-identical to
+ * nvse_pcm16_from_f32 applied to the output of nvse_generator_forward. */
+NVSE_API int nvse_generator_forward_pcm16(nvse_generator* g, const float* mel, int64_t B, int64_t frames, int16_t* out,
+                                 void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Layer-level entry points: the same kernels the generator launches, exposed so the

@@ -126,6 +126,15 @@ class _GeneratorBase(nn.Module):
             object.__setattr__(self, "_engine", GeneratorEngine(self, self._kind))
         return self._engine.forward(self, x)
 
+    @torch.no_grad()
+    def forward_pcm16(self, x):
+        """Inference straight to 16-bit PCM: what the reference's loop does with the waveform next (``sf.write(path,
+        audio, sr, 'PCM_16')``, infers/inference_hifigan.py:89-95), with the quantisation fused into the last kernel.
+        mel ``[B, 80, frames]`` -> int16 ``[B, samples]``."""
+        if self._engine is None:
+            object.__setattr__(self, "_engine", GeneratorEngine(self, self._kind))
+        return self._engine.forward(self, x, pcm16=True)
+
     def remove_weight_norm(self):
         print("Removing weight norm...")
         for up in self.ups:

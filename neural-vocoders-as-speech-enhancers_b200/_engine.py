@@ -202,12 +202,16 @@ class GeneratorEngine:
         self.weights_key, self._train_loaded = key, True  # the per-layer path builds the backward's copies lazily
 
     # ---- forward ---------------------------------------------------------------------
-    def forward(self, module, x, precision=None):
+    def forward(self, module, x, precision=None, pcm16=False):
+        """``pcm16=True`` (inference only): the waveform as int16 PCM, quantised like ``sf.write(..., 'PCM_16')``
+        (infers/inference_hifigan.py:93) inside the last kernel instead of float32."""
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters()))):
             # training step (train_time_wi_inv.py:173-236): forward with a tape + the CUDA backward, fp32 unless the
             # caller opted in to the tensor-core training path (resolve_train_precision)
+            if pcm16:
+                raise RuntimeError("PCM_16 output is an inference feature: call it under torch.no_grad() / module.eval()")
             return _GeneratorTrainFn.apply(self, module, x, *[p for _, p in module.named_parameters()])
         if x.is_cuda:
             dev = x.device
@@ -221,7 +225,7 @@ class GeneratorEngine:
         xd = x.detach().to(dev, torch.float32).contiguous()
         batch, _, frames = xd.shape
         n_out = lib.nvse_generator_out_samples(self.handle, frames)
-        out = torch.empty((batch, n_out), dtype=torch.float32, device=dev)
+        out = torch.empty((batch, n_out), dtype=torch.int16 if pcm16 else torch.float32, device=dev)
         if batch == 0 or frames == 0:
             return out.to(x.device)
         need = lib.nvse_generator_workspace_bytes(self.handle, batch, frames, prec)
@@ -230,8 +234,9 @@ class GeneratorEngine:
             self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(lib.nvse_generator_forward(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
-                                                  _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
+            fwd = lib.nvse_generator_forward_pcm16 if pcm16 else lib.nvse_generator_forward
+            _lib.check(fwd(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
+                           _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
         return out if x.is_cuda else out.to(x.device)
 
     # ---- training ---------------------------------------------------------------------

@@ -244,6 +244,11 @@ __global__ void __launch_bounds__(POST_ROWS) conv_post1_t32_kernel(const ConvF32
     acc += (p0 + p1) + (p2 + p3);
   }
   acc *= a.out_scale;
+  if (a.y_pcm16) {  // same arithmetic as pcm16_kernel (core.cu) on the float result
+    const float o = a.out_act == 1 ? tanhf(acc) : acc;
+    a.y_pcm16[b * a.y_bstride + t] = (int16_t)__float2int_rn(fminf(fmaxf(o * 32767.0f, -32768.0f), 32767.0f));
+    return;
+  }
   float* yr = a.y + b * a.y_bstride + t;
   if (a.accumulate) acc += *yr;
   *yr = a.out_act == 1 ? tanhf(acc) : acc;
@@ -299,6 +304,9 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
     NVSE_REQUIRE(a.in_stride <= 1, NVSE_ERR_UNSUPPORTED, "thin conv: strided input rows are not supported");
     NVSE_REQUIRE(max_off - min_off <= THIN_MAX_SPAN, NVSE_ERR_UNSUPPORTED, "thin conv: tap span %d too wide", max_off - min_off);
     const int span = max_off - min_off;
+    NVSE_REQUIRE(!a.y_pcm16 || (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && !a.accumulate && a.out_mul == 1 &&
+                                a.out_add == 0 && (a.Cin == 16 || a.Cin == 32 || a.Cin == 64)),
+                 NVSE_ERR_UNSUPPORTED, "fp32 conv: fused PCM_16 output is only implemented by the T32 conv_post kernel");
     if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 &&
         (a.Cin == 16 || a.Cin == 32 || a.Cin == 64)) {
       const size_t smem = sizeof(float) * ((size_t)(POST_ROWS + span) * (a.Cin + 4) + (size_t)a.taps.ntaps * a.Cin);

@@ -26,6 +26,8 @@ struct ConvF32Args {
   float out_scale;       // y = [accumulate ? y : 0] + out_scale * (conv + bias + residual)
   int accumulate;
   int out_act;           // 0 none, 1 tanh
+  int16_t* y_pcm16;      // when set (conv_post of the T32 path only): store round(y * 32767) clipped to int16 here INSTEAD of
+                         // y -- the PCM_16 quantisation of sf.write (infers/inference_hifigan.py:93) fused into the last kernel
   int x_t32;             // x is in the T32 layout (thin kernel only: conv_post of the tensor-core path)
   int reflect_left;      // x is viewed through ReflectionPad1d((reflect_left, 0)) (istftnet.py:296,312)
   // backward (grad.cu): a strided input row map and the leaky_relu derivative fused into the epilogue

@@ -42,6 +42,9 @@ struct KernelArgs {
   ConvTcArgs a;
   int nphase;                      // output phases sharing one staged activation tile (ConvTranspose1d); 1 for Conv1d
   int ph_per_cta;                  // phases one CTA computes (blockIdx.z selects the group): nphase, or fewer for small grids
+  int gsz;                         // phases per accumulator group: the phases of a group are adjacent output rows
+                                   // (out_mul * t + p, p + 1, ..), accumulate side by side in TMEM and are stored
+                                   // together, so that every store instruction pair fills whole 32-byte sectors
   ConvTaps ptaps[kMaxPhases];      // tap list of each phase
   int pout_add[kMaxPhases];        // output row = out_mul * t + pout_add[phase]
   int ntile;       // 128-row M tiles per CTA: every weight stage feeds ntile MMAs (weight reuse from smem)
@@ -76,12 +79,19 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)k.stages * stage_bytes);
   // barriers: full[kMaxStages], empty[kMaxStages], accum_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  // bias in shared memory: the epilogue adds it to every 16-column chunk, and a global load there sits on the critical
+  // path of each chunk (ncu, round 2: 21 % of all stall samples of the 256 -> 128 upsampler were that one FADD)
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
+  for (int c = tid; c < Cout; c += kThreads) bias_s[c] = a.bias ? __ldg(a.bias + c) : 0.0f;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
   const uint32_t bar_accum = smem_u32(bars + 2 * kMaxStages), bar_tfree = smem_u32(bars + 2 * kMaxStages + 2);
   const int ph_lo = (int)blockIdx.z * k.ph_per_cta;                                   // this CTA's phases
   const int ph_n = k.nphase - ph_lo < k.ph_per_cta ? k.nphase - ph_lo : k.ph_per_cta;
-  const int nbuf = k.ph_per_cta > 1 ? 2 : 1;  // TMEM accumulator double-buffering across phases
-  const uint32_t tmem_cols = (uint32_t)(Cout * nbuf * ntile) < 32u ? 32u : (uint32_t)(Cout * nbuf * ntile);  // power of two by construction
+  const int gsz = k.gsz;                                // phases per accumulator group
+  const int ngrp = (ph_n + gsz - 1) / gsz;              // groups this CTA computes
+  const int nbuf = k.ph_per_cta > gsz ? 2 : 1;          // TMEM accumulator double-buffering across groups
+  const int gcols = gsz * ntile * Cout;                 // TMEM columns of one group: [phase in group][tile][Cout]
+  const uint32_t tmem_cols = (uint32_t)(gcols * nbuf) < 32u ? 32u : (uint32_t)(gcols * nbuf);  // power of two by construction
 
   if (tid == 0) {
     for (int s = 0; s < k.stages; ++s) {
@@ -225,10 +235,10 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
       uint32_t s = 0, par = 0;
       for (int ph = 0; ph < ph_n; ++ph) {
         const ConvTaps& tp = k.ptaps[ph_lo + ph];
-        const int buf = ph & 1;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ntile * Cout);
-        if (ph >= 2) {  // the epilogue must have drained this accumulator (phase ph - 2)
-          if (!mbar_wait(bar_tfree + 8 * buf, ((ph >> 1) - 1) & 1)) goto mma_exit;
+        const int grp = ph / gsz, pq = ph - grp * gsz, buf = grp & 1;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * gcols + pq * ntile * Cout);
+        if (pq == 0 && grp >= 2) {  // the epilogue must have drained this accumulator (group grp - 2)
+          if (!mbar_wait(bar_tfree + 8 * buf, ((grp >> 1) - 1) & 1)) goto mma_exit;
           tc_fence_after();
         }
         uint32_t acc = 0u;
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
             if (++s == nstage) { s = 0; par ^= 1u; }
           }
         }
-        tc_commit(bar_accum + 8 * buf);  // accumulator of this phase complete -> epilogue
+        if (pq == gsz - 1 || ph == ph_n - 1) tc_commit(bar_accum + 8 * buf);  // accumulators of this group complete -> epilogue
       }
     mma_exit:;
     }
@@ -262,22 +272,25 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
     // ===== epilogue warps: TMEM -> registers -> global =====
     const int quarter = warp & 3, chalf = warp >> 2;  // TMEM lane quarter; which 16-column chunks (even / odd)
     const int row = quarter * 32 + lane;
-    for (int ph = 0; ph < ph_n; ++ph) {
-      const int buf = ph & 1;
-      if (!mbar_wait(bar_accum + 8 * buf, (ph >> 1) & 1)) break;
+    for (int grp = 0; grp < ngrp; ++grp) {
+      const int buf = grp & 1;
+      if (!mbar_wait(bar_accum + 8 * buf, (grp >> 1) & 1)) break;
       tc_fence_after();
+      const int gq = ph_n - grp * gsz < gsz ? ph_n - grp * gsz : gsz;  // phases in this group
      for (int j = 0; j < ntile; ++j) {
       const int t = t0 + j * kTileM + row;
-      const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph_lo + ph];
-      const bool valid = t < a.Trows && orow < a.Tout;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((buf * ntile + j) * Cout);
       for (int c0 = chalf * 16; c0 < Cout; c0 += 16 * (kEpiWarps / 4)) {
+       for (int pq = 0; pq < gq; ++pq) {  // adjacent output rows back to back: whole sectors
+        const int ph = grp * gsz + pq;
+        const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph_lo + ph];
+        const bool valid = t < a.Trows && orow < a.Tout;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * gcols + (pq * ntile + j) * Cout);
         uint32_t v[16];
         tmem_ld_32x16(t_addr + (uint32_t)c0, v);
         if (a.out_bf16) {
           float bq[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q);
+          for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = *(reinterpret_cast<const float4*>(bias_s + c0) + q);
           tmem_ld_wait();
           if (valid) {
             __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(a.y) + b * a.y_bstride + orow * Cout + c0;
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
           const float* rr = a.residual ? a.residual + yoff : nullptr;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            bq[q] = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bq[q] = *(reinterpret_cast<const float4*>(bias_s + c0) + q);
             rq[q] = (valid && rr) ? *reinterpret_cast<const float4*>(rr + qs * q) : make_float4(0.f, 0.f, 0.f, 0.f);
             yq[q] = (valid && a.accumulate) ? *reinterpret_cast<const float4*>(yr + qs * q) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -328,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
             }
           }
         }
+       }
       }
      }
       if (nbuf > 1) {  // hand the accumulator back to the MMA issuer
@@ -367,7 +381,7 @@ int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int C
 }
 
 static constexpr size_t kSmemBudget = 224 * 1024;  // of the 227 KB a CTA may opt in to
-static constexpr size_t kSmemTail = sizeof(uint64_t) * (2 * kMaxStages + 4) + 16;
+static constexpr size_t kSmemTail = sizeof(uint64_t) * (2 * kMaxStages + 4) + 16 + 256 * sizeof(float);  // barriers, TMEM slot, bias
 
 static size_t tc_smem_bytes_rows(int Cin, int Cout, int rows, bool split, int stages) {
   const int rows_pad = rows | 1;
@@ -398,6 +412,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   k.a = a;
   k.nphase = nphase;
   k.ph_per_cta = nphase;
+  k.gsz = 1;
   int mn = phase_taps[0].off[0], mx = mn, total_taps = 0;
   for (int p = 0; p < nphase; ++p) {
     NVSE_REQUIRE(phase_taps[p].ntaps >= 1 && phase_taps[p].ntaps <= kMaxTaps, NVSE_ERR_INVALID, "tensor-core conv: bad tap count");
@@ -412,7 +427,19 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   k.min_off = mn;
   // M tiles per CTA: weight bytes streamed per FLOP fall as 1/ntile (L2 -> smem weight traffic is what
   // bounds the 128-row tile at C >= 128), and per-CTA fixed costs are amortised for the small-C layers.
-  const int nbuf = nphase > 1 ? 2 : 1;
+  // Phases per accumulator group (see KernelArgs::gsz): consecutive output rows stored together.  Two where the
+  // phases come in consecutive-row order (ConvTranspose1d polyphase launches) and two accumulators of 2 * Cout
+  // columns still fit TMEM next to each other (double buffering) -- or the launch only HAS two phases.
+  static const int gsz_env = [] { const char* e = std::getenv("NVSE_TC_GSZ"); return e ? std::atoi(e) : 0; }();
+  int gsz = 1;
+  if (nphase >= 2 && !a.out_bf16) {
+    bool consecutive = true;
+    for (int p = 1; p < nphase; ++p) consecutive = consecutive && phase_out_add[p] == phase_out_add[p - 1] + 1;
+    const int want_g = gsz_env > 0 ? gsz_env : 2;
+    if (consecutive && nphase % want_g == 0 && a.Cout * want_g * (nphase > want_g ? 2 : 1) <= 512) gsz = want_g;
+  }
+  k.gsz = gsz;
+  const int nbuf = nphase > gsz ? 2 : 1;
   int ntile = 1;
   {
     static const int forced = [] { const char* e = std::getenv("NVSE_TC_NTILE"); return e ? std::atoi(e) : 0; }();
@@ -420,7 +447,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
     // several CTAs resident per SM (TMEM columns = Cout * 2 * ntile), which hides the staging latency
     const int want = forced > 0 ? forced : (nphase > 1 ? (a.Cout >= 64 ? 1 : 2) : (a.Cout >= 128 ? 2 : 4));
     const int64_t tiles_needed = ((int64_t)a.Trows + kTileM - 1) / kTileM;
-    while (ntile * 2 <= want && a.Cout * nbuf * ntile * 2 <= 512 && ntile * 2 <= tiles_needed &&
+    while (ntile * 2 <= want && a.Cout * gsz * nbuf * ntile * 2 <= 512 && ntile * 2 <= tiles_needed &&
            tc_smem_bytes_rows(a.Cin, a.Cout, kTileM * ntile * 2 + (mx - mn), a.split_act != 0, 2) <= kSmemBudget)
       ntile *= 2;
   }
@@ -449,6 +476,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   const int sm_count = device_sm_count();
   if (nphase > 1 && (int64_t)grid.x * grid.y * nphase <= 2 * sm_count) {
     k.ph_per_cta = 1;
+    k.gsz = 1;
     grid.z = (unsigned)nphase;
   }
   const double rows = (double)B * a.Trows;

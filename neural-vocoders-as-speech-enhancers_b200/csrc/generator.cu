@@ -169,8 +169,10 @@ int ensure_side_streams(nvse_generator* g) {
   return NVSE_OK;
 }
 
+// out_i16 != null: the waveform is wanted as PCM_16 (int16) INSTEAD of float: fused into conv_post where the last
+// kernel is the T32 conv_post kernel (HiFiGAN on the tensor-core plan), a separate quantisation pass otherwise.
 static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B, int64_t F, float* out, float* ws,
-                        int64_t buf_elems, int nbuf, cudaStream_t st) {
+                        int64_t buf_elems, int nbuf, cudaStream_t st, int16_t* out_i16 = nullptr) {
   const nvse_generator_config& c = g->cfg;
   float* bufA = ws;  // conv_pre output, then the MRF accumulator of every stage
   float* bufU = ws + buf_elems;
@@ -307,12 +309,25 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   a.out_mul = 1; a.out_add = 0; a.in_slope = 0.01f; a.out_scale = 1.0f;  // F.leaky_relu default slope, hifigan.py:120
   if (c.kind == NVSE_GEN_HIFIGAN) {  // hifigan.py:120-124
     a.Tin = a.Tout = a.Trows = (int)T; a.y = out; a.y_bstride = T * post.Cout; a.out_act = 1;
+    if (out_i16) {
+      if (t32 && post.Cout == 1 && (post.Cin == 16 || post.Cin == 32 || post.Cin == 64)) {
+        a.y_pcm16 = out_i16;  // PCM_16 straight out of the last kernel
+        return launch_conv_f32(a, B, st);
+      }
+      a.y = bufU;
+      if (int rc = launch_conv_f32(a, B, st)) return rc;
+      return launch_pcm16(bufU, out_i16, B * T * post.Cout, st);
+    }
     return launch_conv_f32(a, B, st);
   }
   // istftnet.py:311-318: lrelu(0.01) -> ReflectionPad1d((1,0)) -> conv_post -> exp / sin -> iSTFT
   a.reflect_left = 1;
   a.Tin = a.Tout = a.Trows = (int)T + 1; a.y = bufU; a.y_bstride = (T + 1) * post.Cout;
   if (int rc = launch_conv_f32(a, B, st)) return rc;
+  if (out_i16) {  // the iSTFT head writes float; quantise from a workspace buffer
+    if (int rc = launch_istft_head(bufU, bufR, B, T + 1, c.istft_n_fft, c.istft_hop, st)) return rc;
+    return launch_pcm16(bufR, out_i16, B * nvse_generator_out_samples(g, F), st);
+  }
   return launch_istft_head(bufU, out, B, T + 1, c.istft_n_fft, c.istft_hop, st);
 }
 
@@ -480,4 +495,21 @@ extern "C" int nvse_generator_forward(nvse_generator* g, const float* mel, int64
   float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, out, ws, buf_elems,
                       workspace_buffers(g, B, frames, precision), as_stream(stream));
+}
+
+extern "C" int nvse_generator_forward_pcm16(nvse_generator* g, const float* mel, int64_t B, int64_t frames, int16_t* out,
+                                            void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  NVSE_REQUIRE(g && mel && out, NVSE_ERR_INVALID, "nvse_generator_forward_pcm16: null argument");
+  NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_forward_pcm16: call nvse_generator_finalize first");
+  NVSE_REQUIRE(B >= 0 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_forward_pcm16: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
+  NVSE_REQUIRE(precision == NVSE_PRECISION_F32 || precision == NVSE_PRECISION_BF16, NVSE_ERR_INVALID, "bad precision %d", precision);
+  if (B == 0) return NVSE_OK;
+  if (int rc = tc_abort_poll(as_stream(stream))) return rc;
+  const size_t need = nvse_generator_workspace_bytes(g, B, frames, precision);
+  NVSE_REQUIRE(workspace && workspace_bytes >= need, NVSE_ERR_INVALID, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  NVSE_REQUIRE(max_activation_elems(g, frames) * 4 < (int64_t)1 << 40, NVSE_ERR_INVALID, "utterance too long");
+  const int64_t buf_elems = (int64_t)(align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256) / sizeof(float));
+  float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, nullptr, ws, buf_elems,
+                      workspace_buffers(g, B, frames, precision), as_stream(stream), out);
 }

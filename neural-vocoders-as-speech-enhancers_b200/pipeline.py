@@ -75,10 +75,11 @@ class Vocoder:
             nxt = upload(starts[i + 1]) if i + 1 < len(starts) else None
             cur.wait_event(ev)
             chunk.record_stream(cur)
-            y = self.generator(self.mel(chunk))
+            if pcm16:  # quantised inside the generator's last kernel: half the bytes cross PCIe, no extra pass
+                y = self.generator.forward_pcm16(self.mel(chunk))
+            else:
+                y = self.generator(self.mel(chunk))
             y = y.reshape(y.shape[0], -1)
-            if pcm16:  # quantise on the device: half the bytes cross PCIe
-                y = self.pcm16(y)
             if out_host is None:
                 out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=y.dtype, pin_memory=True)
             done = torch.cuda.Event()

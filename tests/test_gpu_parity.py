@@ -558,6 +558,26 @@ def test_pcm16_output_matches_libsndfile_rule():
     assert q.dtype == torch.int16 and np.array_equal(q.numpy(), np.rint(f.numpy() * np.float32(32767.0)).astype(np.int16))
 
 
+@pytest.mark.parametrize("cfg_name,precision", [("hifigan_v1", "bf16"), ("hifigan_v1", "fp32"), ("hifigan_small", "bf16"), ("istftnet", "bf16")])
+def test_forward_pcm16_is_the_quantised_forward(cfg_name, precision):
+    """nvse_generator_forward_pcm16 (PCM_16 fused into conv_post on the tensor-core plan of HiFiGAN, a separate pass on the
+    other plans) is bit-identical to quantising the float output of nvse_generator_forward (infers/inference_hifigan.py:89-95)."""
+    cfg = synth.CONFIGS[cfg_name]
+    gen = build_generator(cfg, synth.make_state(cfg, 8, "unit"), DEV, remove_wn=True)
+    gen.precision = precision
+    mel = torch.from_numpy(synth.make_mel(2, 37, 81)).to(DEV)
+    with torch.no_grad():
+        f = gen(mel)
+        q = gen.forward_pcm16(mel)
+    want = np.clip(np.rint(f.cpu().numpy() * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    assert q.dtype == torch.int16 and tuple(q.shape) == tuple(f.shape)
+    assert np.array_equal(q.cpu().numpy(), want)
+    assert len(np.unique(want)) > 100  # a full-scale signal, not a constant
+    with pytest.raises(RuntimeError, match="inference"):
+        gen.train()
+        gen._engine.forward(gen, mel.requires_grad_(True), pcm16=True)  # the training path has no PCM output
+
+
 def test_generator_forward_is_deterministic_under_repetition():
     """The mbarrier protocols of the fused kernels carry no data race: 20 back-to-back forwards of the same
     batch (cfg3 frame count, all three fused kernel families) are bit-identical and trip no bounded wait."""
