@@ -42,6 +42,16 @@ constexpr int kThreads = (kWorkWarps + 2) * 32;
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 constexpr int kNumBars = 2 * kMaxStages + 4;
+// N = 64: weight slices shared by the row tiles of a CTA go through the tensor core's B collector (tc_ptx.cuh)
+#ifndef NVSE_WS_B
+#define NVSE_WS_B 1
+#endif
+constexpr bool kWsB = NVSE_WS_B != 0;
+// ... but not in the pipelined kernel: same-box A/B (profiles/r02_ws_ab.txt) k = 7: 1.87 -> 2.01 ms, k = 11: 2.75 -> 2.90 ms WITH it
+#ifndef NVSE_WS_PIPE
+#define NVSE_WS_PIPE 0
+#endif
+constexpr bool kWsPipe = NVSE_WS_PIPE != 0;
 
 struct RbKernelArgs {
   ResblockTcArgs a;
@@ -206,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
                   for (int kk = 0; kk < kkn; ++kk) {
 #pragma unroll
                     for (int j = 0; j < n; ++j)
-                      tc_mma_bf16_lohi(d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi,
-                                       (H16 && half) ? idesc_f16 : idesc, acc);
+                      tc_mma_group<kWsB && C == 64, n>(j, d_tmem + (uint32_t)(j * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi,
+                                                       (H16 && half) ? idesc_f16 : idesc, acc);
                     acc = 1u;
                     a_lo += 2u * (uint32_t)k.rows_pad;
                     b_lo += 2u * (uint32_t)C;
@@ -546,15 +556,25 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         const uint32_t id = (H16 && c2) ? idesc_f16 : idesc;
         const uint32_t a_buf = (c2 ? a_lo_odd : a_lo_even) + (uint32_t)(k.P - (a.k - 1) / 2 * d);
         for (int hf = 0; hf < 2; ++hf) {
-          // S_l of this half's tiles and of the adjacent tile of the other half
-          const int j_lo = hf ? HN - 1 : 0, j_hi = hf ? n - 1 : HN;
+          // S_l of this half's tiles and of the adjacent tile of the other half.  Half A reads its right-hand
+          // neighbour (tile HN, the first tile of half B, whose epilogue only starts when conv l-1 on B is complete)
+          // through the taps with a positive row offset alone: that wait is deferred to the first such tap, so the
+          // taps with offsets <= 0 run under the neighbour's epilogue instead of after it.
+          const int j_lo = hf ? HN - 1 : 0, j_hi = hf ? n - 1 : HN - 1;
           for (int j = j_lo; j <= j_hi; ++j)
             if (!mbar_wait(bar_tile + 8 * j, (uint32_t)l & 1u)) goto mma_exit;
+          bool right_ready = hf != 0;
           tc_fence_after();
           RP_STAMP(0);
           uint32_t acc = c2 ? 1u : 0u;
           uint32_t a_tap = a_buf + (uint32_t)(hf * HN * kTileM);
           for (int tap = 0; tap < a.k; tap += TPS) {
+            if (!right_ready && tap + TPS - 1 > (a.k - 1) / 2) {
+              RP_STAMP(0);
+              if (!mbar_wait(bar_tile + 8 * HN, (uint32_t)l & 1u)) goto mma_exit;
+              right_ready = true;
+              RP_STAMP(0);
+            }
             if (!mbar_wait(bar_full + 8 * s, ph)) goto mma_exit;
             tc_fence_after();
             uint32_t b_lo = b_lo0 + s * stage_units;
@@ -566,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
                 for (int kk = 0; kk < kkn; ++kk) {
 #pragma unroll
                   for (int j = 0; j < HN; ++j)
-                    tc_mma_bf16_lohi(d_tmem + (uint32_t)((hf * HN + j) * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, id, acc);
+                    tc_mma_group<kWsPipe && C == 64, HN>(j, d_tmem + (uint32_t)((hf * HN + j) * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, id, acc);
                   acc = 1u;
                   a_lo += 2u * (uint32_t)k.rows_pad;
                   b_lo += 2u * (uint32_t)C;
@@ -577,6 +597,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
             tc_commit(bar_empty + 8 * s);
             if (++s == nstage) { s = 0; ph ^= 1u; }
           }
+          if (!right_ready && !mbar_wait(bar_tile + 8 * HN, (uint32_t)l & 1u)) goto mma_exit;  // (k = 1: no tap looks right)
           tc_commit(bar_accf + 8 * hf);
           RP_STAMP(0);
         }
@@ -697,6 +718,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
+            if (warp == 0) RP_STAMP(1);
           } else {
             // final: y = [y +] out_scale * (X + cb_last) for the central V rows
             const bool valid = r >= k.halo && r < R - k.halo && t < a.T;

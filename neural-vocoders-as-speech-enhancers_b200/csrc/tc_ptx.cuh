@@ -181,6 +181,35 @@ __device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo,
       : "memory");
 }
 
+// Weight-stationary form (tcgen05.mma.ws): the B tile is latched in collector buffer b0 by the first MMA of a group
+// (FILL), re-used by the following ones (USE) and released by the last (LAST), so that a (tap, k-step) weight slice
+// shared by the row tiles of a CTA is read from shared memory once.  Legal for N >= 64 only (N = 32 traps); measured
+// (tools/probe/mma_probe4.cu, profiles/r02_mma_probe4.txt): N = 64 48.1 -> 42.0 cycles per MMA over 4 tiles, 45.1 over 2;
+// a loss at N = 128 (64 -> 69).  Same accumulator layout as the plain form (lane = row).
+enum WsMode { kWsNone = 0, kWsFill = 1, kWsUse = 2, kWsLast = 3 };
+template <int MODE>
+__device__ __forceinline__ void tc_mma_ws_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+#define NVSE_WS_ASM(OPC)                                                                                                  \
+  asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n" \
+               OPC " [%0], da, db, %5, p;\n}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc),  \
+               "r"(accumulate) : "memory")
+  if (MODE == kWsFill) NVSE_WS_ASM("tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill");
+  else if (MODE == kWsUse) NVSE_WS_ASM("tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use");
+  else if (MODE == kWsLast) NVSE_WS_ASM("tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse");
+  else NVSE_WS_ASM("tcgen05.mma.cta_group::1.kind::f16");
+#undef NVSE_WS_ASM
+}
+// MMA number j of a group of NGRP that share one B tile (j is a constant after unrolling)
+template <bool WS, int NGRP>
+__device__ __forceinline__ void tc_mma_group(int j, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  if (!WS || NGRP < 2) tc_mma_ws_lohi<kWsNone>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else if (j == 0) tc_mma_ws_lohi<kWsFill>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else if (j == NGRP - 1) tc_mma_ws_lohi<kWsLast>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else tc_mma_ws_lohi<kWsUse>(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+
 // registers -> TMEM: thread i writes 16 consecutive fp32 columns of lane base+i
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
