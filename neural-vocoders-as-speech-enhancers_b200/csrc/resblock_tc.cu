@@ -64,6 +64,7 @@ struct RbKernelArgs {
   int rows_pad;  // operand buffer rows per 8-channel chunk (P + R + P)
   int stages, kc;
   int sm_count;
+  int ntx, nsets;    // persistent pipelined kernel: tile sets per utterance and in all
   long long* trace;  // debug: clock64 stamps of one CTA's phase boundaries (NVSE_RB_TRACE), else null
 };
 
@@ -441,9 +442,9 @@ done:
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Software-pipelined variant of the chain kernel (C <= 64, NT even): the NT tiles of a CTA are worked on as
-// two halves A and B.  The MMA thread issues conv l on A, then on B, then conv l+1 on A, ...; the epilogue of
-// (l, A) runs while the tensor core works on (l, B), the epilogue of (l, B) while it works on (l+1, A):
+// Software-pipelined, PERSISTENT variant of the chain kernel (C <= 64, NT even): the NT tiles of a tile set are
+// worked on as two halves A and B.  The MMA thread issues conv l on A, then on B, then conv l+1 on A, ...; the
+// epilogue of (l, A) runs while the tensor core works on (l, B), the epilogue of (l, B) while it works on (l+1, A):
 // except for the few rows of B that conv l+1 on A reads across the A/B boundary, the tensor core never waits
 // for an epilogue.  What that takes:
 //   * two operand buffers: the input S_l of conv l lives in OP[l & 1], its epilogue writes S_(l+1) into
@@ -452,6 +453,14 @@ done:
 //     neighbouring tile of the other half; one "accumulator ready" mbarrier per half;
 //   * the weights of every conv stream through the ring twice (once per half): L2 traffic x2, which at
 //     C <= 64 is ~20 B/clk/SM.
+// Persistent: a CTA walks tile sets first, first + gridDim.x, ... (consecutive CTAs take consecutive tile sets of an
+// utterance).  With X and ACC filling tensor memory there is one CTA per SM at C = 64, so nothing else would hide the
+// load / final phases (16 % of a k = 11 block, 22 % at k = 7: profiles/r02_pipe_trace.txt).  The epilogue warps
+// therefore bring in tile j of the NEXT tile set right after writing out tile j of this one -- half A under the MMAs
+// of the last conv on half B, half B under the next set's first MMAs -- with the global loads of the next tile issued
+// BEFORE the final phase of the current one, so that their (DRAM) latency passes under it.  Every resource such an
+// early load touches (the X columns and OP[0] rows of that tile) was last used before the tile's final accumulator
+// completed.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPipeBars = 2 * kMaxStages + 8 + 2;
 
@@ -466,10 +475,10 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   constexpr int TPS = C == 32 ? 4 : 2;  // taps per weight stage (nkc == 1 at C <= 64)
   static_assert(nkc == 1, "the pipelined kernel is for C <= 64");
   const int npairs = a.npairs, L = 2 * npairs;
-  const int64_t b = blockIdx.y;
   const int64_t bstride = a.bstride;
   const int ws4 = a.t32 ? 32 : 1;
-  const int t_in0 = (int)blockIdx.x * k.V - k.halo;
+  const int ntx = k.ntx;      // tile sets per utterance
+  const int nsets = k.nsets;  // tile sets in all (ntx * B)
   const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
   constexpr uint32_t tap_bytes = (uint32_t)KC * C * 2u, stage_bytes = TPS * tap_bytes;
   uint8_t* op0 = smem_raw;  // OP[0], OP[1]
@@ -516,26 +525,29 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_x = tmem_base, tmem_acc = tmem_base + (uint32_t)(n * C);
-  const bool tracing = k.trace != nullptr && blockIdx.x == 3 && blockIdx.y == gridDim.y / 2 && lane == 0;
+  const bool tracing = k.trace != nullptr && blockIdx.x == 3 && lane == 0;
   int tr_i = 0;
 #define RP_STAMP(role) do { if (tracing && tr_i < 60) k.trace[(role) * 64 + tr_i++] = clock64(); } while (0)
+  const int first = (int)blockIdx.x, step = (int)gridDim.x;
+  const int my_sets = first < nsets ? (nsets - first + step - 1) / step : 0;
 
   if (warp == kWorkWarps) {
-    // ===== weight producer: every conv's stages twice (half A, half B) =====
+    // ===== weight producer: every conv's stages twice (half A, half B), for every tile set of this CTA =====
     if (lane == 0) {
       const uint32_t nstage = (uint32_t)k.stages;
       uint32_t s = 0, ph = 1;
-      for (int l = 0; l < L; ++l) {
-        const __nv_bfloat16* wimg = (l & 1) ? a.pair[l >> 1].w2 : a.pair[l >> 1].w1;
-        for (int hf = 0; hf < 2; ++hf)
-          for (int st = 0; st < a.k; st += TPS) {
-            if (!mbar_wait(bar_empty + 8 * s, ph)) goto done;
-            const uint32_t cp_bytes = (uint32_t)min(TPS, a.k - st) * tap_bytes;
-            mbar_arrive_expect_tx(bar_full + 8 * s, cp_bytes);
-            bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (tap_bytes / 2), cp_bytes, bar_full + 8 * s);
-            if (++s == nstage) { s = 0; ph ^= 1u; }
-          }
-      }
+      for (int it = 0; it < my_sets; ++it)
+        for (int l = 0; l < L; ++l) {
+          const __nv_bfloat16* wimg = (l & 1) ? a.pair[l >> 1].w2 : a.pair[l >> 1].w1;
+          for (int hf = 0; hf < 2; ++hf)
+            for (int st = 0; st < a.k; st += TPS) {
+              if (!mbar_wait(bar_empty + 8 * s, ph)) goto done;
+              const uint32_t cp_bytes = (uint32_t)min(TPS, a.k - st) * tap_bytes;
+              mbar_arrive_expect_tx(bar_full + 8 * s, cp_bytes);
+              bulk_copy_g2s(smem_u32(wst + (size_t)s * stage_bytes), wimg + (size_t)st * (tap_bytes / 2), cp_bytes, bar_full + 8 * s);
+              if (++s == nstage) { s = 0; ph ^= 1u; }
+            }
+        }
     }
   } else if (warp == kWorkWarps + 1) {
     // ===== MMA issuer =====
@@ -549,59 +561,60 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
       constexpr uint32_t stage_units = stage_bytes >> 4;
       const uint32_t nstage = (uint32_t)k.stages;
       uint32_t s = 0, ph = 0;
-      for (int l = 0; l < L; ++l) {
-        const int c2 = l & 1;
-        const int d = c2 ? 1 : a.pair[l >> 1].dil;
-        const uint32_t d_tmem = c2 ? tmem_x : tmem_acc;
-        const uint32_t id = (H16 && c2) ? idesc_f16 : idesc;
-        const uint32_t a_buf = (c2 ? a_lo_odd : a_lo_even) + (uint32_t)(k.P - (a.k - 1) / 2 * d);
-        for (int hf = 0; hf < 2; ++hf) {
-          // S_l of this half's tiles and of the adjacent tile of the other half.  Half A reads its right-hand
-          // neighbour (tile HN, the first tile of half B, whose epilogue only starts when conv l-1 on B is complete)
-          // through the taps with a positive row offset alone: that wait is deferred to the first such tap, so the
-          // taps with offsets <= 0 run under the neighbour's epilogue instead of after it.
-          const int j_lo = hf ? HN - 1 : 0, j_hi = hf ? n - 1 : HN - 1;
-          for (int j = j_lo; j <= j_hi; ++j)
-            if (!mbar_wait(bar_tile + 8 * j, (uint32_t)l & 1u)) goto mma_exit;
-          bool right_ready = hf != 0;
-          tc_fence_after();
-          RP_STAMP(0);
-          uint32_t acc = c2 ? 1u : 0u;
-          uint32_t a_tap = a_buf + (uint32_t)(hf * HN * kTileM);
-          for (int tap = 0; tap < a.k; tap += TPS) {
-            if (!right_ready && tap + TPS - 1 > (a.k - 1) / 2) {
-              RP_STAMP(0);
-              if (!mbar_wait(bar_tile + 8 * HN, (uint32_t)l & 1u)) goto mma_exit;
-              right_ready = true;
-              RP_STAMP(0);
-            }
-            if (!mbar_wait(bar_full + 8 * s, ph)) goto mma_exit;
+      uint32_t tphase = 0;  // phase of the tile / accumulator barriers: one per conv, L per tile set
+      for (int it = 0; it < my_sets; ++it)
+        for (int l = 0; l < L; ++l, ++tphase) {
+          const int c2 = l & 1;
+          const int d = c2 ? 1 : a.pair[l >> 1].dil;
+          const uint32_t d_tmem = c2 ? tmem_x : tmem_acc;
+          const uint32_t id = (H16 && c2) ? idesc_f16 : idesc;
+          const uint32_t a_buf = (c2 ? a_lo_odd : a_lo_even) + (uint32_t)(k.P - (a.k - 1) / 2 * d);
+          for (int hf = 0; hf < 2; ++hf) {
+            // S_l of this half's tiles and of the adjacent tile of the other half.  Half A reads its right-hand
+            // neighbour (tile HN, the first tile of half B, whose epilogue only starts when conv l-1 on B is complete)
+            // through the taps with a positive row offset alone: that wait is deferred to the first such tap, so the
+            // taps with offsets <= 0 run under the neighbour's epilogue instead of after it.
+            const int j_lo = hf ? HN - 1 : 0, j_hi = hf ? n - 1 : HN - 1;
+            for (int j = j_lo; j <= j_hi; ++j)
+              if (!mbar_wait(bar_tile + 8 * j, tphase & 1u)) goto mma_exit;
+            bool right_ready = hf != 0;
             tc_fence_after();
-            uint32_t b_lo = b_lo0 + s * stage_units;
-#pragma unroll
-            for (int tt = 0; tt < TPS; ++tt) {
-              if (tap + tt < a.k) {
-                uint32_t a_lo = a_tap;
-#pragma unroll
-                for (int kk = 0; kk < kkn; ++kk) {
-#pragma unroll
-                  for (int j = 0; j < HN; ++j)
-                    tc_mma_group<kWsPipe && C == 64, HN>(j, d_tmem + (uint32_t)((hf * HN + j) * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, id, acc);
-                  acc = 1u;
-                  a_lo += 2u * (uint32_t)k.rows_pad;
-                  b_lo += 2u * (uint32_t)C;
-                }
-                a_tap += (uint32_t)d;
+            RP_STAMP(0);
+            uint32_t acc = c2 ? 1u : 0u;
+            uint32_t a_tap = a_buf + (uint32_t)(hf * HN * kTileM);
+            for (int tap = 0; tap < a.k; tap += TPS) {
+              if (!right_ready && tap + TPS - 1 > (a.k - 1) / 2) {
+                if (!mbar_wait(bar_tile + 8 * HN, tphase & 1u)) goto mma_exit;
+                tc_fence_after();
+                right_ready = true;
               }
+              if (!mbar_wait(bar_full + 8 * s, ph)) goto mma_exit;
+              tc_fence_after();
+              uint32_t b_lo = b_lo0 + s * stage_units;
+#pragma unroll
+              for (int tt = 0; tt < TPS; ++tt) {
+                if (tap + tt < a.k) {
+                  uint32_t a_lo = a_tap;
+#pragma unroll
+                  for (int kk = 0; kk < kkn; ++kk) {
+#pragma unroll
+                    for (int j = 0; j < HN; ++j)
+                      tc_mma_group<kWsPipe && C == 64, HN>(j, d_tmem + (uint32_t)((hf * HN + j) * C), a_lo + (uint32_t)(j * kTileM), hi, b_lo, hi, id, acc);
+                    acc = 1u;
+                    a_lo += 2u * (uint32_t)k.rows_pad;
+                    b_lo += 2u * (uint32_t)C;
+                  }
+                  a_tap += (uint32_t)d;
+                }
+              }
+              tc_commit(bar_empty + 8 * s);
+              if (++s == nstage) { s = 0; ph ^= 1u; }
             }
-            tc_commit(bar_empty + 8 * s);
-            if (++s == nstage) { s = 0; ph ^= 1u; }
+            if (!right_ready && !mbar_wait(bar_tile + 8 * HN, tphase & 1u)) goto mma_exit;  // (k = 1: no tap looks right)
+            tc_commit(bar_accf + 8 * hf);
+            RP_STAMP(0);
           }
-          if (!right_ready && !mbar_wait(bar_tile + 8 * HN, (uint32_t)l & 1u)) goto mma_exit;  // (k = 1: no tap looks right)
-          tc_commit(bar_accf + 8 * hf);
-          RP_STAMP(0);
         }
-      }
     mma_exit:;
     }
     __syncwarp();
@@ -612,145 +625,185 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     const float slope = a.slope;
     constexpr int CPW = C / 32;  // 16-column chunks per warp and tile
     if (warp == 0) RP_STAMP(1);
-    // Rows just outside the tile that the FIRST conv reads: real data (zero outside the sequence) instead of
-    // stale rows -- the first conv is then valid on the whole tile and the chain's halo excludes its padding.
-    {
-      const int n2 = 2 * k.P0;
-      for (int e = (warp * 32 + lane); e < n2 * nchunk; e += kWorkWarps * 32) {
-        const int chunk = e / n2, i = e - chunk * n2;
-        const int orow = i < k.P0 ? k.P - k.P0 + i : k.P + R + (i - k.P0);  // operand-buffer row
-        const int t = t_in0 + orow - k.P;
-        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && t < a.T) {
-          const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, chunk * 8, C) : (int64_t)t * C + chunk * 8));
-          const float4 f0 = __ldg(src), f1 = __ldg(src + ws4);
-          pk.x = pack_bf16(lrelu(f0.x, slope), lrelu(f0.y, slope));
-          pk.y = pack_bf16(lrelu(f0.z, slope), lrelu(f0.w, slope));
-          pk.z = pack_bf16(lrelu(f1.x, slope), lrelu(f1.y, slope));
-          pk.w = pack_bf16(lrelu(f1.z, slope), lrelu(f1.w, slope));
-        }
-        *reinterpret_cast<uint4*>(op0 + ((size_t)chunk * k.rows_pad + orow) * 16) = pk;
+    // Tile jt of tile set `set`, in two steps so that the latency of the global loads can pass under other work:
+    //   load_issue:  this thread's row of x -> registers
+    //   load_commit: registers -> X (TMEM, fp32) and S_0 = bf16(lrelu(x)) -> OP[0], one "tile written" arrival; with the
+    //                first / last tile also the P0 rows just outside the tile set that the FIRST conv reads (real data,
+    //                zero outside the sequence, instead of stale rows: the first conv is then valid on the whole tile
+    //                set and the chain's halo excludes its padding).
+    auto load_issue = [&](int set, int jt, float4 (&v)[CPW][4]) {
+      const int64_t b = set / ntx;
+      const int t = (set - (int)b * ntx) * k.V - k.halo + jt * kTileM + q * 32 + lane;
+      const bool inb = t >= 0 && t < a.T;
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int c0 = (ci * 2 + h) * 16;
+        const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v[ci][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    }
-    // load, two tiles' worth of global loads in flight, one "tile written" arrival per tile:
-    // x -> X (TMEM, fp32) and S_0 = bf16(lrelu(x)) -> OP[0]
-#pragma unroll
-    for (int jt0 = 0; jt0 < n; jt0 += 2) {
-      float4 v[2][CPW][4];
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int t = t_in0 + (jt0 + jj) * kTileM + q * 32 + lane;
-        const bool inb = t >= 0 && t < a.T;
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) {
-          const int c0 = (ci * 2 + h) * 16;
-          const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
-#pragma unroll
-          for (int w = 0; w < 4; ++w) v[jj][ci][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int jt = jt0 + jj;
-        const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
-        const bool inb = t >= 0 && t < a.T;
-#pragma unroll
-        for (int ci = 0; ci < CPW; ++ci) {
-          const int c0 = (ci * 2 + h) * 16;
-          float f[16];
-          uint32_t bits[16];
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            f[4 * w] = v[jj][ci][w].x; f[4 * w + 1] = v[jj][ci][w].y; f[4 * w + 2] = v[jj][ci][w].z; f[4 * w + 3] = v[jj][ci][w].w;
+    };
+    auto load_commit = [&](int set, int jt, const float4 (&v)[CPW][4]) {
+      const int64_t b = set / ntx;
+      const int t_in0 = (set - (int)b * ntx) * k.V - k.halo;
+      if (jt == 0 || jt == n - 1) {
+        const float* xb = a.x + b * bstride;
+        for (int e = (warp * 32 + lane); e < k.P0 * nchunk; e += kWorkWarps * 32) {
+          const int chunk = e / k.P0, i = e - chunk * k.P0;
+          const int orow = jt == 0 ? k.P - k.P0 + i : k.P + R + i;  // operand-buffer row
+          const int t = t_in0 + orow - k.P;
+          uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+          if (t >= 0 && t < a.T) {
+            const float4* src = reinterpret_cast<const float4*>(xb + (a.t32 ? t32_off(t, chunk * 8, C) : (int64_t)t * C + chunk * 8));
+            const float4 f0 = __ldg(src), f1 = __ldg(src + ws4);
+            pk.x = pack_bf16(lrelu(f0.x, slope), lrelu(f0.y, slope));
+            pk.y = pack_bf16(lrelu(f0.z, slope), lrelu(f0.w, slope));
+            pk.z = pack_bf16(lrelu(f1.x, slope), lrelu(f1.y, slope));
+            pk.w = pack_bf16(lrelu(f1.z, slope), lrelu(f1.w, slope));
           }
-#pragma unroll
-          for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
-          tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
-          store_operand<false>(op0, k.rows_pad, k.P + r, c0, f, slope, inb);
+          *reinterpret_cast<uint4*>(op0 + ((size_t)chunk * k.rows_pad + orow) * 16) = pk;
         }
-        tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
+      }
+      const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
+      const bool inb = t >= 0 && t < a.T;
+#pragma unroll
+      for (int ci = 0; ci < CPW; ++ci) {
+        const int c0 = (ci * 2 + h) * 16;
+        float f[16];
+        uint32_t bits[16];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          f[4 * w] = v[ci][w].x; f[4 * w + 1] = v[ci][w].y; f[4 * w + 2] = v[ci][w].z; f[4 * w + 3] = v[ci][w].w;
+        }
+#pragma unroll
+        for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
+        tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
+        store_operand<false>(op0, k.rows_pad, k.P + r, c0, f, slope, inb);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
+    };
+    // L2 prefetch of a half of a tile set (T32: one 128-byte line is 8 rows of a 4-channel group)
+    auto prefetch_half = [&](int set, int hf) {
+      if (!a.t32 || set >= nsets || (lane & 7) != 0) return;
+      const int64_t b = set / ntx;
+      const int t_in0 = (set - (int)b * ntx) * k.V - k.halo;
+#pragma unroll
+      for (int jj = 0; jj < HN; ++jj) {
+        const int t = t_in0 + (hf * HN + jj) * kTileM + q * 32 + lane;
+        if (t >= 0 && t < a.T) {
+#pragma unroll
+          for (int ci = 0; ci < CPW; ++ci) {
+            const float* src = a.x + b * bstride + t32_off(t, (ci * 2 + h) * 16, C);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + w * 128));
+          }
+        }
+      }
+    };
+
+    // first tile set: two tiles of loads in flight
+    if (my_sets > 0) {
+#pragma unroll
+      for (int jt0 = 0; jt0 < n; jt0 += 2) {
+        float4 v0[CPW][4], v1[CPW][4];
+        load_issue(first, jt0, v0);
+        load_issue(first, jt0 + 1, v1);
+        load_commit(first, jt0, v0);
+        load_commit(first, jt0 + 1, v1);
       }
     }
-
     if (warp == 0) RP_STAMP(1);
     bool alive = true;
-    for (int l = 0; l < L && alive; ++l) {
-      const int m = l >> 1, c2 = l & 1;
-      const bool last = (l == L - 1);
-      const float* bias = c2 ? bsm + (kRbMaxPairs + m) * C : bsm + m * C;  // cb_m for X, b1_m for ACC
-      const uint32_t src_tmem = c2 ? tmem_x : tmem_acc;
-      uint8_t* dst_op = op0 + (size_t)((l + 1) & 1) * op_bytes;
-      for (int hf = 0; hf < 2 && alive; ++hf) {
-        alive = mbar_wait_warp(bar_accf + 8 * hf, (uint32_t)l & 1u);
-        if (!alive) break;
-        tc_fence_after();
-        if (warp == 0) RP_STAMP(1);
+    uint32_t tphase = 0;
+    for (int it = 0; it < my_sets && alive; ++it) {
+      const int set = first + it * step, next = set + step;
+      const bool has_next = next < nsets;
+      const int64_t b = set / ntx;
+      const int t_in0 = (set - (int)b * ntx) * k.V - k.halo;
+      for (int l = 0; l < L && alive; ++l, ++tphase) {
+        const int m = l >> 1, c2 = l & 1;
+        const bool last = (l == L - 1);
+        const float* bias = c2 ? bsm + (kRbMaxPairs + m) * C : bsm + m * C;  // cb_m for X, b1_m for ACC
+        const uint32_t src_tmem = c2 ? tmem_x : tmem_acc;
+        uint8_t* dst_op = op0 + (size_t)((l + 1) & 1) * op_bytes;
+        for (int hf = 0; hf < 2 && alive; ++hf) {
+          if (l == 1) prefetch_half(next, hf);  // the next tile set's rows into L2 well before they are loaded
+          alive = mbar_wait_warp(bar_accf + 8 * hf, tphase & 1u);
+          if (!alive) break;
+          tc_fence_after();
+          if (warp == 0) RP_STAMP(1);
 #pragma unroll
-        for (int jj = 0; jj < HN; ++jj) {
-          const int jt = hf * HN + jj;
-          const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
-          if (!last) {
-            // S_(l+1) = bf16 / half (lrelu(acc + bias)), zero outside the sequence
-            uint32_t v[2][16];
-            tmem_ld_32x16(src_tmem + lane_sel + (uint32_t)(jt * C + h * 16), v[0]);
+          for (int jj = 0; jj < HN; ++jj) {
+            const int jt = hf * HN + jj;
+            const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
+            if (!last) {
+              // S_(l+1) = bf16 / half (lrelu(acc + bias)), zero outside the sequence
+              uint32_t v[2][16];
+              tmem_ld_32x16(src_tmem + lane_sel + (uint32_t)(jt * C + h * 16), v[0]);
 #pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) {
-              const int c0 = (ci * 2 + h) * 16;
-              tmem_ld_wait();
-              if (ci + 1 < CPW) tmem_ld_32x16(src_tmem + lane_sel + (uint32_t)(jt * C + ((ci + 1) * 2 + h) * 16), v[(ci + 1) & 1]);
-              float f[16];
+              for (int ci = 0; ci < CPW; ++ci) {
+                const int c0 = (ci * 2 + h) * 16;
+                tmem_ld_wait();
+                if (ci + 1 < CPW) tmem_ld_32x16(src_tmem + lane_sel + (uint32_t)(jt * C + ((ci + 1) * 2 + h) * 16), v[(ci + 1) & 1]);
+                float f[16];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * u);
-                f[4 * u] = __uint_as_float(v[ci & 1][4 * u]) + bq.x;
-                f[4 * u + 1] = __uint_as_float(v[ci & 1][4 * u + 1]) + bq.y;
-                f[4 * u + 2] = __uint_as_float(v[ci & 1][4 * u + 2]) + bq.z;
-                f[4 * u + 3] = __uint_as_float(v[ci & 1][4 * u + 3]) + bq.w;
+                for (int u = 0; u < 4; ++u) {
+                  const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * u);
+                  f[4 * u] = __uint_as_float(v[ci & 1][4 * u]) + bq.x;
+                  f[4 * u + 1] = __uint_as_float(v[ci & 1][4 * u + 1]) + bq.y;
+                  f[4 * u + 2] = __uint_as_float(v[ci & 1][4 * u + 2]) + bq.z;
+                  f[4 * u + 3] = __uint_as_float(v[ci & 1][4 * u + 3]) + bq.w;
+                }
+                if (c2) store_operand<false>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+                else store_operand<H16>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
               }
-              if (c2) store_operand<false>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
-              else store_operand<H16>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
-            if (warp == 0) RP_STAMP(1);
-          } else {
-            // final: y = [y +] out_scale * (X + cb_last) for the central V rows
-            const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
-            float4 yq[CPW][4];
+              fence_proxy_async_smem();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tile + 8 * jt);
+            } else {
+              // the same tile of this CTA's next tile set: loads go out now, are used after this tile is written out
+              float4 nx[CPW][4];
+              if (has_next) load_issue(next, jt, nx);
+              // final: y = [y +] out_scale * (X + cb_last) for the central V rows
+              const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+              float4 yq[CPW][4];
 #pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) {
-              const int c0 = (ci * 2 + h) * 16;
-              const float4* src = reinterpret_cast<const float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+              for (int ci = 0; ci < CPW; ++ci) {
+                const int c0 = (ci * 2 + h) * 16;
+                const float4* src = reinterpret_cast<const float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
 #pragma unroll
-              for (int w = 0; w < 4; ++w) yq[ci][w] = (valid && a.accumulate) ? src[w * ws4] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+                for (int w = 0; w < 4; ++w) yq[ci][w] = (valid && a.accumulate) ? src[w * ws4] : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
 #pragma unroll
-            for (int ci = 0; ci < CPW; ++ci) {
-              const int c0 = (ci * 2 + h) * 16;
-              uint32_t v[16];
-              tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), v);
-              tmem_ld_wait();
-              if (valid) {
-                float4* dst = reinterpret_cast<float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
+              for (int ci = 0; ci < CPW; ++ci) {
+                const int c0 = (ci * 2 + h) * 16;
+                uint32_t v[16];
+                tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), v);
+                tmem_ld_wait();
+                if (valid) {
+                  float4* dst = reinterpret_cast<float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * w);
-                  float4 o;
-                  o.x = (__uint_as_float(v[4 * w]) + bq.x) * a.out_scale + yq[ci][w].x;
-                  o.y = (__uint_as_float(v[4 * w + 1]) + bq.y) * a.out_scale + yq[ci][w].y;
-                  o.z = (__uint_as_float(v[4 * w + 2]) + bq.z) * a.out_scale + yq[ci][w].z;
-                  o.w = (__uint_as_float(v[4 * w + 3]) + bq.w) * a.out_scale + yq[ci][w].w;
-                  dst[w * ws4] = o;
+                  for (int w = 0; w < 4; ++w) {
+                    const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * w);
+                    float4 o;
+                    o.x = (__uint_as_float(v[4 * w]) + bq.x) * a.out_scale + yq[ci][w].x;
+                    o.y = (__uint_as_float(v[4 * w + 1]) + bq.y) * a.out_scale + yq[ci][w].y;
+                    o.z = (__uint_as_float(v[4 * w + 2]) + bq.z) * a.out_scale + yq[ci][w].z;
+                    o.w = (__uint_as_float(v[4 * w + 3]) + bq.w) * a.out_scale + yq[ci][w].w;
+                    dst[w * ws4] = o;
+                  }
                 }
               }
+              // this tile's X columns / OP[0] rows are free now
+              if (has_next) load_commit(next, jt, nx);
             }
           }
+          if (warp == 0) RP_STAMP(1);
         }
       }
     }
@@ -867,6 +920,14 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   k.sm_count = sm_count;
   k.ntile = p.ntile; k.halo = p.halo; k.V = p.V; k.P = p.P; k.P0 = p.P0; k.rows_pad = p.rows_pad; k.stages = p.stages; k.kc = p.kc;
   dim3 grid((unsigned)((a.T + p.V - 1) / p.V), (unsigned)B);
+  // persistent pipelined kernel: one CTA per resident slot, walking the tile sets with stride gridDim.x
+  k.ntx = (int)grid.x;
+  const int64_t nsets = (int64_t)grid.x * B;
+  NVSE_REQUIRE(nsets < (int64_t)1 << 30, NVSE_ERR_INVALID, "fused resblock: too many tiles");
+  k.nsets = (int)nsets;
+  static const int pipe_cap = [] { const char* e = std::getenv("NVSE_RB_PIPE_CTAS"); return e ? std::atoi(e) : 0; }();
+  const int slots = pipe_cap > 0 ? pipe_cap : sm_count * ((2 * p.ntile * a.C <= 256) ? 2 : 1);
+  dim3 pgrid((unsigned)std::min<int64_t>(nsets, slots));
   const double rows = (double)B * a.T;
   ProfScope prof("resblock_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0 * a.npairs,
                  rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
@@ -878,9 +939,9 @@ int launch_resblock_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
 #define RB_LAUNCH_PIPE(CC, NN, SP)                                                                                          \
   if (p.pipe && a.C == CC && p.ntile == NN && (a.h_fp16 != 0) == SP) {                                                      \
     NVSE_CUDA_CHECK(cudaFuncSetAttribute(resblock_pipe_kernel<CC, NN, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
-    resblock_pipe_kernel<CC, NN, SP><<<grid, kThreads, p.smem, st>>>(k);                                                    \
+    resblock_pipe_kernel<CC, NN, SP><<<pgrid, kThreads, p.smem, st>>>(k);                                                   \
   } else
-  RB_LAUNCH_PIPE(32, 4, false) RB_LAUNCH_PIPE(32, 4, true) RB_LAUNCH_PIPE(64, 4, false) RB_LAUNCH_PIPE(64, 4, true) RB_LAUNCH_PIPE(64, 2, false)
+  RB_LAUNCH_PIPE(32, 4, false) RB_LAUNCH_PIPE(32, 4, true) RB_LAUNCH_PIPE(64, 4, false) RB_LAUNCH_PIPE(64, 4, true)
   RB_LAUNCH(32, 4, false) RB_LAUNCH(32, 4, true) RB_LAUNCH(32, 8, false) RB_LAUNCH(64, 4, false) RB_LAUNCH(64, 4, true)
   RB_LAUNCH(64, 2, false) RB_LAUNCH(128, 2, false) RB_LAUNCH(128, 1, false) RB_LAUNCH(256, 1, false)
   return fail(NVSE_ERR_UNSUPPORTED, "fused resblock: no kernel for C=%d with %d tiles", a.C, p.ntile);
