@@ -39,6 +39,8 @@ struct ConvF32Args {
 int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st);
 int launch_repack_weight(const float* src, float* dst, int Cin, int Cout, int k, bool transposed, cudaStream_t st);
 int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st);
+// same with y rows padded to Rpad >= R entries (zero fill): x [B, R, C] -> y [B, C, Rpad]
+int launch_transpose_pad(const float* x, float* y, int64_t B, int64_t R, int64_t C, int64_t Rpad, cudaStream_t st);
 int launch_pcm16(const float* x, int16_t* y, int64_t n, cudaStream_t st);
 int launch_add3(float* a, const float* b, const float* c, int64_t n, cudaStream_t st);  // a = (a + b) + c
 // channels-last [B, T, C] <-> T32 layout (common.cuh)

@@ -53,6 +53,7 @@ struct KernelArgs {
   int rows_pad;    // rows rounded up to an odd count (conflict-free staging stores)
   int stages;      // weight ring depth
   int kc;          // channels per weight stage (min(Cin, 64))
+  int dbg;         // experiments: 1 = skip the epilogue's global stores, 2 = skip the activation staging loads
 };
 
 constexpr int kStageUnroll = 4;  // independent 32-byte loads in flight per thread while staging
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
         const int t = t0 + j * kTileM + q * 32 + lane;
         const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph_lo + ph];
         if (t < a.Trows && orow < a.Tout) {
-          const int64_t base = b * a.y_bstride + orow * Cout;
+          const int64_t base = b * a.y_bstride + orow * (a.y_ld ? a.y_ld : Cout);
           for (int c = half * 32; c < Cout; c += 64) {  // one 128-byte line per 32 fp32 channels
             if (a.residual) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residual + base + c));
             if (a.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float*>(a.y) + base + c));
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
           const int t = t0 + k.min_off + r;
           dst[u] = e < items ? (chunk * k.rows_pad + r) * 16 : -1;
           f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < items && t >= 0 && t < a.Tin) {
+          if (e < items && t >= 0 && t < a.Tin && !(k.dbg & 2)) {
             const float4* src = reinterpret_cast<const float4*>(xb + (a.x_t32 ? t32_off(t, chunk * 8, Cin) : (int64_t)t * Cin + chunk * 8));
             f0[u] = __ldg(src);
             f1[u] = __ldg(src + (a.x_t32 ? 32 : 1));
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
        for (int pq = 0; pq < gq; ++pq) {  // adjacent output rows back to back: whole sectors
         const int ph = grp * gsz + pq;
         const int64_t orow = (int64_t)a.out_mul * t + k.pout_add[ph_lo + ph];
-        const bool valid = t < a.Trows && orow < a.Tout;
+        const bool valid = t < a.Trows && orow < a.Tout && !(k.dbg & 1);
         const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * gcols + (pq * ntile + j) * Cout);
         uint32_t v[16];
         tmem_ld_32x16(t_addr + (uint32_t)c0, v);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
         } else {
           // issue every global load of this chunk before waiting on TMEM (latency overlap)
           float4 bq[4], rq[4], yq[4];
-          const int64_t yoff = b * a.y_bstride + (a.y_t32 ? t32_off(orow, c0, Cout) : orow * Cout + c0);
+          const int64_t yoff = b * a.y_bstride + (a.y_t32 ? t32_off(orow, c0, Cout) : orow * (a.y_ld ? a.y_ld : Cout) + c0);
           const int qs = a.y_t32 ? 128 : 4;  // floats between consecutive 4-channel groups of a row
           float* yr = reinterpret_cast<float*>(a.y) + yoff;
           const float* rr = a.residual ? a.residual + yoff : nullptr;
@@ -357,27 +358,36 @@ done:
   if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// fp32 [j][ci][co] -> bf16 [j][ci/KC][(ci%KC)/8][co][ci%8]
+// fp32 [j][ci][co] -> bf16 [j][ci/KC][(ci%KC)/8][co][ci%8]; the source may be wider (cout_src, first column co0) and have fewer
+// input channels (cin_src <= Cin: the rest of the image is zero)
 __global__ void __launch_bounds__(256) pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img,
-                                                              int Cin, int Cout, int ktaps, int kc, int as_fp16) {
+                                                              int Cin, int Cout, int ktaps, int kc, int as_fp16, int cin_src,
+                                                              int cout_src, int co0) {
   const int64_t n = (int64_t)Cin * Cout * ktaps;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int co = e % Cout, ci = (e / Cout) % Cin, j = e / ((int64_t)Cout * Cin);
     const int64_t dst = ((((int64_t)j * (Cin / kc) + ci / kc) * (kc / 8) + (ci % kc) / 8) * Cout + co) * 8 + (ci % 8);
-    if (as_fp16) reinterpret_cast<__half*>(img)[dst] = __float2half_rn(w[e]);  // same 16-bit slots, IEEE half
-    else img[dst] = __float2bfloat16_rn(w[e]);
+    const float v = ci < cin_src ? w[((int64_t)j * cin_src + ci) * cout_src + co0 + co] : 0.0f;
+    if (as_fp16) reinterpret_cast<__half*>(img)[dst] = __float2half_rn(v);  // same 16-bit slots, IEEE half
+    else img[dst] = __float2bfloat16_rn(v);
   }
 }
 
 }  // namespace
 
-int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int ktaps, cudaStream_t st, bool as_fp16) {
+int launch_pack_weight_tc_slice(const float* w_kio, int cin_src, int cout_src, int co0, __nv_bfloat16* img, int Cin, int Cout,
+                                int ktaps, cudaStream_t st, bool as_fp16) {
   NVSE_REQUIRE(tc_supported(Cin, Cout), NVSE_ERR_UNSUPPORTED, "tensor-core conv: Cin=%d / Cout=%d unsupported", Cin, Cout);
+  NVSE_REQUIRE(cin_src <= Cin && co0 >= 0 && co0 + Cout <= cout_src, NVSE_ERR_INVALID, "tensor-core conv: bad weight slice");
   const int64_t n = (int64_t)Cin * Cout * ktaps;
-  pack_weight_tc_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, st>>>(w_kio, img, Cin, Cout, ktaps,
-                                                                                            tc_kchunk(Cin), as_fp16 ? 1 : 0);
+  pack_weight_tc_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, st>>>(w_kio, img, Cin, Cout, ktaps, tc_kchunk(Cin),
+                                                                                            as_fp16 ? 1 : 0, cin_src, cout_src, co0);
   NVSE_LAUNCH_CHECK("pack_weight_tc_kernel");
   return NVSE_OK;
+}
+
+int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int ktaps, cudaStream_t st, bool as_fp16) {
+  return launch_pack_weight_tc_slice(w_kio, Cin, Cout, 0, img, Cin, Cout, ktaps, st, as_fp16);
 }
 
 static constexpr size_t kSmemBudget = 224 * 1024;  // of the 227 KB a CTA may opt in to
@@ -407,6 +417,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
   NVSE_REQUIRE(!(a.split_act && a.in_bf16), NVSE_ERR_INVALID, "tensor-core conv: split activations need fp32 input");
   NVSE_REQUIRE(!(a.x_t32 && a.in_bf16) && !(a.y_t32 && a.out_bf16), NVSE_ERR_INVALID, "tensor-core conv: the T32 layout is fp32 only");
   NVSE_REQUIRE(!(a.ops_f16 && (a.in_bf16 || a.split_act)), NVSE_ERR_INVALID, "tensor-core conv: half operands need fp32 input and no split");
+  NVSE_REQUIRE(!(a.y_ld && (a.y_t32 || a.out_bf16 || a.y_ld < a.Cout)), NVSE_ERR_INVALID, "tensor-core conv: a row pitch needs fp32 channels-last output");
   if (B == 0 || a.Trows <= 0) return NVSE_OK;
   KernelArgs k;
   k.a = a;
@@ -425,6 +436,8 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
     }
   }
   k.min_off = mn;
+  static const int dbg_env = [] { const char* e = std::getenv("NVSE_TC_DBG"); return e ? std::atoi(e) : 0; }();
+  k.dbg = dbg_env;
   // M tiles per CTA: weight bytes streamed per FLOP fall as 1/ntile (L2 -> smem weight traffic is what
   // bounds the 128-row tile at C >= 128), and per-CTA fixed costs are amortised for the small-C layers.
   // Phases per accumulator group (see KernelArgs::gsz): consecutive output rows stored together.  Two where the

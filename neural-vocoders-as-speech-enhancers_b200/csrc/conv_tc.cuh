@@ -31,6 +31,7 @@ struct ConvTcArgs {
   int Tout;
   int out_bf16;           // y = bf16(lrelu(conv + bias, out_slope))
   int y_t32;              // fp32 y (and residual) are in the T32 layout
+  int y_ld;               // fp32 channels-last y only: row pitch in elements (0 = Cout); y then points at this launch's first column
   ConvTaps taps;
   int out_mul, out_add, Trows;
   float in_slope, out_slope, out_scale;
@@ -55,5 +56,8 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
 // fp32 [k][Cin][Cout] (Layer::w layout) -> bf16 tensor-core image
 // as_fp16: IEEE half instead of bf16 in the same image layout (operands of the C = 32 c2 convs, resblock_tc.cu)
 int launch_pack_weight_tc(const float* w_kio, __nv_bfloat16* img, int Cin, int Cout, int k, cudaStream_t st, bool as_fp16 = false);
+// image of the [Cin x Cout] slice starting at output channel co0 of a [k][cin_src][cout_src] weight, input channels zero-padded to Cin
+int launch_pack_weight_tc_slice(const float* w_kio, int cin_src, int cout_src, int co0, __nv_bfloat16* img, int Cin, int Cout, int k,
+                                cudaStream_t st, bool as_fp16);
 
 }  // namespace nvse

@@ -97,15 +97,15 @@ __global__ void __launch_bounds__(256) weight_norm_fold_kernel(const float* __re
   for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) w[r * cols + c] = vr[c] * sc;
 }
 
-// y[b, j, i] = x[b, i, j] for x: [B, R, C]  (32x32 tiles through padded smem)
+// y[b, j, i] = x[b, i, j] for x: [B, R, C]  (32x32 tiles through padded smem); y rows have Rpad >= R entries, zero beyond R
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t R,
-                                                         int64_t C) {
+                                                         int64_t C, int64_t Rpad) {
   __shared__ float tile[32][33];
   const int64_t b = blockIdx.z;
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const float* xb = x + b * R * C;
-  float* yb = y + b * R * C;
+  float* yb = y + b * Rpad * C;
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int64_t r = r0 + ty + i, c = c0 + tx;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int64_t c = c0 + ty + i, r = r0 + tx;
-    if (r < R && c < C) yb[c * R + r] = tile[tx][ty + i];
+    if (r < Rpad && c < C) yb[c * Rpad + r] = tile[tx][ty + i];
   }
 }
 
@@ -186,14 +186,17 @@ int launch_pcm16(const float* x, int16_t* y, int64_t n, cudaStream_t st) {
   return NVSE_OK;
 }
 
-int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st) {
+int launch_transpose_pad(const float* x, float* y, int64_t B, int64_t R, int64_t C, int64_t Rpad, cudaStream_t st) {
   if (B == 0 || R == 0 || C == 0) return NVSE_OK;
-  NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "transpose: batch %lld exceeds 65535", (long long)B);
-  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
-  NVSE_REQUIRE((R + 31) / 32 <= 65535, NVSE_ERR_INVALID, "transpose: too many rows");
-  transpose_kernel<<<grid, 256, 0, st>>>(x, y, R, C);
+  NVSE_REQUIRE(B <= 65535 && Rpad >= R, NVSE_ERR_INVALID, "transpose: batch %lld exceeds 65535 or bad padding", (long long)B);
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((Rpad + 31) / 32), (unsigned)B);
+  NVSE_REQUIRE((Rpad + 31) / 32 <= 65535, NVSE_ERR_INVALID, "transpose: too many rows");
+  transpose_kernel<<<grid, 256, 0, st>>>(x, y, R, C, Rpad);
   NVSE_LAUNCH_CHECK("transpose_kernel");
   return NVSE_OK;
+}
+int launch_transpose(const float* x, float* y, int64_t B, int64_t R, int64_t C, cudaStream_t st) {
+  return launch_transpose_pad(x, y, B, R, C, R, st);
 }
 
 }  // namespace nvse

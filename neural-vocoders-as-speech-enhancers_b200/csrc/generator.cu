@@ -180,11 +180,29 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   float* bufT = ws + 3 * buf_elems;
   const float slope = 0.1f;  // LRELU_SLOPE, hifigan.py:7
 
-  // [B, 80, F] -> channels-last, then conv_pre (hifigan.py:109)
-  if (int rc = launch_transpose(mel, bufR, B, c.in_channels, F, st)) return rc;
+  // [B, 80, F] -> channels-last, then conv_pre (hifigan.py:109).  16-bit path: a tensor-core GEMM with IEEE-half operands
+  // (10 mantissa bits, like TF32: ~70 dB at this layer against the path's ~50 dB), the mel channels zero-padded to a
+  // supported K and the output channels in slices of <= 256; fp32 path: CUDA cores.
   {
-    const ConvIO io{bufR, false, nullptr, bufA, false, 1.0f, 1.0f, 1.0f, 0};
-    if (int rc = run_conv(g->layer("conv_pre"), false, io, B, F, st)) return rc;
+    const Layer& pre = g->layer("conv_pre");
+    static const bool pre_tc_env = [] { const char* e = std::getenv("NVSE_PRE_TC"); return !(e && e[0] == '0'); }();
+    if (tc && pre_tc_env && pre.pre_n > 0) {
+      if (int rc = launch_transpose_pad(mel, bufR, B, c.in_channels, F, pre.pre_cin, st)) return rc;
+      for (int sl = 0; sl < pre.pre_n; ++sl) {
+        ConvTcArgs a{};
+        a.x = bufR; a.x_bstride = F * pre.pre_cin; a.Tin = (int)F; a.Cin = pre.pre_cin; a.Cout = pre.pre_cout;
+        a.wimg = reinterpret_cast<const __nv_bfloat16*>(pre.w_pre[sl]); a.bias = pre.bias + sl * pre.pre_cout; a.ops_f16 = 1;
+        a.y = bufA + sl * pre.pre_cout; a.y_bstride = F * pre.Cout; a.y_ld = pre.Cout; a.Tout = (int)F;
+        conv1d_taps(pre.k, 1, &a.taps);
+        a.out_mul = 1; a.out_add = 0; a.Trows = (int)F;
+        a.in_slope = 1.0f; a.out_slope = 1.0f; a.out_scale = 1.0f;
+        if (int rc = launch_conv_tc(a, B, st)) return rc;
+      }
+    } else {
+      if (int rc = launch_transpose(mel, bufR, B, c.in_channels, F, st)) return rc;
+      const ConvIO io{bufR, false, nullptr, bufA, false, 1.0f, 1.0f, 1.0f, 0};
+      if (int rc = run_conv(pre, false, io, B, F, st)) return rc;
+    }
   }
   // Fused tensor-core plan: every ResBlock1 as one launch (or one launch per pair, whichever the cost
   // model of resblock_tc.cu prefers).  When every stage can be fused the activations between the
@@ -342,6 +360,18 @@ static bool wants_f16_copy(const Layer& L) { return !L.transposed && L.Cout <= 3
 //     (+5..6 dB at random init), an IEEE-half c1 -> c2 intermediate and w2 image in the fused kernels.
 int finalize_plan(nvse_generator* g) {
   for (Layer& L : g->layers) {
+    if (L.name == "conv_pre" && L.pre_n == 0) {
+      // smallest supported K >= Cin, output channels in equal slices of <= 256
+      int cin = 0, nsl = 1;
+      for (int cand : {32, 64, 128}) if (!cin && L.Cin <= cand) cin = cand;
+      while (L.Cout / nsl > 256 && nsl < 4) nsl *= 2;
+      if (cin && L.Cout % nsl == 0 && tc_supported(cin, L.Cout / nsl) && L.k <= kMaxTaps) {
+        L.pre_cin = cin; L.pre_cout = L.Cout / nsl;
+        for (int sl = 0; sl < nsl; ++sl)
+          NVSE_CUDA_CHECK(cudaMalloc(&L.w_pre[sl], sizeof(__nv_bfloat16) * tc_weight_image_elems(cin, L.pre_cout, L.k)));
+        L.pre_n = nsl;
+      }
+    }
     if (!wants_tc(L)) continue;
     const size_t bytes = sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k);
     if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, bytes));
@@ -352,8 +382,18 @@ int finalize_plan(nvse_generator* g) {
   return NVSE_OK;
 }
 
+int build_extra_images(nvse_generator* g, cudaStream_t st) {
+  for (Layer& L : g->layers)
+    for (int sl = 0; sl < L.pre_n; ++sl)
+      if (int rc = launch_pack_weight_tc_slice(L.w, L.Cin, L.Cout, sl * L.pre_cout, reinterpret_cast<__nv_bfloat16*>(L.w_pre[sl]),
+                                               L.pre_cin, L.pre_cout, L.k, st, true))
+        return rc;
+  return NVSE_OK;
+}
+
 int finalize_bf16(nvse_generator* g, cudaStream_t st) {
   if (int rc = finalize_plan(g)) return rc;
+  if (int rc = build_extra_images(g, st)) return rc;
   for (Layer& L : g->layers) {
     if (!wants_tc(L)) continue;
     if (int rc = launch_pack_weight_tc(L.w, reinterpret_cast<__nv_bfloat16*>(L.w_bf16), L.Cin, L.Cout, L.k, st)) return rc;
@@ -418,6 +458,7 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     cudaFree(L.w_f16);
     cudaFree(L.wT);
     cudaFree(L.wT_bf16);
+    for (void* q : L.w_pre) cudaFree(q);
   }
   delete g;
   return NVSE_OK;

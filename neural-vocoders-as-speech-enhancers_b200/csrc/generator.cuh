@@ -19,6 +19,10 @@ struct Layer {
   void* w_f16 = nullptr;   // the same image in IEEE half: second conv of a ResBlock1 pair at C <= 32 (resblock_tc.cuh h_fp16)
   bool tc_split = false;   // activations as hi+lo bf16 pairs on the tensor-core path (accuracy)
   bool tc_f16 = false;     // IEEE-half operands (w_f16) on the tensor-core path: the upsamplers
+  // conv_pre on the tensor cores (16-bit path): IEEE-half images of its output-channel slices, input channels zero-padded
+  // to pre_cin (80 -> 128); pre_cout channels per slice (N <= 256 per MMA)
+  void* w_pre[4] = {nullptr, nullptr, nullptr, nullptr};
+  int pre_cin = 0, pre_cout = 0, pre_n = 0;
   bool have_w = false, have_bias = false;
   float* wT = nullptr;     // training path: per-tap transposed weights [k][Cout][Cin] (the dgrad operand), built lazily
   void* wT_bf16 = nullptr; // training path, tensor-core dgrad: the bf16 image of wT (as a layer with Cin <-> Cout)
@@ -57,6 +61,7 @@ int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64
 int ensure_side_streams(nvse_generator* g);  // g->side[], ev_fork, ev_join[]: the ResBlocks of an MRF run concurrently
 int finalize_plan(nvse_generator* g);                    // allocates the tensor-core image buffers, sets the per-layer precision flags
 int finalize_bf16(nvse_generator* g, cudaStream_t st);  // finalize_plan + builds the tensor-core weight images
+int build_extra_images(nvse_generator* g, cudaStream_t st);  // images derived from Layer::w that the batched loader does not write (conv_pre)
 int tc_abort_status(bool reset, unsigned int* flag);
 int tc_abort_bind(unsigned int* host_word_dev);
 int tc_abort_clear(cudaStream_t st);

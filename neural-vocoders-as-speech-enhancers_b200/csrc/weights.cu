@@ -223,6 +223,7 @@ extern "C" int nvse_generator_load_weights(nvse_generator* g, const float* const
   NVSE_LAUNCH_CHECK("load_scales_kernel");
   load_weights_kernel<<<(unsigned)ld->total_blocks, 256, 0, st>>>(ld->d_layers, ld->d_blk_layer, ld->d_blk_first);
   NVSE_LAUNCH_CHECK("load_weights_kernel");
+  if (int rc = build_extra_images(g, st)) return rc;
   for (Layer& L : g->layers) L.have_w = L.have_bias = true;
   g->finalized = true;
   g->train_ready = with_train != 0;
