@@ -496,7 +496,7 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
             traffic_note = (f"dram__bytes_read+write per launch, mean over the {tj['launches']} tensor-core launches of one forward "
                             f"(algorithmic bytes per launch by the same count: {tj['algorithmic_bytes_per_launch']:.3e})")
-    tc = [k for k in prof if k["kernel"].startswith(("conv_tc", "resblock_tc", "pair_tc"))]
+    tc = [k for k in prof if k["kernel"].startswith(("conv_tc", "ups_tc", "resblock_tc", "pair_tc"))]
     tc_ms, tc_flops, tc_n = sum(k["ms"] for k in tc), sum(k["flops"] for k in tc), sum(k["launches"] for k in tc)
     all_ms = sum(k["ms"] for k in prof)
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
@@ -516,7 +516,7 @@ def main():
                 "bytes_note": "per rank",
                 "ms_per_step": ms_e2e / args.steps, "api": "Vocoder.run_host: pinned host wav -> mel_spectrogram -> HiFiGAN -> pinned host wav"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "resblock_tc_kernel + pair_tc_kernel + conv_tc_kernel (tcgen05 implicit-GEMM convs: fused MRF ResBlocks + upsamplers)",
+        "roofline": {"bound": "tensor", "kernel": "resblock_tc / resblock_pipe / pair_tc + ups_tc / conv_tc kernels (tcgen05 implicit-GEMM convs: fused MRF ResBlocks, upsamplers, conv_pre)",
                      "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + ", sustained bf16",
                      "launches": tc_n, "avg_launch_ms": tc_ms / tc_n if tc_n else None, "share_of_step": tc_ms / all_ms if all_ms else None,

@@ -5,6 +5,7 @@
 #include "generator.cuh"
 #include "conv_tc.cuh"
 #include "resblock_tc.cuh"
+#include "ups_tc.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -106,6 +107,13 @@ int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64
                        cudaStream_t st, bool x_t32, bool y_t32) {
   const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
   const int nph = (int)std::min<int64_t>(L.stride, Tout);
+  static const bool ups_env = [] { const char* e = std::getenv("NVSE_UPS_TC"); return !(e && e[0] == '0'); }();
+  if (tc && ups_env && L.w_ups && x_t32 && y_t32) {  // all phases in one persistent launch (ups_tc.cu)
+    UpsTcArgs a{};
+    a.x = x; a.x_bstride = t32_rows(Tin) * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout; a.stride = L.stride;
+    a.wimg = L.w_ups; a.bias = L.bias; a.y = y; a.y_bstride = t32_rows(Tout) * L.Cout; a.in_slope = in_slope;
+    return launch_ups_tc(a, B, st);
+  }
   if (tc && L.w_bf16) {
     for (int r0 = 0; r0 < nph; r0 += kTcMaxPhases) {
       const int n = std::min(kTcMaxPhases, nph - r0);
@@ -376,13 +384,20 @@ int finalize_plan(nvse_generator* g) {
     const size_t bytes = sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k);
     if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, bytes));
     if ((wants_f16_copy(L) || L.transposed) && !L.w_f16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_f16, bytes));
-    if (L.transposed) L.tc_f16 = true;
+    if (L.transposed) {
+      L.tc_f16 = true;
+      if (!L.w_ups && ups_tc_supported(L.Cin, L.Cout, L.k, L.stride, L.padding))
+        NVSE_CUDA_CHECK(cudaMalloc(&L.w_ups, sizeof(__nv_bfloat16) * ups_tc_image_elems(L.Cin, L.Cout, L.k)));
+    }
     else L.tc_split = L.Cout <= 32 && tc_split_fits(L.Cin, L.Cout, (L.k - 1) * L.dilation);
   }
   return NVSE_OK;
 }
 
 int build_extra_images(nvse_generator* g, cudaStream_t st) {
+  for (Layer& L : g->layers)
+    if (L.w_ups)
+      if (int rc = launch_pack_weight_ups(L.w, L.w_ups, L.Cin, L.Cout, L.stride, st)) return rc;
   for (Layer& L : g->layers)
     for (int sl = 0; sl < L.pre_n; ++sl)
       if (int rc = launch_pack_weight_tc_slice(L.w, L.Cin, L.Cout, sl * L.pre_cout, reinterpret_cast<__nv_bfloat16*>(L.w_pre[sl]),
@@ -459,6 +474,7 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     cudaFree(L.wT);
     cudaFree(L.wT_bf16);
     for (void* q : L.w_pre) cudaFree(q);
+    cudaFree(L.w_ups);
   }
   delete g;
   return NVSE_OK;

@@ -21,6 +21,7 @@ struct Layer {
   bool tc_f16 = false;     // IEEE-half operands (w_f16) on the tensor-core path: the upsamplers
   // conv_pre on the tensor cores (16-bit path): IEEE-half images of its output-channel slices, input channels zero-padded
   // to pre_cin (80 -> 128); pre_cout channels per slice (N <= 256 per MMA)
+  void* w_ups = nullptr;   // ConvTranspose1d with k = 2 * stride: stage-ordered half image of the persistent all-phase kernel (ups_tc.cuh)
   void* w_pre[4] = {nullptr, nullptr, nullptr, nullptr};
   int pre_cin = 0, pre_cout = 0, pre_n = 0;
   bool have_w = false, have_bias = false;

@@ -6,6 +6,7 @@
 #include "conv_tc.cuh"
 #include "generator.cuh"
 #include "resblock_tc.cuh"
+#include "ups_tc.cuh"
 #include "grad.cuh"
 
 using namespace nvse;
@@ -145,7 +146,9 @@ extern "C" int nvse_tc_abort_status(int reset, int* flag) {
   unsigned int v3 = 0, v4 = 0;
   if (int rc = pair_abort_status(reset != 0, &v3)) return rc;
   if (int rc = wgrad_abort_status(reset != 0, &v4)) return rc;
-  *flag = (int)(v | v2 | v3 | v4);
+  unsigned int v5 = 0;
+  if (int rc = ups_abort_status(reset != 0, &v5)) return rc;
+  *flag = (int)(v | v2 | v3 | v4 | v5);
   if (reset) tc_abort_host_clear();
   return NVSE_OK;
 }

@@ -11,6 +11,7 @@
 #include "generator.cuh"
 #include "grad.cuh"
 #include "resblock_tc.cuh"
+#include "ups_tc.cuh"
 
 namespace nvse {
 
@@ -35,6 +36,7 @@ int tc_abort_bind_device() {
   if (int rc = rb_abort_bind(dptr)) return rc;
   if (int rc = pair_abort_bind(dptr)) return rc;
   if (int rc = wgrad_abort_bind(dptr)) return rc;
+  if (int rc = ups_abort_bind(dptr)) return rc;
   if (dev >= 0 && dev < 64) g_bound[dev] = true;
   return NVSE_OK;
 }
@@ -47,6 +49,7 @@ int tc_abort_poll(cudaStream_t st) {
   if (int rc = rb_abort_clear(st)) return rc;
   if (int rc = pair_abort_clear(st)) return rc;
   if (int rc = wgrad_abort_clear(st)) return rc;
+  if (int rc = ups_abort_clear(st)) return rc;
   return fail(NVSE_ERR_STATE, "a tensor-core kernel of an earlier call gave up on a bounded wait (> 0.2 s: GPU time-slicing, a debugger, or a "
                               "protocol bug): every result since that call is invalid; the failure flags have been cleared");
 }

@@ -424,9 +424,10 @@ def test_batched_weight_load_matches_per_layer_load():
         g_gpu._engine.weights_key = None   # force a reload
         g_gpu(mel)
         l2 = lib_mod.launch_count()
-    # the whole reload is two launches for all layers + one per <= 256-channel slice of conv_pre's half-precision image
-    pre_slices = max(1, cfg["upsample_initial_channel"] // 256)
-    assert (l2 - l1) - (l1 - l0) == 2 + pre_slices
+    # the whole reload is two launches for all layers (instead of several per layer) + one per derived image the batched
+    # kernel does not write: the <= 256-channel slices of conv_pre's half-precision image, the upsamplers' all-phase images
+    extra = max(1, cfg["upsample_initial_channel"] // 256) + len(cfg["upsample_rates"])
+    assert 2 <= (l2 - l1) - (l1 - l0) <= 2 + extra
     dout = torch.from_numpy(gold["dout"]).cuda()
     grads = []
     for g in (g_gpu, g_cpu):

@@ -629,3 +629,45 @@ def test_reassigned_parameter_is_picked_up():
         y2 = gen(mel)
     assert not torch.equal(y0, y1) and float((y1 - y0).abs().max()) > 1e-2
     assert float((y2 - y0).abs().max()) < 1e-6 and float((y2 - y1).abs().max()) > 1e-2   # (b + 0.25) - 0.25 rounds
+
+
+@pytest.mark.parametrize("frames,batch", [(37, 2), (129, 3)])
+def test_persistent_upsampler_matches_polyphase_launches(frames, batch, tmp_path):
+    """ups_tc.cu (all phases of a ConvTranspose1d side by side in one persistent launch, transposed stores) against the
+    per-phase conv_tc launches it replaces (NVSE_UPS_TC=0, read once per process: run in a child): same half operands and
+    fp32 accumulation, only the summation order differs.  Tile counts with partial last tiles at every stage."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "polyphase.npy")
+    child = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path[:0] = [{here!r}, {os.path.dirname(here)!r}]\n"
+        "import synth\n"
+        "from util import build_generator\n"
+        "cfg = synth.HIFIGAN_V1\n"
+        "gen = build_generator(cfg, synth.make_state(cfg, 21, 'init'), 'cuda:0', True)\n"
+        f"mel = torch.from_numpy(synth.make_mel({batch}, {frames}, 77)).to('cuda:0')\n"
+        "with torch.no_grad():\n"
+        f"    np.save({out!r}, gen(mel).reshape({batch}, -1).cpu().numpy())\n"
+    )
+    env = dict(os.environ, NVSE_UPS_TC="0")
+    subprocess.run([sys.executable, "-c", child], check=True, env=env, timeout=600)
+    ref = np.load(out)
+    gen = build_generator(A, synth.make_state(A, 21, "init"), DEV, True)
+    mel = torch.from_numpy(synth.make_mel(batch, frames, 77)).to(DEV)
+    with torch.no_grad():
+        got = gen(mel).reshape(batch, -1).cpu().numpy()
+        gen.precision = "fp32"
+        f32 = gen(mel).reshape(batch, -1).cpu().numpy()
+    assert got.shape == ref.shape
+    # a different fp32 summation order moves some 16-bit roundings of the ResBlocks behind the upsamplers: the two paths
+    # agree far better than either agrees with the fp32 path, and are equally close to it
+    snr = np_oracle.snr_db(ref, got)
+    s_new, s_old = np_oracle.snr_db(f32, got), np_oracle.snr_db(f32, ref)
+    report(f"persistent upsampler vs polyphase launches ({batch} x {frames} frames): SNR {snr:.1f} dB; vs the fp32 path {s_new:.1f} dB "
+           f"(polyphase launches: {s_old:.1f} dB)")
+    assert snr >= 60.0 and snr >= max(s_new, s_old) + 3.0
+    assert abs(s_new - s_old) <= 1.5 and s_new >= 40.0
+    assert not lib_mod.tc_abort_status()

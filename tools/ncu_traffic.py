@@ -14,7 +14,7 @@ def to_bytes(v, u):
 per_kernel, tot, n = {}, 0.0, 0
 for r in data:
     name = r[ix["Kernel Name"]]
-    if not any(s in name for s in ("resblock_", "pair_tc", "conv_tc")):
+    if not any(s in name for s in ("resblock_", "pair_tc", "conv_tc", "ups_tc")):
         continue
     # ncu scales units per row in the raw page: re-read them from the per-row unit columns when present
     rd = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]])
@@ -24,7 +24,7 @@ for r in data:
     tot += rd + wr; n += 1
 bench = json.loads(open(bench_json).read().strip().splitlines()[-1])
 steps = bench["steps"]
-tc = [k for k in bench["kernels"] if k["kernel"].startswith(("conv_tc", "resblock_tc", "pair_tc"))]
+tc = [k for k in bench["kernels"] if k["kernel"].startswith(("conv_tc", "ups_tc", "resblock_tc", "pair_tc"))]
 alg = sum(k["gbs"] * 1e9 * k["ms_per_step"] * 1e-3 for k in tc)  # algorithmic bytes per step (per forward x forwards per step)
 launches_step = sum(k["launches"] for k in tc) / steps
 out = {"micro_batch": mb, "seconds": sec, "launches": n, "dram_bytes_per_launch": tot / n,

@@ -5,7 +5,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 from util import lib_mod, pkg  # noqa: E402
-pat = sys.argv[1] if len(sys.argv) > 1 else "conv_tc"
+pat = sys.argv[1] if len(sys.argv) > 1 else "_tc["
 import synth  # noqa: E402
 torch.manual_seed(0)
 g = pkg.HiFiGAN(synth.AttrDict(synth.HIFIGAN_V1)).to("cuda").eval()
