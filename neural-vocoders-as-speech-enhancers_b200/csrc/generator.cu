@@ -108,9 +108,10 @@ int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64
   const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
   const int nph = (int)std::min<int64_t>(L.stride, Tout);
   static const bool ups_env = [] { const char* e = std::getenv("NVSE_UPS_TC"); return !(e && e[0] == '0'); }();
-  if (tc && ups_env && L.w_ups && x_t32 && y_t32) {  // all phases in one persistent launch (ups_tc.cu)
+  static const bool ups_xcl_env = [] { const char* e = std::getenv("NVSE_UPS_XCL"); return !(e && e[0] == '0'); }();
+  if (tc && ups_env && L.w_ups && y_t32 && (x_t32 || (ups_xcl_env && L.stride == 8 && !((L.Cin / 8) & (L.Cin / 8 - 1))))) {  // all phases in one persistent launch (ups_tc.cu)
     UpsTcArgs a{};
-    a.x = x; a.x_bstride = t32_rows(Tin) * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout; a.stride = L.stride;
+    a.x = x; a.x_cl = x_t32 ? 0 : 1; a.x_bstride = (x_t32 ? t32_rows(Tin) : Tin) * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout; a.stride = L.stride;
     a.wimg = L.w_ups; a.bias = L.bias; a.y = y; a.y_bstride = t32_rows(Tout) * L.Cout; a.in_slope = in_slope;
     return launch_ups_tc(a, B, st);
   }

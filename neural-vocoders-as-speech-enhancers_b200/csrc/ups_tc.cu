@@ -58,7 +58,8 @@ __device__ __forceinline__ bool mbar_wait_all(uint32_t bar, uint32_t parity) {
 }
 
 // MINB = resident CTAs per SM the register budget is set for; with one CTA per SM staging keeps twice the loads in flight
-template <int U, int MINB>
+// XCL: channels-last input (the first upsampler reads conv_pre's output) instead of T32
+template <int U, int MINB, bool XCL>
 __global__ void __launch_bounds__(kThreads, MINB) ups_tc_kernel(const __grid_constant__ UpsKernelArgs k) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const UpsTcArgs& a = k.a;
@@ -210,17 +211,36 @@ __global__ void __launch_bounds__(kThreads, MINB) ups_tc_kernel(const __grid_con
       for (int e0 = wtid; e0 < items; e0 += kWorkWarps * 32 * kStageUnroll) {
         float4 f0[kStageUnroll], f1[kStageUnroll];
         int dst[kStageUnroll];
+        if constexpr (XCL) {
+          // channels-last input: consecutive lanes take consecutive 8-channel chunks of a row (contiguous); the odd row pitch
+          // of the tile keeps the shared-memory stores conflict-free.  nchunk is a power of two.
+          const int cshift = 31 - __clz(nchunk);
 #pragma unroll
-        for (int u = 0; u < kStageUnroll; ++u) {
-          const int e = e0 + u * kWorkWarps * 32;
-          const int chunk = e / rows, r = e - chunk * rows;  // consecutive lanes: consecutive rows of a chunk (T32: contiguous)
-          const int t = t0 - 1 + r;
-          dst[u] = e < items ? (chunk * kRowsPad + r) * 16 : -1;
-          f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < items && t >= 0 && t < a.Tin) {
-            const float4* src = reinterpret_cast<const float4*>(xb + t32_off(t, chunk * 8, Cin));
-            f0[u] = __ldg(src);
-            f1[u] = __ldg(src + 32);
+          for (int u = 0; u < kStageUnroll; ++u) {
+            const int e = e0 + u * kWorkWarps * 32;
+            const int chunk = e & (nchunk - 1), r = e >> cshift;
+            const int t = t0 - 1 + r;
+            dst[u] = e < items ? (chunk * kRowsPad + r) * 16 : -1;
+            f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < items && t >= 0 && t < a.Tin) {
+              const float4* src = reinterpret_cast<const float4*>(xb + (int64_t)t * Cin + chunk * 8);
+              f0[u] = __ldg(src);
+              f1[u] = __ldg(src + 1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < kStageUnroll; ++u) {
+            const int e = e0 + u * kWorkWarps * 32;
+            const int chunk = e / rows, r = e - chunk * rows;  // consecutive lanes: consecutive rows of a chunk (T32: contiguous)
+            const int t = t0 - 1 + r;
+            dst[u] = e < items ? (chunk * kRowsPad + r) * 16 : -1;
+            f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < items && t >= 0 && t < a.Tin) {
+              const float4* src = reinterpret_cast<const float4*>(xb + t32_off(t, chunk * 8, Cin));
+              f0[u] = __ldg(src);
+              f1[u] = __ldg(src + 32);
+            }
           }
         }
 #pragma unroll
@@ -396,6 +416,8 @@ int launch_pack_weight_ups(const float* w_kio, void* img, int Cin, int Cout, int
 int launch_ups_tc(const UpsTcArgs& a, int64_t B, cudaStream_t st) {
   NVSE_REQUIRE(ups_tc_supported(a.Cin, a.Cout, 2 * a.stride, a.stride, a.stride / 2), NVSE_ERR_UNSUPPORTED,
                "ups_tc: Cin=%d Cout=%d stride=%d unsupported", a.Cin, a.Cout, a.stride);
+  NVSE_REQUIRE(!a.x_cl || (a.stride == 8 && !((a.Cin / 8) & (a.Cin / 8 - 1))), NVSE_ERR_UNSUPPORTED,
+               "ups_tc: channels-last input needs stride 8 and a power-of-two channel count");
   if (B == 0 || a.Tin <= 0) return NVSE_OK;
   UpsKernelArgs k;
   k.a = a;
@@ -425,13 +447,13 @@ int launch_ups_tc(const UpsTcArgs& a, int64_t B, cudaStream_t st) {
   const double rows = (double)B * a.Tin;
   ProfScope prof("ups_tc", a.Cin, a.Cout, 2.0 * rows * a.Cin * a.Cout * 2.0 * a.stride,
                  rows * (a.Cin * 4.0 + (double)a.stride * a.Cout * 4.0), st);
-#define UPS_LAUNCH(UU, MB)                                                                                                    \
-  if (a.stride == UU && per_sm == MB) {                                                                                       \
-    NVSE_CUDA_CHECK(cudaFuncSetAttribute(ups_tc_kernel<UU, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
-    ups_tc_kernel<UU, MB><<<grid, kThreads, smem, st>>>(k);                                                                   \
+#define UPS_LAUNCH(UU, MB, XC)                                                                                                \
+  if (a.stride == UU && per_sm == MB && (a.x_cl != 0) == XC) {                                                                \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(ups_tc_kernel<UU, MB, XC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    ups_tc_kernel<UU, MB, XC><<<grid, kThreads, smem, st>>>(k);                                                               \
   } else
-  UPS_LAUNCH(8, 1) UPS_LAUNCH(2, 1) UPS_LAUNCH(2, 2)
-  return fail(NVSE_ERR_UNSUPPORTED, "ups_tc: no kernel for stride %d", a.stride);
+  UPS_LAUNCH(8, 1, false) UPS_LAUNCH(8, 1, true) UPS_LAUNCH(2, 1, false) UPS_LAUNCH(2, 2, false)
+  return fail(NVSE_ERR_UNSUPPORTED, "ups_tc: no kernel for stride %d%s", a.stride, a.x_cl ? " with channels-last input" : "");
 #undef UPS_LAUNCH
   NVSE_LAUNCH_CHECK("ups_tc_kernel");
   return NVSE_OK;

@@ -8,7 +8,7 @@
 namespace nvse {
 
 struct UpsTcArgs {
-  const float* x;      // [B][t32_rows(Tin)][Cin] fp32, T32 layout; leaky_relu(in_slope) is applied on load
+  const float* x;      // [B][t32_rows(Tin)][Cin] fp32, T32 layout (or, x_cl, channels-last [B][Tin][Cin]); leaky_relu(in_slope) on load
   int64_t x_bstride;   // elements per utterance
   int Tin, Cin, Cout, stride;
   const void* wimg;    // IEEE-half image built by launch_pack_weight_ups
@@ -16,6 +16,7 @@ struct UpsTcArgs {
   float* y;            // [B][t32_rows(stride * Tin)][Cout] fp32, T32 layout
   int64_t y_bstride;
   float in_slope;
+  int x_cl;            // x is channels-last [B][Tin][Cin] instead of T32 (stride 8 only: the first upsampler reads conv_pre's output)
 };
 
 // k = 2 * stride, padding = stride / 2, stride 2 or 8, Cin a multiple of 32, channel slices of 16-channel chunks
