@@ -462,7 +462,7 @@ def main():
     if not parity["parity_snr_db"] >= (40.0 if args.precision == "bf16" else 80.0):
         raise SystemExit(f"timed output fails the parity gate: {parity}")
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):
         host_step()
     ms_e2e = timed(host_step, args.steps)
     if pkg._lib.tc_abort_status():

@@ -120,20 +120,21 @@ class _GeneratorBase(nn.Module):
         self.invalidate_engine()
         return out
 
-    def forward(self, x):
-        """mel ``[B, 80, frames]`` -> waveform ``[B, samples]`` on ``x.device``."""
+    def forward(self, x, out=None):
+        """mel ``[B, 80, frames]`` -> waveform ``[B, samples]`` on ``x.device`` (``out``: inference only, write into this
+        device tensor instead of allocating the result)."""
         if self._engine is None:
             object.__setattr__(self, "_engine", GeneratorEngine(self, self._kind))
-        return self._engine.forward(self, x)
+        return self._engine.forward(self, x, out=out)
 
     @torch.no_grad()
-    def forward_pcm16(self, x):
+    def forward_pcm16(self, x, out=None):
         """Inference straight to 16-bit PCM: what the reference's loop does with the waveform next (``sf.write(path,
         audio, sr, 'PCM_16')``, infers/inference_hifigan.py:89-95), with the quantisation fused into the last kernel.
         mel ``[B, 80, frames]`` -> int16 ``[B, samples]``."""
         if self._engine is None:
             object.__setattr__(self, "_engine", GeneratorEngine(self, self._kind))
-        return self._engine.forward(self, x, pcm16=True)
+        return self._engine.forward(self, x, pcm16=True, out=out)
 
     def remove_weight_norm(self):
         print("Removing weight norm...")

@@ -202,9 +202,10 @@ class GeneratorEngine:
         self.weights_key, self._train_loaded = key, True  # the per-layer path builds the backward's copies lazily
 
     # ---- forward ---------------------------------------------------------------------
-    def forward(self, module, x, precision=None, pcm16=False):
+    def forward(self, module, x, precision=None, pcm16=False, out=None):
         """``pcm16=True`` (inference only): the waveform as int16 PCM, quantised like ``sf.write(..., 'PCM_16')``
-        (infers/inference_hifigan.py:93) inside the last kernel instead of float32."""
+        (infers/inference_hifigan.py:93) inside the last kernel instead of float32.  ``out`` (inference only): a
+        contiguous device tensor ``[B, samples]`` of the result's dtype to write into instead of allocating one."""
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters()))):
@@ -225,7 +226,12 @@ class GeneratorEngine:
         xd = x.detach().to(dev, torch.float32).contiguous()
         batch, _, frames = xd.shape
         n_out = lib.nvse_generator_out_samples(self.handle, frames)
-        out = torch.empty((batch, n_out), dtype=torch.int16 if pcm16 else torch.float32, device=dev)
+        odt = torch.int16 if pcm16 else torch.float32
+        if out is not None:
+            if not (out.is_cuda and out.device == dev and out.dtype == odt and tuple(out.shape) == (batch, n_out) and out.is_contiguous()):
+                raise RuntimeError(f"out must be a contiguous {odt} tensor of shape {(batch, n_out)} on {dev}")
+        else:
+            out = torch.empty((batch, n_out), dtype=odt, device=dev)
         if batch == 0 or frames == 0:
             return out.to(x.device)
         need = lib.nvse_generator_workspace_bytes(self.handle, batch, frames, prec)

@@ -58,27 +58,48 @@ class Vocoder:
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_h2d"):
             self._h2d, self._d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._stage = None
         self._h2d.wait_stream(cur)
         self._d2h.wait_stream(cur)
         starts = list(range(0, wav_host.shape[0], self.micro_batch))
+        # Two device input and two device output buffers, kept across calls and used alternately: no allocation (and no
+        # allocator-driven cudaMalloc while blocks wait for their cross-stream use to end) on the steady-state path.
+        # consumed[k]: the kernels have read input buffer k; drained[k]: output buffer k has reached the host.
+        key = (int(wav_host.shape[-1]), bool(pcm16), min(self.micro_batch, max(1, wav_host.shape[0])))
+        if starts and (self._stage is None or self._stage["key"] != key):
+            self._stage = {"key": key, "in": [torch.empty((key[2], key[0]), dtype=torch.float32, device=dev) for _ in range(2)],
+                           "out": [None, None], "consumed": [None, None], "drained": [None, None]}
+        stg = self._stage
 
-        def upload(s):
+        def upload(i):
+            s, k = starts[i], i & 1
+            n = min(self.micro_batch, wav_host.shape[0] - s)
             with torch.cuda.stream(self._h2d):
-                chunk = wav_host[s:s + self.micro_batch].to(dev, non_blocking=True)
+                if stg["consumed"][k] is not None:
+                    self._h2d.wait_event(stg["consumed"][k])
+                chunk = stg["in"][k][:n]
+                chunk.copy_(wav_host[s:s + n], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._h2d)
             return chunk, ev
 
-        nxt = upload(starts[0]) if starts else None
+        nxt = upload(0) if starts else None
         for i, s in enumerate(starts):
             chunk, ev = nxt
-            nxt = upload(starts[i + 1]) if i + 1 < len(starts) else None
+            k = i & 1
+            nxt = upload(i + 1) if i + 1 < len(starts) else None
             cur.wait_event(ev)
-            chunk.record_stream(cur)
-            if pcm16:  # quantised inside the generator's last kernel: half the bytes cross PCIe, no extra pass
-                y = self.generator.forward_pcm16(self.mel(chunk))
-            else:
-                y = self.generator(self.mel(chunk))
+            mel = self.mel(chunk)
+            stg["consumed"][k] = torch.cuda.Event()
+            stg["consumed"][k].record(cur)
+            if stg["drained"][k] is not None:
+                cur.wait_event(stg["drained"][k])
+            obuf = stg["out"][k]
+            obuf = obuf[:chunk.shape[0]] if obuf is not None and obuf.shape[0] >= chunk.shape[0] else None
+            # quantised inside the generator's last kernel with pcm16: half the bytes cross PCIe, no extra pass
+            y = self.generator.forward_pcm16(mel, out=obuf) if pcm16 else self.generator(mel, out=obuf)
+            if stg["out"][k] is None or stg["out"][k].shape[0] < y.shape[0]:
+                stg["out"][k] = y
             y = y.reshape(y.shape[0], -1)
             if out_host is None:
                 out_host = torch.empty((wav_host.shape[0], y.shape[1]), dtype=y.dtype, pin_memory=True)
@@ -86,8 +107,9 @@ class Vocoder:
             done.record(cur)
             with torch.cuda.stream(self._d2h):
                 self._d2h.wait_event(done)
-                y.record_stream(self._d2h)
                 out_host[s:s + y.shape[0]].copy_(y, non_blocking=True)
+                stg["drained"][k] = torch.cuda.Event()
+                stg["drained"][k].record(self._d2h)
         cur.wait_stream(self._d2h)
         if out_host is None:  # no utterances: an empty result of the right width, like the device-resident path
             h = self.h
