@@ -487,9 +487,9 @@ def main():
 
     pk = peaks()
     # DRAM traffic of the tensor-core kernels from the committed `ncu --set full` capture of one forward
-    # (profiles/r01_ncu_traffic.json: bytes per launch, same shapes as this workload's micro-batch)
+    # (profiles/r02_ncu_traffic.json: bytes per launch, same shapes as this workload's micro-batch)
     traffic, traffic_note = None, "no ncu capture for this micro-batch"
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.isfile(tpath):
         tj = json.load(open(tpath))
         if tj.get("micro_batch") == args.micro_batch and tj.get("seconds") == args.seconds:
