@@ -191,65 +191,67 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
 
 // ------------------------------------------------------------------------------------------
 // conv_post of the tensor-core path (HiFi-GAN: Cin -> 1 channel, hifigan.py:120-122): the input is the
-// T32-layout MRF output.  Memory-bound: one pass over x with fully coalesced 16-byte loads into a
-// padded shared tile (row pitch Cin + 4 floats: conflict-free 128-bit stores and loads with one thread
-// per row), then one output sample per thread.
+// T32-layout MRF output.  Memory-bound: one pass over x with fully coalesced 16-byte loads, one thread
+// per input row (see the kernel).
 // ------------------------------------------------------------------------------------------
 constexpr int POST_ROWS = 256;
 
-// CIN is compile-time so that the staging pass issues all CIN / 4 independent 16-byte loads of a row before the first
-// store: with one load in flight per thread the kernel ran at 1.7 TB/s on a pure streaming job (BENCH_r01).
+// conv_post of the tensor-core path: Cout = 1, T32 input.  One thread per INPUT row: the row's CIN values are loaded straight
+// into registers (CIN / 4 independent 16-byte loads, coalesced 512-byte warp requests), activated, and multiplied against every
+// tap's weight vector (broadcast shared-memory reads): ntaps partial dot products per row.  The partials go through a small
+// shared array and output o sums part[j][o + off_j - min_off].  A CTA of 256 input rows produces 256 - span outputs.  The
+// round-1 kernel staged the activated rows in shared memory and read each of them ntaps times: 4 x the shared-memory
+// wavefronts, which (not HBM) bounded it at 2.5 TB/s.
 template <int CIN>
 __global__ void __launch_bounds__(POST_ROWS) conv_post1_t32_kernel(const ConvF32Args a, int min_off, int span) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int pitch = CIN + 4, c4n = CIN >> 2;
-  const int nrows = POST_ROWS + span;
-  float* xs = sm;                   // [nrows][pitch]
-  float* ws = sm + nrows * pitch;   // [ntaps][Cin]
+  constexpr int c4n = CIN >> 2;
+  const int ntaps = a.taps.ntaps;
+  float* ws = sm;                    // [ntaps][CIN]
+  float* part = sm + ntaps * CIN;    // [ntaps][POST_ROWS]
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.y;
-  const int t0 = blockIdx.x * POST_ROWS;
+  const int nout = POST_ROWS - span;
+  const int o0 = blockIdx.x * nout;   // first output row of this CTA
+  const int t = o0 + min_off + tid;   // this thread's input row
   const float* __restrict__ xb = a.x + b * a.x_bstride;
-  for (int e = tid; e < a.taps.ntaps * CIN; e += POST_ROWS) {
+  float4 v[c4n];
+  const bool in = t >= 0 && t < a.Tin;
+  const float4* src = reinterpret_cast<const float4*>(xb + t32_off(in ? t : 0, 0, CIN));
+#pragma unroll
+  for (int c4 = 0; c4 < c4n; ++c4) v[c4] = in ? __ldg(src + 32 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // T32: 4-channel groups 128 floats apart
+  for (int e = tid; e < ntaps * CIN; e += POST_ROWS) {
     const int tap = e / CIN, c = e - tap * CIN;
     ws[e] = a.w[(int64_t)a.taps.widx[tap] * CIN + c];
   }
-  for (int r = tid; r < nrows; r += POST_ROWS) {
-    const int t = t0 + min_off + r;
-    float4 v[c4n];
-    const bool in = t >= 0 && t < a.Tin;
-    const float4* src = reinterpret_cast<const float4*>(xb + t32_off(in ? t : 0, 0, CIN));
 #pragma unroll
-    for (int c4 = 0; c4 < c4n; ++c4) v[c4] = in ? __ldg(src + 32 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // T32: 4-channel groups 128 floats apart
-#pragma unroll
-    for (int c4 = 0; c4 < c4n; ++c4) {
-      float4 q = v[c4];
-      q.x = lrelu(q.x, a.in_slope); q.y = lrelu(q.y, a.in_slope); q.z = lrelu(q.z, a.in_slope); q.w = lrelu(q.w, a.in_slope);
-      *reinterpret_cast<float4*>(xs + r * pitch + 4 * c4) = q;
-    }
+  for (int c4 = 0; c4 < c4n; ++c4) {
+    v[c4].x = lrelu(v[c4].x, a.in_slope); v[c4].y = lrelu(v[c4].y, a.in_slope);
+    v[c4].z = lrelu(v[c4].z, a.in_slope); v[c4].w = lrelu(v[c4].w, a.in_slope);
   }
   __syncthreads();
-  const int t = t0 + tid;
-  if (t >= a.Trows) return;
-  float acc = a.bias ? a.bias[0] : 0.0f;
-  for (int tap = 0; tap < a.taps.ntaps; ++tap) {
-    const float4* xr = reinterpret_cast<const float4*>(xs + (tid + a.taps.off[tap] - min_off) * pitch);
+  for (int tap = 0; tap < ntaps; ++tap) {
     const float4* wr = reinterpret_cast<const float4*>(ws + tap * CIN);
     float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
     for (int c4 = 0; c4 < c4n; ++c4) {
-      const float4 xv = xr[c4], wv = wr[c4];
-      p0 = fmaf(xv.x, wv.x, p0); p1 = fmaf(xv.y, wv.y, p1); p2 = fmaf(xv.z, wv.z, p2); p3 = fmaf(xv.w, wv.w, p3);
+      const float4 wv = wr[c4];
+      p0 = fmaf(v[c4].x, wv.x, p0); p1 = fmaf(v[c4].y, wv.y, p1); p2 = fmaf(v[c4].z, wv.z, p2); p3 = fmaf(v[c4].w, wv.w, p3);
     }
-    acc += (p0 + p1) + (p2 + p3);
+    part[tap * POST_ROWS + tid] = (p0 + p1) + (p2 + p3);
   }
+  __syncthreads();
+  const int o = o0 + tid;
+  if (tid >= nout || o >= a.Trows) return;
+  float acc = a.bias ? a.bias[0] : 0.0f;
+  for (int tap = 0; tap < ntaps; ++tap) acc += part[tap * POST_ROWS + tid + a.taps.off[tap] - min_off];
   acc *= a.out_scale;
   if (a.y_pcm16) {  // same arithmetic as pcm16_kernel (core.cu) on the float result
-    const float o = a.out_act == 1 ? tanhf(acc) : acc;
-    a.y_pcm16[b * a.y_bstride + t] = (int16_t)__float2int_rn(fminf(fmaxf(o * 32767.0f, -32768.0f), 32767.0f));
+    const float ov = a.out_act == 1 ? tanhf(acc) : acc;
+    a.y_pcm16[b * a.y_bstride + o] = (int16_t)__float2int_rn(fminf(fmaxf(ov * 32767.0f, -32768.0f), 32767.0f));
     return;
   }
-  float* yr = a.y + b * a.y_bstride + t;
+  float* yr = a.y + b * a.y_bstride + o;
   if (a.accumulate) acc += *yr;
   *yr = a.out_act == 1 ? tanhf(acc) : acc;
 }
@@ -309,8 +311,9 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
                  NVSE_ERR_UNSUPPORTED, "fp32 conv: fused PCM_16 output is only implemented by the T32 conv_post kernel");
     if (a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 &&
         (a.Cin == 16 || a.Cin == 32 || a.Cin == 64)) {
-      const size_t smem = sizeof(float) * ((size_t)(POST_ROWS + span) * (a.Cin + 4) + (size_t)a.taps.ntaps * a.Cin);
-      dim3 grid((unsigned)((a.Trows + POST_ROWS - 1) / POST_ROWS), (unsigned)B);
+      const size_t smem = sizeof(float) * ((size_t)a.taps.ntaps * POST_ROWS + (size_t)a.taps.ntaps * a.Cin);
+      const int nout = POST_ROWS - span;  // outputs per CTA (one thread per input row)
+      dim3 grid((unsigned)((a.Trows + nout - 1) / nout), (unsigned)B);
 #define POST_LAUNCH(CV)                                                                                                          \
   if (a.Cin == CV) {                                                                                                             \
     NVSE_CUDA_CHECK(cudaFuncSetAttribute(conv_post1_t32_kernel<CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \

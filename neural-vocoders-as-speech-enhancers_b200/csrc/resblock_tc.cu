@@ -840,7 +840,8 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
   // C = 128, whole k = 3 ResBlock: one tile per CTA lets two CTAs share an SM (TMEM 256 columns each), and
   // the overlap of one CTA's load / final phases with the other's MMAs outweighs the larger halo share
   if (C == 128 && npairs > 1 && k <= 3) ntile = 1;
-  if (C == 64 && k <= 3) ntile = 2;  // same trade at C = 64: 1.37 -> 1.13 ms for the k = 3 ResBlock of stage 3
+  static const int pipe_kmin = [] { const char* e = std::getenv("NVSE_RB_PIPE_KMIN"); return e ? std::atoi(e) : 5; }();
+  if (C == 64 && k <= 3 && pipe_kmin > 3) ntile = 2;  // same trade at C = 64: 1.37 -> 1.13 ms for the k = 3 ResBlock of stage 3
   if (forced > 0) ntile = std::min(forced, 256 / C);
   const int kc = tc_kchunk(C);
   const size_t stage_bytes = (size_t)(C == 32 ? 4 : (C == 64 ? 2 : 1)) * kc * C * 2;  // TPS taps per stage, as in the kernels
@@ -849,7 +850,7 @@ bool make_plan(int C, int k, const int* dil, int npairs, RbPlan* p) {
     const int R = kTileM * ntile;
     const int rows_pad = R + 2 * P;
     static const bool pipe_env = [] { const char* e = std::getenv("NVSE_RB_PIPE"); return !(e && e[0] == '0'); }();
-    const bool pipe = pipe_env && C <= 64 && k >= 5 && ntile == 4;  // measured: -3..-9 % from k = 5 up, a loss at k = 3
+    const bool pipe = pipe_env && C <= 64 && k >= pipe_kmin && ntile == 4;  // measured: -3..-9 % from k = 5 up, a loss at k = 3
     const size_t opb = (pipe ? 2 : 1) * (((size_t)(C / 8) * rows_pad * 16 + 127) & ~(size_t)127);
     const size_t tail = sizeof(float) * 2 * kRbMaxPairs * C + sizeof(uint64_t) * (pipe ? kPipeBars : kNumBars) + 16;
     if (R - 2 * halo < 32) return false;  // not enough useful rows per tile: per-layer kernels do better
