@@ -80,6 +80,11 @@ NVSE_API int64_t nvse_frontend_num_frames(const nvse_frontend* fe, int64_t T);
  * Requires T > n_fft/2 (reflect padding), like torch.stft. */
 NVSE_API int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
                           int64_t y_row_stride, float* out, void* stream);
+/* Ragged batch: y [B, T] padded to the longest utterance, samples_dev [B] int32 ON THE DEVICE = samples of each utterance
+ * (n_fft/2 < samples_dev[b] <= T).  Utterance b gets the log-mel of its own samples (reflect padding at ITS end, bit-identical
+ * to a single-utterance call): frames [0, 1 + samples_dev[b] / hop) of out [B, n_mels, 1 + T / hop]; the rest is not written. */
+NVSE_API int nvse_frontend_mel_ragged_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride,
+                                 const int32_t* samples_dev, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Generator: Models.HiFiGAN / Models.iSTFTNet forward
@@ -140,6 +145,14 @@ NVSE_API size_t nvse_generator_workspace_bytes(const nvse_generator* g, int64_t 
  * fp32 residual stream, fp32 conv_pre / conv_post). */
 NVSE_API int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t B, int64_t frames, float* out,
                            void* workspace, size_t workspace_bytes, int precision, void* stream);
+/* Ragged batch (the reference's inference loop, infers/inference_hifigan.py:67-95, runs utterances of different lengths one
+ * at a time): mel [B, in_channels, frames] padded to the longest utterance, frames_dev [B] int32 ON THE DEVICE = the mel
+ * frames of each utterance (1 <= frames_dev[b] <= frames).  Utterance b is computed exactly -- bit for bit -- as if it were
+ * passed alone with frames_dev[b] frames: every kernel treats its rows beyond that length like rows beyond the end of the
+ * sequence.  out [B, out_samples(frames)]; the samples of utterance b beyond out_samples(frames_dev[b]) are undefined.
+ * HiFiGAN, NVSE_PRECISION_BF16 (the fused tensor-core plan) only. */
+NVSE_API int nvse_generator_forward_ragged(nvse_generator* g, const float* mel, int64_t B, int64_t frames, const int32_t* frames_dev,
+                                  float* out, void* workspace, size_t workspace_bytes, int precision, void* stream);
 /* The same forward with the waveform delivered as PCM_16 (int16 [B, out_samples]) instead of float: the quantisation of
  * sf.write(..., 'PCM_16') (infers/inference_hifigan.py:93-95: round(x * 32767), clipped) fused into the last kernel
  * where that kernel is conv_post of the tensor-core plan, one extra pass otherwise.  Bit-identical to

@@ -120,12 +120,13 @@ class _GeneratorBase(nn.Module):
         self.invalidate_engine()
         return out
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, frames=None):
         """mel ``[B, 80, frames]`` -> waveform ``[B, samples]`` on ``x.device`` (``out``: inference only, write into this
-        device tensor instead of allocating the result)."""
+        device tensor instead of allocating the result; ``frames``: inference only, mel frames per utterance of a padded
+        batch -- every utterance is computed exactly as if it were passed alone, see ``GeneratorEngine.forward``)."""
         if self._engine is None:
             object.__setattr__(self, "_engine", GeneratorEngine(self, self._kind))
-        return self._engine.forward(self, x, out=out)
+        return self._engine.forward(self, x, out=out, frames=frames)
 
     @torch.no_grad()
     def forward_pcm16(self, x, out=None):

@@ -202,17 +202,20 @@ class GeneratorEngine:
         self.weights_key, self._train_loaded = key, True  # the per-layer path builds the backward's copies lazily
 
     # ---- forward ---------------------------------------------------------------------
-    def forward(self, module, x, precision=None, pcm16=False, out=None):
+    def forward(self, module, x, precision=None, pcm16=False, out=None, frames=None):
         """``pcm16=True`` (inference only): the waveform as int16 PCM, quantised like ``sf.write(..., 'PCM_16')``
         (infers/inference_hifigan.py:93) inside the last kernel instead of float32.  ``out`` (inference only): a
-        contiguous device tensor ``[B, samples]`` of the result's dtype to write into instead of allocating one."""
+        contiguous device tensor ``[B, samples]`` of the result's dtype to write into instead of allocating one.
+        ``frames`` (inference only, HiFiGAN on the 16-bit path): int tensor ``[B]``, the mel frames of each utterance of a
+        batch padded to the longest one -- utterance ``b`` comes out bit-identical to passing ``x[b:b+1, :, :frames[b]]``
+        alone (``nvse_generator_forward_ragged``); its samples beyond its own length are undefined."""
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:
             raise RuntimeError(f"expected mel of shape [B, {self.cfg.in_channels}, frames], got {tuple(x.shape)}")
         if torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters()))):
             # training step (train_time_wi_inv.py:173-236): forward with a tape + the CUDA backward, fp32 unless the
             # caller opted in to the tensor-core training path (resolve_train_precision)
-            if pcm16:
-                raise RuntimeError("PCM_16 output is an inference feature: call it under torch.no_grad() / module.eval()")
+            if pcm16 or frames is not None:
+                raise RuntimeError("PCM_16 output / ragged batches are inference features: call them under torch.no_grad() / module.eval()")
             return _GeneratorTrainFn.apply(self, module, x, *[p for _, p in module.named_parameters()])
         if x.is_cuda:
             dev = x.device
@@ -223,6 +226,7 @@ class GeneratorEngine:
         lib = _lib.load()
         self._ensure(module, dev)
         prec = resolve_precision(precision or getattr(module, "precision", None))
+        per_item = frames
         xd = x.detach().to(dev, torch.float32).contiguous()
         batch, _, frames = xd.shape
         n_out = lib.nvse_generator_out_samples(self.handle, frames)
@@ -240,9 +244,18 @@ class GeneratorEngine:
             self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            fwd = lib.nvse_generator_forward_pcm16 if pcm16 else lib.nvse_generator_forward
-            _lib.check(fwd(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
-                           _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
+            if per_item is not None:
+                if pcm16:
+                    raise RuntimeError("ragged batches deliver float output (quantise with Vocoder.pcm16)")
+                fd = torch.as_tensor(per_item).to(dev, torch.int32).contiguous()
+                if fd.shape != (batch,) or (batch and (int(fd.min()) < 1 or int(fd.max()) > frames)):
+                    raise RuntimeError(f"frames must be an int tensor [{batch}] with values in [1, {frames}]")
+                _lib.check(lib.nvse_generator_forward_ragged(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(fd), _lib.ptr(out),
+                                                             _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
+            else:
+                fwd = lib.nvse_generator_forward_pcm16 if pcm16 else lib.nvse_generator_forward
+                _lib.check(fwd(self.handle, _lib.ptr(xd), batch, frames, _lib.ptr(out),
+                               _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
         return out if x.is_cuda else out.to(x.device)
 
     # ---- training ---------------------------------------------------------------------

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "nvse_frontend_destroy": (_i, [_vp]),
     "nvse_frontend_num_frames": (_i64, [_vp, _i64]),
     "nvse_frontend_mel_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "nvse_frontend_mel_ragged_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "nvse_frontend_stft_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nvse_inverse_mel_f32": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i64, _vp]),
     "nvse_frontend_backward_scratch_bytes": (_sz, [_vp, _i64, _i64]),
@@ -67,6 +68,7 @@ PROTOTYPES = {
     "nvse_generator_workspace_bytes": (_sz, [_vp, _i64, _i64, _i]),
     "nvse_generator_forward": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _i, _vp]),
     "nvse_generator_forward_pcm16": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _i, _vp]),
+    "nvse_generator_forward_ragged": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _i, _vp]),
     "nvse_weight_norm_fold_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "nvse_pcm16_from_f32": (_i, [_vp, _vp, _i64, _vp]),
     "nvse_transpose_bct_to_btc_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _vp]),

@@ -66,6 +66,19 @@ __host__ __device__ inline int64_t t32_off(int64_t t, int c, int C) {
 }
 __host__ __device__ inline int64_t t32_rows(int64_t T) { return (T + 31) / 32 * 32; }
 
+// Per-utterance valid row counts of a padded (ragged) batch: utterance b has min(T, lens[b] * mul + add) valid rows at this
+// stage (lens = mel frames per utterance on the device; every stage's length is an affine function of it), T when lens is
+// null.  Rows at or beyond it are treated exactly like rows beyond T: they read as zero (the convolutions' zero padding).
+struct RowLens {
+  const int* lens;
+  int mul, add;
+};
+__device__ __forceinline__ int valid_rows(const RowLens& l, int64_t b, int T) {
+  if (!l.lens) return T;
+  const int v = l.lens[b] * l.mul + l.add;
+  return v < T ? (v > 0 ? v : 0) : T;
+}
+
 constexpr int kMaxTaps = 16;
 
 // One "tap-list" convolution over channels-last activations.  A plain dilated Conv1d is a

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(POST_ROWS) conv_post1_t32_kernel(const ConvF32
   const int t = o0 + min_off + tid;   // this thread's input row
   const float* __restrict__ xb = a.x + b * a.x_bstride;
   float4 v[c4n];
-  const bool in = t >= 0 && t < a.Tin;
+  const bool in = t >= 0 && t < valid_rows(a.in_lens, b, a.Tin);
   const float4* src = reinterpret_cast<const float4*>(xb + t32_off(in ? t : 0, 0, CIN));
 #pragma unroll
   for (int c4 = 0; c4 < c4n; ++c4) v[c4] = in ? __ldg(src + 32 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // T32: 4-channel groups 128 floats apart
@@ -291,6 +291,9 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
   NVSE_REQUIRE(a.taps.ntaps >= 1 && a.taps.ntaps <= kMaxTaps, NVSE_ERR_INVALID, "conv: %d taps unsupported", a.taps.ntaps);
   NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "conv: batch %lld exceeds 65535 per launch", (long long)B);
   if (B == 0 || a.Trows <= 0) return NVSE_OK;
+  const bool post_t32 = a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 &&
+                        (a.Cin == 16 || a.Cin == 32 || a.Cin == 64);
+  NVSE_REQUIRE(!a.in_lens.lens || post_t32, NVSE_ERR_UNSUPPORTED, "fp32 conv: per-utterance lengths are only implemented by the T32 conv_post kernel");
   int min_off = a.taps.off[0], max_off = a.taps.off[0];
   for (int i = 1; i < a.taps.ntaps; ++i) {
     min_off = std::min(min_off, a.taps.off[i]);

@@ -34,6 +34,7 @@ struct ConvF32Args {
   int in_stride;         // input row of tap i = max(in_stride, 1) * t + off[i]  (dgrad of a ConvTranspose1d)
   const float* mask;     // same shape as y, or null:  conv *= (mask > 0 ? 1 : mask_slope)  before `residual` is added
   float mask_slope;
+  RowLens in_lens;       // ragged batch (T32 conv_post kernel only): valid input rows per utterance; null lens: Tin
 };
 
 int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st);

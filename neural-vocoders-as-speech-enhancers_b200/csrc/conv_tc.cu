@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
 
   // ---- stage the activation tile (all warps): lrelu + bf16 + K-major core-matrix layout ------
   {
+    const int Tin_b = valid_rows(a.in_lens, b, a.Tin);  // this utterance's valid rows (ragged batches)
     const int items = k.rows * nchunk;
     const int cshift = 31 - __clz(nchunk);
     if (a.in_bf16) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
           const int t = t0 + k.min_off + r;
           dst[u] = e < items ? (chunk * k.rows_pad + r) * 16 : -1;
           v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (e < items && t >= 0 && t < a.Tin) v[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)t * Cin + chunk * 8));
+          if (e < items && t >= 0 && t < Tin_b) v[u] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)t * Cin + chunk * 8));
         }
 #pragma unroll
         for (int u = 0; u < kStageUnroll; ++u)
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
           const int t = t0 + k.min_off + r;
           dst[u] = e < items ? (chunk * k.rows_pad + r) * 16 : -1;
           f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < items && t >= 0 && t < a.Tin && !(k.dbg & 2)) {
+          if (e < items && t >= 0 && t < Tin_b && !(k.dbg & 2)) {
             const float4* src = reinterpret_cast<const float4*>(xb + (a.x_t32 ? t32_off(t, chunk * 8, Cin) : (int64_t)t * Cin + chunk * 8));
             f0[u] = __ldg(src);
             f1[u] = __ldg(src + (a.x_t32 ? 32 : 1));
@@ -334,10 +335,10 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_tc_kernel(const __grid_co
                 if (!(mq.z > 0.0f)) o.z *= a.mask_slope;
                 if (!(mq.w > 0.0f)) o.w *= a.mask_slope;
               }
-              o.x = (o.x + rq[q].x) * a.out_scale + yq[q].x;
-              o.y = (o.y + rq[q].y) * a.out_scale + yq[q].y;
-              o.z = (o.z + rq[q].z) * a.out_scale + yq[q].z;
-              o.w = (o.w + rq[q].w) * a.out_scale + yq[q].w;
+              o.x = __fadd_rn(__fmul_rn(o.x + rq[q].x, a.out_scale), yq[q].x);
+              o.y = __fadd_rn(__fmul_rn(o.y + rq[q].y, a.out_scale), yq[q].y);
+              o.z = __fadd_rn(__fmul_rn(o.z + rq[q].z, a.out_scale), yq[q].z);
+              o.w = __fadd_rn(__fmul_rn(o.w + rq[q].w, a.out_scale), yq[q].w);
               *reinterpret_cast<float4*>(yr + qs * q) = o;
             }
           }

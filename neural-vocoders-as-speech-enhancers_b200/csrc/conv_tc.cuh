@@ -41,6 +41,7 @@ struct ConvTcArgs {
   float mask_slope;       //   is added (the leaky_relu derivative of the layer input); fp32 channels-last output only
   int ops_f16;            // stage the (fp32) activations as IEEE half; `wimg` must then be a half image.  Used by the
                           // upsamplers, where bf16 rounding of the WEIGHTS is the largest error of the whole path
+  RowLens in_lens;        // ragged batch: valid INPUT rows per utterance (rows beyond read as zero); lens == null: Tin
 };
 
 // shared memory one CTA of the kernel needs for this shape (used to decide whether split fits)

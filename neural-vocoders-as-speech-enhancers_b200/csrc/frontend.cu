@@ -246,6 +246,7 @@ struct Frontend2Params {
   int nyquist;               // bin 512 carries mel weight
   const int4* items;         // mel projection work items: (mel row, first tap, taps, slices of the row | slice index << 8)
   int nitems;                // padded so that the slices of a row never straddle a warp
+  const int* lens;           // ragged batch: samples per utterance (<= T; reflect padding and frame count follow it), or null
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -267,16 +268,17 @@ __device__ __forceinline__ void fe2_stage(const Frontend2Params& q, int64_t g, f
   const FrontendParams& p = q.f;
   const int64_t b = g / q.groups;
   const int64_t f0 = (g - b * q.groups) * kFe2Frames;
-  const int nf = (int)((p.F - f0) < kFe2Frames ? (p.F - f0) : kFe2Frames);
+  const int64_t Tb = q.lens ? (q.lens[b] < p.T ? q.lens[b] : p.T) : p.T, Fb = 1 + Tb / p.hop;  // this utterance's samples / frames
+  const int nf = (int)((Fb - f0) < kFe2Frames ? (Fb - f0) : kFe2Frames);
   const float* __restrict__ yrow = p.y + b * p.y_stride;
   const int64_t s0 = f0 * p.hop - kNfft / 2;  // un-padded sample index of staged sample 0
-  if (s0 >= 0 && s0 + q.nsmp <= p.T && ((reinterpret_cast<uintptr_t>(yrow + s0) & 15) == 0)) {
+  if (s0 >= 0 && s0 + q.nsmp <= Tb && ((reinterpret_cast<uintptr_t>(yrow + s0) & 15) == 0)) {
     for (int i = tid * 4; i + 3 < q.nsmp; i += kFe2Threads * 4) cp_async16(ssmp + i, yrow + s0 + i);
     for (int i = (q.nsmp & ~3) + tid; i < q.nsmp; i += kFe2Threads) ssmp[i] = __ldg(yrow + s0 + i);
   } else {
     const int need = (nf - 1) * p.hop + kNfft;  // samples the existing frames cover; the rest is never stored
     for (int i = tid; i < q.nsmp; i += kFe2Threads) {  // element-wise, still asynchronous
-      if (i < need) cp_async4(ssmp + i, yrow + reflect_index(s0 + i, p.T));
+      if (i < need) cp_async4(ssmp + i, yrow + reflect_index(s0 + i, Tb));
       else ssmp[i] = 0.0f;
     }
   }
@@ -298,7 +300,8 @@ __global__ void __launch_bounds__(kFe2Threads, 4) mel_frontend2_kernel(const Fro
   for (; g < q.total; g += gridDim.x) {
     const int64_t b = g / q.groups;
     const int64_t f0 = (g - b * q.groups) * kFe2Frames;
-    const int nf = (int)((p.F - f0) < kFe2Frames ? (p.F - f0) : kFe2Frames);  // frames of this group that exist
+    const int64_t Fb = q.lens ? 1 + (q.lens[b] < p.T ? q.lens[b] : p.T) / p.hop : p.F;
+    const int nf = (int)((Fb - f0) < kFe2Frames ? (Fb - f0) : kFe2Frames);  // frames of this group that exist (<= 0: none stored)
     cp_async_wait_all();
     __syncthreads();  // samples of this group are in place; the previous group's output tile has been stored
 
@@ -1047,8 +1050,22 @@ extern "C" int64_t nvse_frontend_num_frames(const nvse_frontend* fe, int64_t T) 
   return 1 + T / fe->hop;
 }
 
+static int frontend_mel_impl(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride, const int* lens,
+                             float* out, void* stream);
+
 extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
                                      int64_t y_row_stride, float* out, void* stream) {
+  return frontend_mel_impl(fe, y, B, T, y_row_stride, nullptr, out, stream);
+}
+
+extern "C" int nvse_frontend_mel_ragged_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride,
+                                            const int32_t* samples_dev, float* out, void* stream) {
+  NVSE_REQUIRE(samples_dev, NVSE_ERR_INVALID, "nvse_frontend_mel_ragged_f32: null lengths");
+  return frontend_mel_impl(fe, y, B, T, y_row_stride, samples_dev, out, stream);
+}
+
+static int frontend_mel_impl(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride, const int* lens,
+                             float* out, void* stream) {
   using namespace nvse;
   NVSE_REQUIRE(fe && y && out, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: null argument");
   NVSE_REQUIRE(B >= 0 && y_row_stride >= T, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: bad B/stride");
@@ -1085,6 +1102,7 @@ extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, in
   q.nyquist = fe->nyquist;
   q.items = fe->items;
   q.nitems = fe->nitems;
+  q.lens = lens;
   const size_t smem2 = sizeof(float) * ((size_t)q.nsmp_pad + (size_t)kFe2Warps * 2 * kFe2Scratch);
   if (!legacy && smem2 <= 100 * 1024 && fe->n_mels <= kFe2MaxMels) {  // the staged kernel (persistent CTAs, 8 consecutive frames per step)
     static const int ctas_per_sm = [] { const char* e = std::getenv("NVSE_FE_CTAS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 4; }();
@@ -1100,6 +1118,7 @@ extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, in
     return NVSE_OK;
   }
   // very large hops: one warp per frame pair straight from global memory
+  NVSE_REQUIRE(!lens, NVSE_ERR_UNSUPPORTED, "nvse_frontend_mel_ragged_f32: per-utterance lengths need the staged kernel (hop too large)");
   const int64_t tasks = B * p.pairs;
   const int64_t ctas = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;
   NVSE_REQUIRE(ctas <= 0x7fffffff, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: problem too large for one launch");

@@ -104,7 +104,7 @@ static int run_conv(const Layer& L, bool tc, const ConvIO& io, int64_t B, int64_
 // path up to 8 phases share one launch: the activation tile is staged once and the phases ping-pong
 // between two TMEM accumulators.
 int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
-                       cudaStream_t st, bool x_t32, bool y_t32) {
+                       cudaStream_t st, bool x_t32, bool y_t32, RowLens in_lens) {
   const int64_t Tout = (Tin - 1) * L.stride - 2 * L.padding + L.k;
   const int nph = (int)std::min<int64_t>(L.stride, Tout);
   static const bool ups_env = [] { const char* e = std::getenv("NVSE_UPS_TC"); return !(e && e[0] == '0'); }();
@@ -113,6 +113,7 @@ int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64
     UpsTcArgs a{};
     a.x = x; a.x_cl = x_t32 ? 0 : 1; a.x_bstride = (x_t32 ? t32_rows(Tin) : Tin) * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin; a.Cout = L.Cout; a.stride = L.stride;
     a.wimg = L.w_ups; a.bias = L.bias; a.y = y; a.y_bstride = t32_rows(Tout) * L.Cout; a.in_slope = in_slope;
+    a.in_lens = in_lens;
     return launch_ups_tc(a, B, st);
   }
   if (tc && L.w_bf16) {
@@ -134,11 +135,12 @@ int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64
       a.out_mul = L.stride; a.Trows = (int)((Tout - r0 + L.stride - 1) / L.stride);
       a.in_slope = in_slope; a.out_slope = 1.0f; a.out_scale = 1.0f;
       a.split_act = L.tc_split && !L.tc_f16;
+      a.in_lens = in_lens;
       if (int rc = launch_conv_tc_phases(a, taps, out_add, n, B, st)) return rc;
     }
     return NVSE_OK;
   }
-  NVSE_REQUIRE(!x_t32 && !y_t32, NVSE_ERR_STATE, "ConvTranspose1d %s: the T32 layout needs the tensor-core path", L.name.c_str());
+  NVSE_REQUIRE(!x_t32 && !y_t32 && !in_lens.lens, NVSE_ERR_STATE, "ConvTranspose1d %s: the T32 layout / ragged batches need the tensor-core path", L.name.c_str());
   for (int r = 0; r < nph; ++r) {
     ConvF32Args a{};
     a.x = x; a.x_bstride = Tin * L.Cin; a.Tin = (int)Tin; a.Cin = L.Cin;
@@ -180,8 +182,11 @@ int ensure_side_streams(nvse_generator* g) {
 
 // out_i16 != null: the waveform is wanted as PCM_16 (int16) INSTEAD of float: fused into conv_post where the last
 // kernel is the T32 conv_post kernel (HiFiGAN on the tensor-core plan), a separate quantisation pass otherwise.
+// frames_dev != null (ragged batch): mel frames per utterance on the device; utterance b is computed exactly as if it were
+// alone with frames_dev[b] frames (every kernel treats its rows beyond that like rows beyond the end of the sequence); its
+// output samples beyond its own length are undefined.  Tensor-core HiFiGAN plan only.
 static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B, int64_t F, float* out, float* ws,
-                        int64_t buf_elems, int nbuf, cudaStream_t st, int16_t* out_i16 = nullptr) {
+                        int64_t buf_elems, int nbuf, cudaStream_t st, int16_t* out_i16 = nullptr, const int* frames_dev = nullptr) {
   const nvse_generator_config& c = g->cfg;
   float* bufA = ws;  // conv_pre output, then the MRF accumulator of every stage
   float* bufU = ws + buf_elems;
@@ -205,9 +210,11 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
         conv1d_taps(pre.k, 1, &a.taps);
         a.out_mul = 1; a.out_add = 0; a.Trows = (int)F;
         a.in_slope = 1.0f; a.out_slope = 1.0f; a.out_scale = 1.0f;
+        a.in_lens = RowLens{frames_dev, 1, 0};
         if (int rc = launch_conv_tc(a, B, st)) return rc;
       }
     } else {
+      NVSE_REQUIRE(!frames_dev, NVSE_ERR_UNSUPPORTED, "ragged batches need conv_pre on the tensor cores");
       if (int rc = launch_transpose(mel, bufR, B, c.in_channels, F, st)) return rc;
       const ConvIO io{bufR, false, nullptr, bufA, false, 1.0f, 1.0f, 1.0f, 0};
       if (int rc = run_conv(pre, false, io, B, F, st)) return rc;
@@ -248,11 +255,16 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
       per_launch[(size_t)i * c.num_kernels + j] = per;
     }
   }
+  NVSE_REQUIRE(!frames_dev || (t32 && c.kind == NVSE_GEN_HIFIGAN), NVSE_ERR_UNSUPPORTED,
+               "ragged batches are implemented on the fused tensor-core HiFiGAN plan only");
+  RowLens lens{frames_dev, 1, 0};  // valid rows per utterance at the current stage (affine in the frame count)
   int64_t T = F;
   for (int i = 0; i < c.num_upsamples; ++i) {
     const Layer& up = g->layer("ups." + std::to_string(i));
-    if (int rc = run_conv_transpose(up, tc, bufA, B, T, bufU, slope, st, t32 && i > 0, t32)) return rc;  // hifigan.py:111-112
+    if (int rc = run_conv_transpose(up, tc, bufA, B, T, bufU, slope, st, t32 && i > 0, t32, lens)) return rc;  // hifigan.py:111-112
     T = (T - 1) * up.stride - 2 * up.padding + up.k;
+    lens.mul *= up.stride;
+    lens.add = lens.add * up.stride + (up.k - up.stride - 2 * up.padding);
     const bool stage_concurrent = t32 && nbuf >= 12 && B * T <= kConcurrentRows;
     if (stage_concurrent) {
       if (int rc = ensure_side_streams(g)) return rc;
@@ -281,6 +293,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
           ra.t32 = 1; ra.bstride = t32_rows(T) * l0.Cin;
           ra.slope = slope; ra.out_scale = last ? inv : 1.0f; ra.accumulate = last && j > 0 && !conc;
           ra.h_fp16 = l0.Cin <= 32;  // the c1 -> c2 intermediate and w2 in IEEE half (see finalize_bf16)
+          ra.lens = lens;
           for (int q = 0; q < per; ++q) {
             const Layer& c1 = g->layer(p + ".convs1." + std::to_string(m0 + q));
             const Layer& c2 = g->layer(p + ".convs2." + std::to_string(m0 + q));
@@ -334,6 +347,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   a.w = post.w; a.bias = post.bias; a.Cout = post.Cout;
   conv1d_taps(post.k, 1, &a.taps);
   a.out_mul = 1; a.out_add = 0; a.in_slope = 0.01f; a.out_scale = 1.0f;  // F.leaky_relu default slope, hifigan.py:120
+  a.in_lens = lens;
   if (c.kind == NVSE_GEN_HIFIGAN) {  // hifigan.py:120-124
     a.Tin = a.Tout = a.Trows = (int)T; a.y = out; a.y_bstride = T * post.Cout; a.out_act = 1;
     if (out_i16) {
@@ -553,6 +567,23 @@ extern "C" int nvse_generator_forward(nvse_generator* g, const float* mel, int64
   float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, out, ws, buf_elems,
                       workspace_buffers(g, B, frames, precision), as_stream(stream));
+}
+
+extern "C" int nvse_generator_forward_ragged(nvse_generator* g, const float* mel, int64_t B, int64_t frames, const int32_t* frames_dev,
+                                             float* out, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  NVSE_REQUIRE(g && mel && out && frames_dev, NVSE_ERR_INVALID, "nvse_generator_forward_ragged: null argument");
+  NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_generator_forward_ragged: call nvse_generator_finalize first");
+  NVSE_REQUIRE(B >= 0 && frames >= 1, NVSE_ERR_INVALID, "nvse_generator_forward_ragged: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
+  NVSE_REQUIRE(precision == NVSE_PRECISION_BF16, NVSE_ERR_UNSUPPORTED, "nvse_generator_forward_ragged: the 16-bit tensor-core path only");
+  if (B == 0) return NVSE_OK;
+  if (int rc = tc_abort_poll(as_stream(stream))) return rc;
+  const size_t need = nvse_generator_workspace_bytes(g, B, frames, precision);
+  NVSE_REQUIRE(workspace && workspace_bytes >= need, NVSE_ERR_INVALID, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  NVSE_REQUIRE(max_activation_elems(g, frames) * 4 < (int64_t)1 << 40, NVSE_ERR_INVALID, "utterance too long");
+  const int64_t buf_elems = (int64_t)(align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256) / sizeof(float));
+  float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  return forward_impl(g, true, mel, B, frames, out, ws, buf_elems, workspace_buffers(g, B, frames, precision), as_stream(stream), nullptr,
+                      frames_dev);
 }
 
 extern "C" int nvse_generator_forward_pcm16(nvse_generator* g, const float* mel, int64_t B, int64_t frames, int16_t* out,

@@ -58,7 +58,7 @@ int launch_unpad_reflect_left(const float* dy, float* dx, int64_t B, int64_t T, 
 
 // ConvTranspose1d layer (polyphase): tensor cores (IEEE-half operands) when tc and the layer has an image, else fp32
 int run_conv_transpose(const Layer& L, bool tc, const float* x, int64_t B, int64_t Tin, float* y, float in_slope,
-                       cudaStream_t st, bool x_t32 = false, bool y_t32 = false);
+                       cudaStream_t st, bool x_t32 = false, bool y_t32 = false, RowLens in_lens = RowLens{nullptr, 1, 0});
 int ensure_side_streams(nvse_generator* g);  // g->side[], ev_fork, ev_join[]: the ResBlocks of an MRF run concurrently
 int finalize_plan(nvse_generator* g);                    // allocates the tensor-core image buffers, sets the per-layer precision flags
 int finalize_bf16(nvse_generator* g, cudaStream_t st);  // finalize_plan + builds the tensor-core weight images

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
       const int ub = item / k.tiles_per_seq, tx = item - ub * k.tiles_per_seq;
       const int t_in0 = tx * k.V - k.halo;
       const float* xb = a.x + (int64_t)ub * bstride;
+      const int Tb = valid_rows(a.lens, ub, a.T);  // this utterance's valid rows (ragged batches)
       uint8_t* op = op0 + (size_t)b * op_bytes;
       if (lw == 0) PT_STAMP(2);
       if (i >= 2 && !wait_warp(bar_op_free + 8 * b, (uint32_t)((i >> 1) - 1) & 1u)) break;  // c2(i-2) has read OP[b]
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
           const int e = e0 + u * (kLoadWarps * 32);
           const int chunk = e / rows_all, orow = e - chunk * rows_all, t = t_in0 + orow - k.P;
           f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < units && t >= 0 && t < a.T) {
+          if (e < units && t >= 0 && t < Tb) {
             const float4* src = reinterpret_cast<const float4*>(xb + t32_off(t, chunk * 8, C));
             f0[u] = __ldg(src);
             f1[u] = __ldg(src + 32);
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
       const int item = (int)blockIdx.x + i * (int)gridDim.x;
       const int ub = item / k.tiles_per_seq, tx = item - ub * k.tiles_per_seq;
       const int t_in0 = tx * k.V - k.halo;
+      const int Tb = valid_rows(a.lens, ub, a.T);
       uint8_t* op = op0 + (size_t)b * op_bytes;
       // epi1: OP[b] = bf16(lrelu(ACC1 + b1)), zero outside the sequence
       if (!wait_warp(bar_acc1, (uint32_t)i & 1u)) break;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
         tmem_ld_32x16(tmem_acc1 + lane_sel + (uint32_t)(jt * C + c0), v);
         tmem_ld_wait();
         uint32_t hi[8];
-        const bool inb = t >= 0 && t < a.T;
+        const bool inb = t >= 0 && t < Tb;
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
           const float a0 = lrelu(__uint_as_float(v[2 * w]) + b1[c0 + 2 * w], slope);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
         for (int u = 0; u < U; ++u) {
           const int it = i0 + u, c0 = ((it % CPW) * 2 + h) * 16;
           const int r = (it / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
-          const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+          const bool valid = r >= k.halo && r < R - k.halo && t < Tb;
           const int64_t off = (int64_t)ub * bstride + t32_off(t, c0, C);
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
         for (int u = 0; u < U; ++u) {
           const int it = i0 + u, c0 = ((it % CPW) * 2 + h) * 16, jt = it / CPW;
           const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
-          const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+          const bool valid = r >= k.halo && r < R - k.halo && t < Tb;
           uint32_t v[16];
           tmem_ld_32x16(tmem_acc2 + lane_sel + (uint32_t)(jt * C + c0), v);
           tmem_ld_wait();
@@ -316,10 +318,10 @@ __global__ void __launch_bounds__(kThreads, 1) pair_tc_kernel(const __grid_const
             for (int w = 0; w < 4; ++w) {
               const float4 bq = *reinterpret_cast<const float4*>(b2 + c0 + 4 * w);
               float4 o;
-              o.x = (__uint_as_float(v[4 * w]) + bq.x + xq[u][w].x) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].x : 0.f);
-              o.y = (__uint_as_float(v[4 * w + 1]) + bq.y + xq[u][w].y) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].y : 0.f);
-              o.z = (__uint_as_float(v[4 * w + 2]) + bq.z + xq[u][w].z) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].z : 0.f);
-              o.w = (__uint_as_float(v[4 * w + 3]) + bq.w + xq[u][w].w) * a.out_scale + (ACCUM ? yq[ACCUM ? u : 0][w].w : 0.f);
+              o.x = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w]) + bq.x + xq[u][w].x, a.out_scale), (ACCUM ? yq[ACCUM ? u : 0][w].x : 0.f));
+              o.y = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 1]) + bq.y + xq[u][w].y, a.out_scale), (ACCUM ? yq[ACCUM ? u : 0][w].y : 0.f));
+              o.z = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 2]) + bq.z + xq[u][w].z, a.out_scale), (ACCUM ? yq[ACCUM ? u : 0][w].z : 0.f));
+              o.w = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 3]) + bq.w + xq[u][w].w, a.out_scale), (ACCUM ? yq[ACCUM ? u : 0][w].w : 0.f));
               dst[w * 32] = o;
             }
           }

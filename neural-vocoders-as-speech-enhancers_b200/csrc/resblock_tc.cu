@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
   const int64_t bstride = a.bstride;
   const int ws4 = a.t32 ? 32 : 1;  // float4 stride between the 4-channel groups of one row
   const int t_in0 = (int)blockIdx.x * k.V - k.halo;  // time index of tile row 0
+  const int Tb = valid_rows(a.lens, b, a.T);            // this utterance's valid rows (ragged batches)
   const uint32_t op_bytes = (((uint32_t)nchunk * k.rows_pad * 16u) + 127u) & ~127u;
   constexpr uint32_t tap_bytes = (uint32_t)KC * C * 2u, stage_bytes = TPS * tap_bytes;
   uint8_t* op = smem_raw;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         const int orow = i < k.P0 ? k.P - k.P0 + i : k.P + R + (i - k.P0);  // operand-buffer row
         const int t = t_in0 + orow - k.P;
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-        if (t >= 0 && t < a.T) {
+        if (t >= 0 && t < Tb) {
           const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, chunk * 8, C) : (int64_t)t * C + chunk * 8));
           const float4 f0 = __ldg(src), f1 = __ldg(src + ws4);
           pk.x = pack_bf16(lrelu(f0.x, slope), lrelu(f0.y, slope));
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16;
         const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
         const float4* src = reinterpret_cast<const float4*>(a.x + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
-        const bool inb = t >= 0 && t < a.T;
+        const bool inb = t >= 0 && t < Tb;
 #pragma unroll
         for (int w = 0; w < 4; ++w) v[u][w] = inb ? __ldg(src + w * ws4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
 #pragma unroll
         for (int w = 0; w < 16; ++w) bits[w] = __float_as_uint(f[w]);
         tmem_st_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), bits);
-        store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+        store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < Tb);
       }
     }
     tmem_st_wait();
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
 #pragma unroll
         for (int i = 0; i < IT; ++i) {
           const int c0 = ((i % CPW) * 2 + h) * 16, t = nt0 + (i / CPW) * kTileM + q * 32 + lane;
-          if (t >= 0 && t < a.T) {
+          if (t >= 0 && t < Tb) {
             const float* src = a.x + (int64_t)nb * bstride + t32_off(t, c0, C);
 #pragma unroll
             for (int w = 0; w < 4; ++w) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + w * 128));
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
             f[4 * u + 2] = __uint_as_float(v[i & 1][4 * u + 2]) + bq.z;
             f[4 * u + 3] = __uint_as_float(v[i & 1][4 * u + 3]) + bq.w;
           }
-          store_operand<H16>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+          store_operand<H16>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < Tb);
         }
       }
       fence_proxy_async_smem();
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
               f[4 * u + 2] = __uint_as_float(v[i & 1][4 * u + 2]) + bq.z;
               f[4 * u + 3] = __uint_as_float(v[i & 1][4 * u + 3]) + bq.w;
             }
-            store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+            store_operand<false>(op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < Tb);
           }
         }
         fence_proxy_async_smem();
@@ -394,7 +395,9 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         if (lane == 0) mbar_arrive(bar_op);
         RB_WSTAMP();
       } else {
-        // final: y = [y +] out_scale * (X + cb_last) for the central V rows
+        // final: y = [y +] out_scale * (X + cb_last) for the central V rows.  The product is rounded before the sum (no FMA): the
+        // MRF total is then (r0/3 + r1/3) + r2/3 with every term rounded, bit-identical to the small-job mode, where the three
+        // ResBlocks write their own buffers and add3 sums them -- a batch's results must not depend on which mode its size selects
 #pragma unroll
         for (int i0 = 0; i0 < IT; i0 += U) {
           float4 yq[U][4];
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
           for (int u = 0; u < U; ++u) {
             const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16;
             const int r = (i / CPW) * kTileM + q * 32 + lane, t = t_in0 + r;
-            const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+            const bool valid = r >= k.halo && r < R - k.halo && t < Tb;
             const float4* src = reinterpret_cast<const float4*>(a.y + b * bstride + (a.t32 ? t32_off(t, c0, C) : (int64_t)t * C + c0));
 #pragma unroll
             for (int w = 0; w < 4; ++w) yq[u][w] = (valid && a.accumulate) ? src[w * ws4] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
           for (int u = 0; u < U; ++u) {
             const int i = i0 + u, c0 = ((i % CPW) * 2 + h) * 16, jt = i / CPW;
             const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
-            const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+            const bool valid = r >= k.halo && r < R - k.halo && t < Tb;
             uint32_t v[16];
             tmem_ld_32x16(tmem_x + lane_sel + (uint32_t)(jt * C + c0), v);
             tmem_ld_wait();
@@ -421,10 +424,10 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
               for (int w = 0; w < 4; ++w) {
                 const float4 bq = *reinterpret_cast<const float4*>(cb + c0 + 4 * w);
                 float4 o;
-                o.x = (__uint_as_float(v[4 * w]) + bq.x) * a.out_scale + yq[u][w].x;
-                o.y = (__uint_as_float(v[4 * w + 1]) + bq.y) * a.out_scale + yq[u][w].y;
-                o.z = (__uint_as_float(v[4 * w + 2]) + bq.z) * a.out_scale + yq[u][w].z;
-                o.w = (__uint_as_float(v[4 * w + 3]) + bq.w) * a.out_scale + yq[u][w].w;
+                o.x = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w]) + bq.x, a.out_scale), yq[u][w].x);
+                o.y = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 1]) + bq.y, a.out_scale), yq[u][w].y);
+                o.z = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 2]) + bq.z, a.out_scale), yq[u][w].z);
+                o.w = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 3]) + bq.w, a.out_scale), yq[u][w].w);
                 dst[w * ws4] = o;
               }
             }
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     auto load_issue = [&](int set, int jt, float4 (&v)[CPW][4]) {
       const int64_t b = set / ntx;
       const int t = (set - (int)b * ntx) * k.V - k.halo + jt * kTileM + q * 32 + lane;
-      const bool inb = t >= 0 && t < a.T;
+      const bool inb = t >= 0 && t < valid_rows(a.lens, b, a.T);
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
         const int c0 = (ci * 2 + h) * 16;
@@ -646,6 +649,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
     auto load_commit = [&](int set, int jt, const float4 (&v)[CPW][4]) {
       const int64_t b = set / ntx;
       const int t_in0 = (set - (int)b * ntx) * k.V - k.halo;
+      const int Tb = valid_rows(a.lens, b, a.T);
       if (jt == 0 || jt == n - 1) {
         const float* xb = a.x + b * bstride;
         for (int e = (warp * 32 + lane); e < k.P0 * nchunk; e += kWorkWarps * 32) {
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
           const int orow = jt == 0 ? k.P - k.P0 + i : k.P + R + i;  // operand-buffer row
           const int t = t_in0 + orow - k.P;
           uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-          if (t >= 0 && t < a.T) {
+          if (t >= 0 && t < Tb) {
             const float4* src = reinterpret_cast<const float4*>(xb + (a.t32 ? t32_off(t, chunk * 8, C) : (int64_t)t * C + chunk * 8));
             const float4 f0 = __ldg(src), f1 = __ldg(src + ws4);
             pk.x = pack_bf16(lrelu(f0.x, slope), lrelu(f0.y, slope));
@@ -665,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
         }
       }
       const int r = jt * kTileM + q * 32 + lane, t = t_in0 + r;
-      const bool inb = t >= 0 && t < a.T;
+      const bool inb = t >= 0 && t < Tb;
 #pragma unroll
       for (int ci = 0; ci < CPW; ++ci) {
         const int c0 = (ci * 2 + h) * 16;
@@ -724,6 +728,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
       const bool has_next = next < nsets;
       const int64_t b = set / ntx;
       const int t_in0 = (set - (int)b * ntx) * k.V - k.halo;
+      const int Tb = valid_rows(a.lens, b, a.T);
       for (int l = 0; l < L && alive; ++l, ++tphase) {
         const int m = l >> 1, c2 = l & 1;
         const bool last = (l == L - 1);
@@ -758,8 +763,8 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
                   f[4 * u + 2] = __uint_as_float(v[ci & 1][4 * u + 2]) + bq.z;
                   f[4 * u + 3] = __uint_as_float(v[ci & 1][4 * u + 3]) + bq.w;
                 }
-                if (c2) store_operand<false>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
-                else store_operand<H16>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < a.T);
+                if (c2) store_operand<false>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < Tb);
+                else store_operand<H16>(dst_op, k.rows_pad, k.P + r, c0, f, slope, t >= 0 && t < Tb);
               }
               fence_proxy_async_smem();
               tc_fence_before();
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
               float4 nx[CPW][4];
               if (has_next) load_issue(next, jt, nx);
               // final: y = [y +] out_scale * (X + cb_last) for the central V rows
-              const bool valid = r >= k.halo && r < R - k.halo && t < a.T;
+              const bool valid = r >= k.halo && r < R - k.halo && t < Tb;
               float4 yq[CPW][4];
 #pragma unroll
               for (int ci = 0; ci < CPW; ++ci) {
@@ -791,10 +796,10 @@ __global__ void __launch_bounds__(kThreads, (2 * NT * C <= 256) ? 2 : 1) resbloc
                   for (int w = 0; w < 4; ++w) {
                     const float4 bq = *reinterpret_cast<const float4*>(bias + c0 + 4 * w);
                     float4 o;
-                    o.x = (__uint_as_float(v[4 * w]) + bq.x) * a.out_scale + yq[ci][w].x;
-                    o.y = (__uint_as_float(v[4 * w + 1]) + bq.y) * a.out_scale + yq[ci][w].y;
-                    o.z = (__uint_as_float(v[4 * w + 2]) + bq.z) * a.out_scale + yq[ci][w].z;
-                    o.w = (__uint_as_float(v[4 * w + 3]) + bq.w) * a.out_scale + yq[ci][w].w;
+                    o.x = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w]) + bq.x, a.out_scale), yq[ci][w].x);
+                    o.y = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 1]) + bq.y, a.out_scale), yq[ci][w].y);
+                    o.z = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 2]) + bq.z, a.out_scale), yq[ci][w].z);
+                    o.w = __fadd_rn(__fmul_rn(__uint_as_float(v[4 * w + 3]) + bq.w, a.out_scale), yq[ci][w].w);
                     dst[w * ws4] = o;
                   }
                 }

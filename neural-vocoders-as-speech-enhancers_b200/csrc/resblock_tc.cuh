@@ -30,6 +30,7 @@ struct ResblockTcArgs {
   int accumulate;
   int h_fp16;        // the c1 -> c2 intermediate and the w2 images are IEEE half instead of bf16 (same range of values,
                      // three more mantissa bits): where rounding of that intermediate costs the most SNR (tests/bf16_budget.py)
+  RowLens lens;      // ragged batch: valid rows per utterance (rows beyond are zero, like rows beyond T); null lens: T
 };
 
 // true when the fused kernel handles this shape (otherwise the caller uses the per-layer kernels)

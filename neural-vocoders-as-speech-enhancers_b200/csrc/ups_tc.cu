@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ups_tc_kernel(const __grid_con
       const int64_t b = tile / k.ntx;
       const int t0 = (tile - (int)b * k.ntx) * kTileM;
       const float* xb = a.x + b * a.x_bstride;
+      const int Tin_b = valid_rows(a.in_lens, b, a.Tin);
       uint8_t* dstb = abuf + (size_t)buf * a_bytes;
       const int rows = kTileM + 2, items = rows * nchunk;
       for (int e0 = wtid; e0 < items; e0 += kWorkWarps * 32 * kStageUnroll) {
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ups_tc_kernel(const __grid_con
             const int t = t0 - 1 + r;
             dst[u] = e < items ? (chunk * kRowsPad + r) * 16 : -1;
             f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < items && t >= 0 && t < a.Tin) {
+            if (e < items && t >= 0 && t < Tin_b) {
               const float4* src = reinterpret_cast<const float4*>(xb + (int64_t)t * Cin + chunk * 8);
               f0[u] = __ldg(src);
               f1[u] = __ldg(src + 1);
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, MINB) ups_tc_kernel(const __grid_con
             const int t = t0 - 1 + r;
             dst[u] = e < items ? (chunk * kRowsPad + r) * 16 : -1;
             f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < items && t >= 0 && t < a.Tin) {
+            if (e < items && t >= 0 && t < Tin_b) {
               const float4* src = reinterpret_cast<const float4*>(xb + t32_off(t, chunk * 8, Cin));
               f0[u] = __ldg(src);
               f1[u] = __ldg(src + 32);

@@ -16,6 +16,7 @@ struct UpsTcArgs {
   float* y;            // [B][t32_rows(stride * Tin)][Cout] fp32, T32 layout
   int64_t y_bstride;
   float in_slope;
+  RowLens in_lens;     // ragged batch: valid input rows per utterance (null lens: Tin)
   int x_cl;            // x is channels-last [B][Tin][Cin] instead of T32 (stride 8 only: the first upsampler reads conv_pre's output)
 };
 

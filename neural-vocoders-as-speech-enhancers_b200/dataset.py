@@ -66,13 +66,19 @@ def _frontend(sampling_rate, n_fft, num_mels, hop_size, win_size, fmin, fmax, ba
 
 
 def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax,
-                    center=True, in_dataset=False):
+                    center=True, in_dataset=False, *, lengths=None):
     """log-mel spectrogram ``[B, num_mels, 1 + T // hop_size]`` (or ``[num_mels, F]`` for 1-D
     input) of ``y``.  ``center`` is accepted and ignored exactly as in the reference, which
-    always calls ``torch.stft(center=True)`` (dataset.py:62 vs :84)."""
+    always calls ``torch.stft(center=True)`` (dataset.py:62 vs :84).
+
+    ``lengths`` (extension, keyword-only, inference): int tensor ``[B]`` of samples per utterance for a batch padded to
+    the longest one.  Utterance ``b`` gets the log-mel of its own ``lengths[b]`` samples (reflect padding at its own end),
+    bit-identical to a single-utterance call, in frames ``[0, 1 + lengths[b] // hop_size)``; later frames are undefined."""
     global mel_window
     if y.dim() not in (1, 2):
         raise RuntimeError(f"mel_spectrogram expects a 1-D or 2-D waveform tensor, got {tuple(y.shape)}")
+    if lengths is not None and (y.dim() != 2 or (torch.is_grad_enabled() and y.requires_grad)):
+        raise RuntimeError("mel_spectrogram(lengths=...) takes a 2-D batch and is an inference feature")
     if torch.is_grad_enabled() and y.requires_grad:  # the mel-L1 loss of the trainer (train_time_wi_inv.py:173-179,231-235)
         return _MelFn.apply(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, in_dataset)
     out_device = torch.device("cpu") if in_dataset else y.device
@@ -98,8 +104,18 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     lib = _lib.load()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib.nvse_frontend_mel_f32(fe, _lib.ptr(yd), batch, samples, yd.stride(0) if batch > 1 else samples,
-                                             _lib.ptr(out), C.c_void_p(stream)))
+        if lengths is not None:
+            ld = torch.as_tensor(lengths).to(dev, torch.int32).contiguous()
+            if ld.shape != (batch,):
+                raise RuntimeError(f"lengths must have shape [{batch}], got {tuple(ld.shape)}")
+            if batch and (int(ld.min()) <= n_fft // 2 or int(ld.max()) > samples):
+                raise RuntimeError(f"lengths must lie in ({n_fft // 2}, {samples}] (reflect padding needs more than n_fft/2 samples)")
+            out.zero_()  # frames beyond an utterance's own are not written by the kernel
+            _lib.check(lib.nvse_frontend_mel_ragged_f32(fe, _lib.ptr(yd), batch, samples, yd.stride(0) if batch > 1 else samples,
+                                                        _lib.ptr(ld), _lib.ptr(out), C.c_void_p(stream)))
+        else:
+            _lib.check(lib.nvse_frontend_mel_f32(fe, _lib.ptr(yd), batch, samples, yd.stride(0) if batch > 1 else samples,
+                                                 _lib.ptr(out), C.c_void_p(stream)))
     if squeeze:
         out = out[0]
     return out if out.device == out_device else out.to(out_device)

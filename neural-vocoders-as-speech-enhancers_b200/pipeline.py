@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from .dataset import mel_spectrogram
-from .shard import bucket_by_length
+from .shard import bucket_by_length, bucket_padded
 
 
 class Vocoder:
@@ -123,14 +123,38 @@ class Vocoder:
         return out_host
 
     @torch.no_grad()
-    def run_list(self, wavs):
-        """Ragged input: a list of 1-D float32 waveforms (CPU or device) -> list of 1-D CPU waveforms,
-        in the input order.  Utterances are grouped by exact length (``bucket_by_length``), so no
-        padding is involved and each result equals the single-utterance result; empty list -> []."""
+    def run_list(self, wavs, max_pad=0.25):
+        """Ragged input: a list of 1-D float32 waveforms (CPU or device) -> list of 1-D CPU waveforms, in the input order;
+        empty list -> [].  The reference vocodes such a list one utterance at a time (infers/inference_hifigan.py:67).
+        Here utterances of similar length (``bucket_padded``: at most ``max_pad`` of a batch is padding) share a batch that
+        is zero-padded to its longest member and carries the per-utterance lengths: the front-end reflects every utterance
+        at its own end and every generator kernel masks it at its own length, so each result is BIT-IDENTICAL to the
+        single-utterance result (tests/test_gpu_parity.py).  Generators without the ragged path (iSTFTNet, fp32 precision)
+        fall back to groups of exactly equal length."""
         outs = [None] * len(wavs)
-        for group in bucket_by_length([int(w.shape[-1]) for w in wavs], self.micro_batch):
-            batch = torch.stack([wavs[i].reshape(-1).to(torch.float32) for i in group]).to(self.device, non_blocking=True)
-            y = self.generator(self.mel(batch)).reshape(len(group), -1).cpu()
+        h = self.h
+        lens = [int(w.shape[-1]) for w in wavs]
+        ragged_ok = (not hasattr(h, "gen_istft_hop_size") and getattr(self.generator, "precision", None) in (None, "bf16")
+                     and all(n > int(h.n_fft) // 2 for n in lens))
+        if not ragged_ok:
+            for group in bucket_by_length(lens, self.micro_batch):
+                batch = torch.stack([wavs[i].reshape(-1).to(torch.float32) for i in group]).to(self.device, non_blocking=True)
+                y = self.generator(self.mel(batch)).reshape(len(group), -1).cpu()
+                for j, i in enumerate(group):
+                    outs[i] = y[j]
+            return outs
+        up = 1
+        for u in h.upsample_rates:
+            up *= int(u)
+        for group in bucket_padded(lens, self.micro_batch, max_pad):
+            tmax = max(lens[i] for i in group)
+            batch = torch.zeros((len(group), tmax), dtype=torch.float32, device=self.device)
             for j, i in enumerate(group):
-                outs[i] = y[j]
+                batch[j, :lens[i]].copy_(wavs[i].reshape(-1).to(torch.float32), non_blocking=True)
+            n = torch.tensor([lens[i] for i in group], dtype=torch.int32, device=self.device)
+            frames = 1 + torch.div(n, int(h.hop_size), rounding_mode="floor")
+            mel = mel_spectrogram(batch, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax, lengths=n)
+            y = self.generator(mel, frames=frames.to(torch.int32)).reshape(len(group), -1).cpu()
+            for j, i in enumerate(group):
+                outs[i] = y[j, :(1 + lens[i] // int(h.hop_size)) * up].clone()
         return outs

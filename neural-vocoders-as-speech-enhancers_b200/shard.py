@@ -51,6 +51,26 @@ def bucket_by_length(lengths: Sequence[int], max_batch: int) -> List[List[int]]:
     return out
 
 
+def bucket_padded(lengths: Sequence[int], max_batch: int, max_pad: float = 0.25) -> List[List[int]]:
+    """Ragged utterances on ONE GPU with padding: utterances sorted by length (longest first) are cut into groups of at most
+    ``max_batch`` whose shortest member is at least ``(1 - max_pad)`` of the longest, so that at most ``max_pad`` of a
+    group's rows are padding.  The kernels mask every utterance at its own length (``nvse_generator_forward_ragged``), so
+    each result is still bit-identical to vocoding the utterance alone.  Deterministic; every index appears exactly once."""
+    if max_batch < 1 or not 0.0 <= max_pad < 1.0:
+        raise ValueError("max_batch must be >= 1 and 0 <= max_pad < 1")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    out: List[List[int]] = []
+    cur: List[int] = []
+    for i in order:
+        if cur and (len(cur) >= max_batch or int(lengths[i]) < (1.0 - max_pad) * int(lengths[cur[0]])):
+            out.append(cur)
+            cur = []
+        cur.append(i)
+    if cur:
+        out.append(cur)
+    return out
+
+
 def allreduce_gradients(parameters, group=None, average=True):
     """Data-parallel training (SURVEY.md §8e "collective, training only"): ONE all-reduce over a single flat buffer
     of every gradient (13.9 M fp32 = 55.7 MB for HiFi-GAN V1; on NVSwitch the cost is launch latency, not links, so

@@ -526,6 +526,42 @@ def test_vocoder_run_list_ragged_matches_single_utterance_runs():
         assert torch.equal(o, alone)
 
 
+def test_padded_ragged_batches_are_bit_identical_to_single_utterance_runs():
+    """Utterances of DIFFERENT lengths in one zero-padded batch with per-utterance lengths (nvse_frontend_mel_ragged_f32,
+    nvse_generator_forward_ragged): the front-end reflects each utterance at its own end and every generator kernel masks
+    it at its own length, so each result equals -- bit for bit -- vocoding the utterance alone (the reference's per-file
+    loop, infers/inference_hifigan.py:67-95).  Lengths chosen to end inside, on and just past tile / block boundaries of
+    the stages; one batch mixes a 0.4 s and a 1.6 s utterance (max_pad=0.9)."""
+    cfg = synth.HIFIGAN_V1
+    gen = build_generator(cfg, synth.make_state(cfg, 5, "init"), DEV, remove_wn=True)
+    gen.precision = "bf16"
+    h = synth.AttrDict(cfg)
+    voc = pkg.Vocoder(gen, h, micro_batch=8, device=DEV)
+    lens = [9000, 11000, 10500, 22050, 21000, 35000, 8192, 8191, 8193, 33024, 4097, 30000]
+    wavs = [torch.from_numpy(synth.make_wave(1, n, 70 + i)[0]) for i, n in enumerate(lens)]
+    alone = []
+    for w in wavs:
+        m = _mel(w.to(DEV)[None])
+        with torch.no_grad():
+            alone.append(gen(m).reshape(-1).cpu())
+    for max_pad in (0.25, 0.9):
+        outs = voc.run_list(wavs, max_pad=max_pad)
+        assert [o.numel() for o in outs] == [(1 + n // cfg["hop_size"]) * cfg["hop_size"] for n in lens]
+        for i, (o, a) in enumerate(zip(outs, alone)):
+            assert torch.equal(o, a), (max_pad, i, lens[i], float((o - a).abs().max()))
+    # the padded front-end by itself: frames of every utterance equal its single-utterance log-mel
+    tmax = max(lens)
+    batch = torch.zeros((len(lens), tmax), device=DEV)
+    for j, w in enumerate(wavs):
+        batch[j, :lens[j]] = w.to(DEV)
+    mel = _mel(batch, lengths=torch.tensor(lens, dtype=torch.int32, device=DEV))
+    for j, w in enumerate(wavs):
+        f = 1 + lens[j] // cfg["hop_size"]
+        assert torch.equal(mel[j, :, :f], _mel(w.to(DEV)[None])[0])
+    assert not lib_mod.tc_abort_status()
+    report(f"padded ragged batches ({len(lens)} utterances, 4097 .. 35000 samples, up to 90 % padding): bit-identical to single-utterance runs")
+
+
 def test_vocoder_run_host_overlapped_copies_match_device_run():
     """Host-buffer pipeline (copies on side streams, overlapped with the kernels): identical to the
     device-resident run, with an utterance count that is not a multiple of the micro-batch."""
