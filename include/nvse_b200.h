@@ -293,6 +293,32 @@ NVSE_API int nvse_weight_norm_backward_f32(const float* v, const float* g, const
 NVSE_API int nvse_istft_head_backward_f32(const float* z, const float* dout, float* dz, int64_t B, int64_t Tp, int n_fft,
                                  int hop, void* stream);
 
+/* ---- discriminators: MultiPeriodDiscriminator / MultiScaleDiscriminator -------------------------
+ * Replaces the convolution stacks of DiscriminatorP (Models/models.py:15-87: Conv2d (k,1) / (stride,1) over
+ * [B, C, T/period, period]) and DiscriminatorS (Models/models.py:187-214: grouped strided Conv1d over [B, C, T]) and what
+ * autograd runs through them in train_time_wi_inv.py:188-236.  One operation covers both: a strided grouped convolution
+ * along axis 2 of a CHANNELS-FIRST tensor x [B, Cin, L, W] (W = period for DiscriminatorP, 1 for DiscriminatorS) with the
+ * following leaky_relu fused:   y = lrelu(conv(x, w, stride, pad, groups) + bias, out_slope),   y [B, Cout, Lo, W],
+ * Lo = (L + 2 pad - k) / stride + 1 (nvse_disc_conv_out_len), w [Cout, Cin/groups, k] (the PyTorch Conv1d / Conv2d(k,1)
+ * layout), bias [Cout] or NULL, out_slope = 1 for no activation (conv_post).  These layouts ARE the feature maps the
+ * reference returns.  fp32, bit-reproducible. */
+NVSE_API int64_t nvse_disc_conv_out_len(int64_t L, int k, int stride, int pad);
+NVSE_API int nvse_disc_conv_forward_f32(const float* x, const float* w, const float* bias, float* y, int64_t B, int Cin, int Cout,
+                               int64_t L, int W, int k, int stride, int pad, int groups, float out_slope, void* stream);
+/* Backward of the above: dy [B, Cout, Lo, W] is the gradient w.r.t. the ACTIVATED output y (the leaky_relu derivative is taken
+ * from the sign of y); dx [B, Cin, L, W], dw [Cout, Cin/groups, k], dbias [Cout] -- any of the three may be NULL.  scratch:
+ * caller-owned, nvse_disc_conv_backward_scratch_bytes (masked gradient, per-phase transposed sub-filters of the data gradient,
+ * partial sums of the split weight-gradient reduction, added in a fixed order). */
+NVSE_API size_t nvse_disc_conv_backward_scratch_bytes(int64_t B, int Cin, int Cout, int64_t L, int W, int k, int stride, int pad,
+                                             int groups);
+NVSE_API int nvse_disc_conv_backward_f32(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
+                                float* dbias, int64_t B, int Cin, int Cout, int64_t L, int W, int k, int stride, int pad,
+                                int groups, float out_slope, void* scratch, size_t scratch_bytes, void* stream);
+/* AvgPool1d(k, stride, padding=pad) with count_include_pad (MultiScaleDiscriminator.meanpools, Models/models.py:225-228):
+ * x [rows, T] -> y [rows, (T + 2 pad - k) / stride + 1], and its backward dy -> dx [rows, T]. */
+NVSE_API int nvse_avgpool1d_f32(const float* x, float* y, int64_t rows, int64_t T, int k, int stride, int pad, void* stream);
+NVSE_API int nvse_avgpool1d_backward_f32(const float* dy, float* dx, int64_t rows, int64_t T, int k, int stride, int pad, void* stream);
+
 /* The tensor-core kernels bound every mbarrier wait (a protocol bug must never hang the GPU); a
  * tripped timeout sets a device flag and later tensor-core launches return without computing.
  * *flag = 1 if it is set; reset != 0 clears it.  Synchronises the device. */

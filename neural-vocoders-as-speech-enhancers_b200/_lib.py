@@ -92,6 +92,12 @@ PROTOTYPES = {
     "nvse_conv_transpose1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_weight_norm_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "nvse_istft_head_backward_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
+    "nvse_disc_conv_out_len": (_i64, [_i64, _i, _i, _i]),
+    "nvse_disc_conv_forward_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp]),
+    "nvse_disc_conv_backward_scratch_bytes": (_sz, [_i64, _i, _i, _i64, _i, _i, _i, _i, _i]),
+    "nvse_disc_conv_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
+    "nvse_avgpool1d_f32": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _vp]),
+    "nvse_avgpool1d_backward_f32": (_i, [_vp, _vp, _i64, _i64, _i, _i, _i, _vp]),
     "nvse_tc_abort_status": (_i, [_i, C.POINTER(_i)]),
     "nvse_debug_rb_trace": (_i, [C.POINTER(C.c_longlong)]),
 }

@@ -119,3 +119,61 @@ def istftnet_forward_autograd(folded, cfg, mel):
     nb = n_fft // 2 + 1
     spec = torch.exp(x[:, :nb]) * torch.exp(1j * torch.sin(x[:, nb:]))
     return torch.istft(spec, n_fft, hop, n_fft, window=torch.hann_window(n_fft, device=spec.device))
+
+
+# ---- waveform discriminators (Models/models.py:15-113, 187-246): functional restatement over a flat state dict -------
+def _folded_disc_weight(state, prefix):
+    """The effective convolution weight of one layer: weight_norm (``weight_g * weight_v / ||weight_v||``, norm over all
+    dims but 0 -- torch.nn.utils.weight_norm, Models/models.py:5,18) or the plain ``weight`` a test passes after folding."""
+    if prefix + ".weight_g" in state:
+        g, v = state[prefix + ".weight_g"], state[prefix + ".weight_v"]
+        return g * v / v.flatten(1).norm(dim=1).reshape([-1] + [1] * (v.dim() - 1))
+    return state[prefix + ".weight"]
+
+
+DISC_P_LAYERS = [(3, 2), (3, 2), (3, 2), (3, 2), (1, 2)]             # (stride, padding) of DiscriminatorP.convs, k = 5
+DISC_S_LAYERS = [(1, 1, 7), (2, 4, 20), (2, 16, 20), (4, 16, 20), (4, 16, 20), (1, 16, 20), (1, 1, 2)]  # (stride, groups, padding)
+
+
+def disc_p_forward(state, prefix, x, period):
+    """DiscriminatorP.forward (Models/models.py:63-87): reflect-pad to a multiple of the period, view as
+    [B, 1, T/period, period], five (k,1) convolutions + leaky_relu(0.1), conv_post.  Returns (flattened logits, fmap)."""
+    fmap = []
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    b, c, t = x.shape
+    if t % period != 0:
+        n_pad = period - (t % period)
+        x = F.pad(x, (0, n_pad), "reflect")
+        t = t + n_pad
+    x = x.view(b, c, t // period, period)
+    for i, (stride, pad) in enumerate(DISC_P_LAYERS):
+        x = F.conv2d(x, _folded_disc_weight(state, f"{prefix}.convs.{i}"), state[f"{prefix}.convs.{i}.bias"],
+                     stride=(stride, 1), padding=(pad, 0))
+        x = F.leaky_relu(x, 0.1)
+        fmap.append(x)
+    x = F.conv2d(x, _folded_disc_weight(state, f"{prefix}.conv_post"), state[f"{prefix}.conv_post.bias"], padding=(1, 0))
+    fmap.append(x)
+    return torch.flatten(x, 1, -1), fmap
+
+
+def disc_s_forward(state, prefix, x):
+    """DiscriminatorS.forward (Models/models.py:202-214) from folded / weight-normed weights (the spectral_norm variant is
+    checked through the module itself, its weight depends on the power-iteration buffers)."""
+    fmap = []
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    for i, (stride, groups, pad) in enumerate(DISC_S_LAYERS):
+        x = F.conv1d(x, _folded_disc_weight(state, f"{prefix}.convs.{i}"), state[f"{prefix}.convs.{i}.bias"], stride=stride,
+                     padding=pad, groups=groups)
+        x = F.leaky_relu(x, 0.1)
+        fmap.append(x)
+    x = F.conv1d(x, _folded_disc_weight(state, f"{prefix}.conv_post"), state[f"{prefix}.conv_post.bias"], padding=1)
+    fmap.append(x)
+    return torch.flatten(x, 1, -1), fmap
+
+
+def disc_conv(x, w, bias, stride, pad, groups, slope):
+    """One discriminator layer on [B, C, L, W] (what nvse_disc_conv_forward_f32 computes): conv along L + leaky_relu."""
+    y = F.conv2d(x, w.unsqueeze(-1), bias, stride=(stride, 1), padding=(pad, 0), groups=groups)
+    return F.leaky_relu(y, slope) if slope != 1.0 else y

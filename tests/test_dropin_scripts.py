@@ -112,7 +112,12 @@ assert mel_spectrogram.__code__.co_filename.startswith({dropin!r})
 assert HiFiGAN.__module__.startswith("neural-vocoders-as-speech-enhancers_b200"), HiFiGAN.__module__
 assert iSTFTNet.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")
 assert HDDemucas.__module__ == "Models.hddemucas" and sys.modules["Models.hddemucas"].__file__.startswith({ref!r})
-assert MultiPeriodDiscriminator.__module__ == "Models.models"
+assert MultiPeriodDiscriminator.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")  # B200-backed discriminators
+assert MultiScaleDiscriminator.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")
+import Models.models
+assert Models.models.__file__.startswith({dropin!r})
+assert feature_loss.__code__.co_filename.startswith({ref!r})  # everything else of Models/models.py stays the reference's own
+assert Models.models.MultiResolutionDiscriminator.__module__ == "_nvse_reference_models"
 import Models.hifigan, Models.istftnet
 assert Models.hifigan.__file__.startswith({dropin!r}) and Models.hifigan.HiFiGAN is HiFiGAN
 # the data-loader call (dataset.py:218-241): CPU tensors in, the reference's own function, no CUDA involved
