@@ -217,6 +217,63 @@ def train_step(pkg, synth, cfg, dev, batch=16, frames=32, steps=5):
     return out
 
 
+def disc_step(pkg, dev, batch=16, samples=8192, steps=3):
+    """Secondary number: the discriminator half of the reference's training step at its own shape
+    (train_time_wi_inv.py:188-236: D step on (y, y_g.detach()) + the generator step's pass through MPD and MSD with the
+    feature and least-squares losses, backward to y_g), this repo's fp32 kernels (csrc/disc.cu) next to the SAME module
+    tree on stock PyTorch (cuDNN) with TF32 on (PyTorch's default, what the reference trains with) and off."""
+    models = pkg.Models.models
+    torch.manual_seed(0)
+    y = torch.rand(batch, samples, device=dev) - 0.5
+    yh = (torch.rand(batch, samples, device=dev) - 0.5).requires_grad_(True)
+    torch.manual_seed(1)
+    nets = [models.MultiPeriodDiscriminator([2, 3, 5, 7, 11]).to(dev).train(), models.MultiScaleDiscriminator().to(dev).train()]
+
+    def step():
+        for net in nets:
+            d_r, d_g, _, _ = net(y, yh.detach())
+            models.ls_discriminator_loss(d_r, d_g)[0].backward()
+            net.zero_grad(set_to_none=True)
+        loss = 0
+        for net in nets:
+            d_r, d_g, f_r, f_g = net(y, yh)
+            loss = loss + models.ls_generator_loss(d_g)[0] + models.feature_loss(f_r, f_g)
+        loss.backward()
+        yh.grad = None
+        for net in nets:
+            net.zero_grad(set_to_none=True)
+
+    def timed():
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = pkg._lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, int((pkg._lib.launch_count() - l0) / steps)
+
+    out = {"config": f"MPD (periods 2,3,5,7,11) + MSD, batch {batch} x {samples} samples: D step + G-step pass, forward + backward"}
+    out["ms_fp32"], out["gpu_launches"] = timed()
+    saved = (models._DiscConv1d.forward, models._DiscConv2d.forward, models._MeanPool.forward, torch.backends.cudnn.allow_tf32)
+    lrelu = lambda x, sl: x if sl == 1.0 else torch.nn.functional.leaky_relu(x, sl)  # noqa: E731
+    try:
+        models._DiscConv1d.forward = lambda self, x, slope=1.0: lrelu(torch.nn.Conv1d.forward(self, x), slope)
+        models._DiscConv2d.forward = lambda self, x, slope=1.0: lrelu(torch.nn.Conv2d.forward(self, x), slope)
+        models._MeanPool.forward = lambda self, x: torch.nn.functional.avg_pool1d(x, self.kernel_size, self.stride, self.padding)
+        torch.backends.cudnn.allow_tf32 = True
+        out["stock_pytorch_tf32_ms"] = timed()[0]
+        torch.backends.cudnn.allow_tf32 = False
+        out["stock_pytorch_fp32_ms"] = timed()[0]
+    finally:
+        models._DiscConv1d.forward, models._DiscConv2d.forward, models._MeanPool.forward, torch.backends.cudnn.allow_tf32 = saved
+    out["note"] = "fp32 CUDA-core kernels (bit-reproducible); cuDNN's TF32 tensor-core path is faster, see DESIGN.md"
+    return out
+
+
 def cfg1_gpu(voc, synth, dev, reps=30):
     """cfg1 of BASELINE.json on the GPU through the public host-to-host call: batch 1, 2 s -> mel -> HiFi-GAN V1 -> wav."""
     wav = torch.from_numpy(synth.make_wave(1, 2 * SR, 3)).pin_memory()
@@ -534,7 +591,7 @@ def main():
     if extras:  # secondary numbers: none of them may cost the headline line
         for key, fn in (("cfg1_gpu", lambda: cfg1_gpu(voc, synth, dev)), ("cfg2_frontend", lambda: cfg2_frontend(voc, synth, cfg, dev, pk)),
                         ("eager_b200", lambda: eager_competitor(args, synth, cfg, dev, wav_dev)),
-                        ("train_step", lambda: train_step(pkg, synth, cfg, dev))):
+                        ("train_step", lambda: train_step(pkg, synth, cfg, dev)), ("disc_step", lambda: disc_step(pkg, dev))):
             try:
                 line[key] = fn()
             except Exception as e:  # noqa: BLE001

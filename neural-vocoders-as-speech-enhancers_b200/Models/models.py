@@ -138,6 +138,7 @@ class DiscriminatorP(nn.Module):
     def __init__(self, period, kernel_size=5, stride=3, use_spectral_norm=False):
         super().__init__()
         self.period = period
+        self.use_spectral_norm = use_spectral_norm
         norm_f = nn.utils.spectral_norm if use_spectral_norm else _weight_norm
         pad = (get_padding(5, 1), 0)
         self.convs = nn.ModuleList([
@@ -186,6 +187,7 @@ class DiscriminatorS(nn.Module):
 
     def __init__(self, use_spectral_norm=False):
         super().__init__()
+        self.use_spectral_norm = use_spectral_norm
         norm_f = nn.utils.spectral_norm if use_spectral_norm else _weight_norm
         self.convs = nn.ModuleList([
             norm_f(_DiscConv1d(1, 128, 15, 1, padding=7)),
@@ -246,8 +248,16 @@ def _run_pairs(discriminators, prepare, y, y_hat, chain=False):
         yi, yhi = prepare(i, y), prepare(i, y_hat)
         if chain:
             y, y_hat = yi, yhi
-        y_d_r, fmap_r = d(yi)
-        y_d_g, fmap_g = d(yhi)
+        if yi.shape == yhi.shape and not (d.training and getattr(d, "use_spectral_norm", False)):
+            # one pass over the concatenated batch: every sample is independent and both calls would use the same weights
+            # (a training-mode spectral_norm layer re-estimates its weight on every call, so that case keeps the two calls)
+            n = yi.shape[0]
+            out, fmap = d(torch.cat([yi, yhi], dim=0))
+            y_d_r, y_d_g = out[:n], out[n:]
+            fmap_r, fmap_g = [f[:n] for f in fmap], [f[n:] for f in fmap]
+        else:
+            y_d_r, fmap_r = d(yi)
+            y_d_g, fmap_g = d(yhi)
         y_d_rs.append(y_d_r)
         fmap_rs.append(fmap_r)
         y_d_gs.append(y_d_g)

@@ -48,6 +48,16 @@ struct DConvArgs {
 template <int NCO>
 struct WVec;
 template <>
+struct WVec<16> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(p + 4 * q);
+      v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
+  }
+};
+template <>
 struct WVec<8> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -69,11 +79,24 @@ struct WVec<2> {
   }
 };
 
+// n / d for 0 <= n < 2^14 with a precomputed reciprocal m = ceil(2^20 / d), d <= 64: exact (n * (m*d - 2^20) < 2^20), no division
+__host__ __device__ __forceinline__ uint32_t fdiv_magic(int d) { return ((1u << 20) + d - 1) / d; }
+__device__ __forceinline__ int fdiv(int n, uint32_t magic) { return (int)(((uint64_t)(uint32_t)n * magic) >> 20); }
+
+// 4-byte asynchronous global -> shared copy; `valid` = false writes a zero instead (src-size 0)
+__device__ __forceinline__ void cp_async4_zfill(float* dst_smem, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+               "r"(valid ? 4 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int NCO, int NPI>
-__global__ void __launch_bounds__(kDThreads) dconv_kernel(const DConvArgs a) {
+__global__ void __launch_bounds__(kDThreads, 2) dconv_kernel(const DConvArgs a) {
   constexpr int TCO = 8 * NCO, TP = 32 * NPI, TCOP = TCO + 4;
   extern __shared__ __align__(16) float smem[];
-  __shared__ int toff[64];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int W = a.W, s = a.s_in, nt = a.nt;
   const int ntiles_co = (a.Cout_g + TCO - 1) / TCO;
@@ -85,12 +108,8 @@ __global__ void __launch_bounds__(kDThreads) dconv_kernel(const DConvArgs a) {
   const int off_min = a.dt > 0 ? a.off0 : a.off0 - (nt - 1);
   const int nrel = s * (mlast - m0) + nt;  // input rows this tile touches
   const int pitch = a.pitch, cpitch = s * pitch;
-  float* xs = smem;                                          // [ci_chunk][s][pitch]
-  float* ws = smem + ((a.ci_chunk * cpitch + 3) & ~3);       // [ci_chunk * nt][TCOP]
-  if (tid < nt) {
-    const int e = a.dt > 0 ? tid : nt - 1 - tid;             // row offset of tap `tid` above the lowest tap
-    toff[tid] = (e % s) * pitch + (e / s) * W;
-  }
+  const int xs_floats = (a.ci_chunk * cpitch + 3) & ~3;
+  const int buf_floats = xs_floats + a.ci_chunk * nt * TCOP;  // one stage: x slab [ci_chunk][s][pitch] + weights [ci_chunk * nt][TCOP]
   float acc[NCO][NPI];
 #pragma unroll
   for (int c = 0; c < NCO; ++c)
@@ -101,37 +120,72 @@ __global__ void __launch_bounds__(kDThreads) dconv_kernel(const DConvArgs a) {
   const float* wg = a.w + (int64_t)(g * a.Cout_g + co0) * a.Cin_g * nt;
   const int row0 = s * m0 + off_min;
   const int nrw = nrel * W;
-  for (int ci0 = 0; ci0 < a.Cin_g; ci0 += a.ci_chunk) {
+  const uint32_t magic_w = fdiv_magic(W), magic_s = fdiv_magic(s);
+  // stage input channels [ci0, ci0 + cic) into buffer `buf`, asynchronously (out-of-range rows / channels as zeros)
+  auto stage = [&](int ci0, int buf) {
+    float* xs = smem + buf * buf_floats;
+    float* ws = xs + xs_floats;
     const int cic = min(a.ci_chunk, a.Cin_g - ci0);
-    __syncthreads();  // the previous chunk has been consumed (and toff is visible)
-    for (int idx = tid; idx < cic * nrw; idx += kDThreads) {
-      const int ci = idx / nrw, r = idx - ci * nrw, rel = r / W, w = r - rel * W;
-      const int gr = row0 + rel;
-      const float v = (gr >= 0 && gr < a.Lin) ? __ldg(inb + ((int64_t)(ci0 + ci) * a.Lin + gr) * W + w) : 0.0f;
-      xs[ci * cpitch + (rel % s) * pitch + (rel / s) * W + w] = v;
+    // one warp per input channel: (row, w) of the slab is a contiguous run of global memory
+    for (int ci = ty; ci < cic; ci += 8) {
+      const float* src = inb + (int64_t)(ci0 + ci) * a.Lin * W + (int64_t)row0 * W;
+      float* dst = xs + ci * cpitch;
+      for (int r = tx; r < nrw; r += 32) {
+        const int rel = fdiv(r, magic_w), w = r - rel * W;
+        const int q = fdiv(rel, magic_s), ph = rel - q * s;
+        const int gr = row0 + rel;
+        const bool ok = gr >= 0 && gr < a.Lin;
+        cp_async4_zfill(dst + ph * pitch + q * W + w, ok ? src + r : inb, ok);
+      }
     }
     const int nk = cic * nt;
-    for (int idx = tid; idx < TCO * nk; idx += kDThreads) {
-      const int oc = idx / nk, e = idx - oc * nk;
-      ws[e * TCOP + oc] = (co0 + oc < a.Cout_g) ? __ldg(wg + ((int64_t)oc * a.Cin_g + ci0) * nt + e) : 0.0f;
+    for (int oc = ty; oc < TCO; oc += 8) {  // one warp per output channel: its [cic][nt] weights are contiguous
+      const bool ok = co0 + oc < a.Cout_g;
+      const float* src = wg + ((int64_t)(ok ? oc : 0) * a.Cin_g + ci0) * nt;
+      for (int e = tx; e < nk; e += 32) cp_async4_zfill(ws + e * TCOP + oc, src + e, ok);
+    }
+    cp_async_commit();
+  };
+  const int nchunks = (a.Cin_g + a.ci_chunk - 1) / a.ci_chunk;
+  stage(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch + 1 < nchunks) {
+      stage((ch + 1) * a.ci_chunk, (ch + 1) & 1);  // the next stage loads while this one is multiplied
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const int cic = min(a.ci_chunk, a.Cin_g - ch * a.ci_chunk);
+    const float* xs = smem + (ch & 1) * buf_floats;
+    const float* ws = xs + xs_floats;
+    // taps are walked in slab order (e = row offset above the lowest tap: phase e % s, row e / s of the de-interleaved
+    // slab), so the slab pointer advances by `pitch` within a row group and wraps to the next row after s taps
+    const int wstep = a.dt > 0 ? TCOP : -TCOP;
+    const int wrap = W - (s - 1) * pitch;
     for (int ci = 0; ci < cic; ++ci) {
-      const float* xc = xs + ci * cpitch + pl0 + tx;
-      const float* wc = ws + ci * nt * TCOP + ty * NCO;
+      const float* xp = xs + ci * cpitch + pl0 + tx;
+      const float* wp = ws + (ci * nt + (a.dt > 0 ? 0 : nt - 1)) * TCOP + ty * NCO;
+      int ph = 0;
 #pragma unroll 2
-      for (int t = 0; t < nt; ++t) {
+      for (int e = 0; e < nt; ++e, wp += wstep) {
         float wv[NCO], xv[NPI];
-        WVec<NCO>::load(wc + t * TCOP, wv);
-        const float* xp = xc + toff[t];
+        WVec<NCO>::load(wp, wv);
 #pragma unroll
         for (int i = 0; i < NPI; ++i) xv[i] = xp[32 * i];
 #pragma unroll
         for (int c = 0; c < NCO; ++c)
 #pragma unroll
           for (int i = 0; i < NPI; ++i) acc[c][i] = fmaf(wv[c], xv[i], acc[c][i]);
+        if (++ph == s) {
+          ph = 0;
+          xp += wrap;
+        } else {
+          xp += pitch;
+        }
       }
     }
+    __syncthreads();  // this buffer is refilled by the stage issued in the next iteration
   }
 
   float* outb = a.out + b * a.out_bstride;
@@ -154,18 +208,62 @@ __global__ void __launch_bounds__(kDThreads) dconv_kernel(const DConvArgs a) {
   }
 }
 
+// Cout = 1 (conv_post of both discriminators): one warp-lane per output position, the input channels split over the 8 warps
+// of a CTA and summed through shared memory in a fixed order.  out[b, 0, m, w] = bias + sum_{ci, t} w[ci][t] x[b, ci, s m + t - pad, w]
+__global__ void __launch_bounds__(kDThreads) dconv_cout1_kernel(const DConvArgs a) {
+  __shared__ float red[8][33];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int W = a.W, nt = a.nt;
+  const int64_t b = blockIdx.y;
+  const int p = blockIdx.x * 32 + tx;
+  const int m = p / W, w = p - m * W;
+  const bool live = m < a.M;
+  const float* inb = a.in + b * a.in_bstride;
+  float acc = 0.0f;
+  if (live) {
+    const int r0 = a.s_in * m + a.off0;
+    for (int ci = ty; ci < a.Cin_g; ci += 8) {
+      const float* xc = inb + (int64_t)ci * a.Lin * W + w;
+      const float* wc = a.w + ci * nt;
+      for (int t = 0; t < nt; ++t) {
+        const int gr = r0 + t;
+        if (gr >= 0 && gr < a.Lin) acc = fmaf(__ldg(wc + t), __ldg(xc + (int64_t)gr * W), acc);
+      }
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && live) {
+    float v = red[0][tx];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) v += red[q][tx];
+    v += a.bias ? __ldg(a.bias) : 0.0f;
+    v = v > 0.0f ? v : v * a.slope;
+    a.out[b * a.out_bstride + (int64_t)m * W + w] = v;
+  }
+}
+
 int dconv_pitch(int TP, int W, int nt, int s) { return (TP + W * (2 + (nt - 1) / s)) | 1; }
 
 int launch_dconv(DConvArgs a, int64_t B, cudaStream_t st) {
   NVSE_REQUIRE(a.nt >= 1 && a.nt <= 64, NVSE_ERR_UNSUPPORTED, "discriminator conv: %d taps (supported: 1..64)", a.nt);
   constexpr int TP = 128;
-  a.ci_chunk = std::max(1, std::min(std::min(16, a.Cin_g), 48 / a.nt));
+  a.ci_chunk = std::max(1, std::min(std::min(16, a.Cin_g), 96 / a.nt));
   a.pitch = dconv_pitch(TP, a.W, a.nt, a.s_in);
   const int64_t positions = (int64_t)a.M * a.W;
   if (positions <= 0 || B <= 0) return NVSE_OK;
-  const int nco = a.Cout_g >= 64 ? 8 : (a.Cout_g >= 32 ? 4 : 2);
+  if (a.Cout_g == 1 && a.groups == 1 && a.dt > 0 && a.out_mul == 1 && a.out_add == 0) {
+    dim3 grid1((unsigned)((positions + 31) / 32), (unsigned)B);
+    NVSE_REQUIRE(B <= 65535, NVSE_ERR_UNSUPPORTED, "discriminator conv: batch too large");
+    ProfScope prof("dconv", a.Cin_g, 1, 2.0 * B * positions * (double)a.Cin_g * a.nt, 4.0 * B * ((double)positions + (double)a.Lin * a.W * a.Cin_g), st);
+    dconv_cout1_kernel<<<grid1, kDThreads, 0, st>>>(a);
+    NVSE_LAUNCH_CHECK("dconv_cout1_kernel");
+    return NVSE_OK;
+  }
+  const int nco = a.Cout_g >= 128 ? 16 : (a.Cout_g >= 64 ? 8 : (a.Cout_g >= 32 ? 4 : 2));
   const int TCO = 8 * nco;
-  const size_t smem = sizeof(float) * (size_t)(((a.ci_chunk * a.s_in * a.pitch + 3) & ~3) + a.ci_chunk * a.nt * (TCO + 4));
+  if (nco == 16) a.ci_chunk = std::max(1, std::min(a.ci_chunk, 64 / a.nt));
+  const size_t smem = 2 * sizeof(float) * (size_t)(((a.ci_chunk * a.s_in * a.pitch + 3) & ~3) + a.ci_chunk * a.nt * (TCO + 4));
   dim3 grid((unsigned)((positions + TP - 1) / TP), (unsigned)(a.groups * ((a.Cout_g + TCO - 1) / TCO)), (unsigned)B);
   NVSE_REQUIRE(B <= 65535 && grid.y <= 65535, NVSE_ERR_UNSUPPORTED, "discriminator conv: grid too large");
   auto go = [&](auto kern) -> int {
@@ -177,6 +275,7 @@ int launch_dconv(DConvArgs a, int64_t B, cudaStream_t st) {
   ProfScope prof("dconv", a.Cin_g * a.groups, a.Cout_g * a.groups,
                  2.0 * B * positions * a.Cout_g * a.groups * (double)a.Cin_g * a.nt,
                  4.0 * B * ((double)positions * a.Cout_g * a.groups + (double)a.Lin * a.W * a.Cin_g * a.groups), st);
+  if (nco == 16) return go(dconv_kernel<16, 4>);
   if (nco == 8) return go(dconv_kernel<8, 4>);
   if (nco == 4) return go(dconv_kernel<4, 4>);
   return go(dconv_kernel<2, 4>);
@@ -197,7 +296,7 @@ constexpr int kWgTPK = 64;   // positions per staged chunk
 constexpr int kWgNCJ = 4;    // (ic, j) columns per thread -> 128 columns per CTA
 
 template <int NCO>
-__global__ void __launch_bounds__(kDThreads) dwgrad_kernel(const DWgradArgs a) {
+__global__ void __launch_bounds__(kDThreads, 2) dwgrad_kernel(const DWgradArgs a) {
   constexpr int TCO = 8 * NCO, TC = 32 * kWgNCJ, OTP = TCO + 4;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -209,8 +308,8 @@ __global__ void __launch_bounds__(kDThreads) dwgrad_kernel(const DWgradArgs a) {
   const int ic_first = col0 / k;
   const int nic = min(a.Cin_g - 1, (col0 + TC - 1) / k) - ic_first + 1;
   const int pitch = a.pitch, cpitch = s * pitch;
-  float* xs = smem;                                         // [nic_max][s][pitch]
-  float* dzs = smem + ((a.nic_max * cpitch + 3) & ~3);      // [kWgTPK][OTP]
+  const int xs_floats = (a.nic_max * cpitch + 3) & ~3;
+  const int buf_floats = xs_floats + kWgTPK * OTP;          // one stage: x slab [nic_max][s][pitch] + dz tile [kWgTPK][OTP]
 
   int colbase[kWgNCJ];
 #pragma unroll
@@ -231,30 +330,50 @@ __global__ void __launch_bounds__(kDThreads) dwgrad_kernel(const DWgradArgs a) {
 
   const int positions = a.Lo * W;
   const int qn = pitch / W;  // staged rows per phase (every entry a chunk can read is initialised)
+  const int nrw = qn * s * W;
+  const uint32_t magic_w = fdiv_magic(W), magic_s = fdiv_magic(s);
   const int c_begin = blockIdx.z * a.chunks_per_split, c_end = min(a.total_chunks, c_begin + a.chunks_per_split);
-  for (int ch = c_begin; ch < c_end; ++ch) {
+  auto stage = [&](int ch, int buf) {
+    float* xs = smem + buf * buf_floats;
+    float* dzs = xs + xs_floats;
     const int64_t b = ch / a.chunks_per_b;
     const int pc0 = (ch - (int)b * a.chunks_per_b) * kWgTPK;
-    const int m0 = pc0 / W, pl0 = pc0 - m0 * W;
-    const int row0 = s * m0 - a.pad;
+    const int row0 = s * (pc0 / W) - a.pad;
     const float* xb = a.x + b * a.x_bstride + (int64_t)(g * a.Cin_g + ic_first) * a.L * W;
     const float* dzb = a.dz + b * a.dz_bstride + (int64_t)(g * a.Cout_g + co0) * positions;
-    __syncthreads();
-    const int nrw = qn * s * W;
-    for (int idx = tid; idx < nic * nrw; idx += kDThreads) {
-      const int ic = idx / nrw, r = idx - ic * nrw, rel = r / W, w = r - rel * W;
-      const int gr = row0 + rel;
-      const float v = (gr >= 0 && gr < a.L) ? __ldg(xb + ((int64_t)ic * a.L + gr) * W + w) : 0.0f;
-      xs[ic * cpitch + (rel % s) * pitch + (rel / s) * W + w] = v;
+    for (int ic = ty; ic < nic; ic += 8) {
+      const float* src = xb + (int64_t)ic * a.L * W + (int64_t)row0 * W;
+      float* dst = xs + ic * cpitch;
+      for (int r = tx; r < nrw; r += 32) {
+        const int rel = fdiv(r, magic_w), w = r - rel * W;
+        const int q = fdiv(rel, magic_s), ph = rel - q * s;
+        const int gr = row0 + rel;
+        const bool ok = gr >= 0 && gr < a.L;
+        cp_async4_zfill(dst + ph * pitch + q * W + w, ok ? src + r : xb, ok);
+      }
     }
     for (int idx = tid; idx < TCO * kWgTPK; idx += kDThreads) {
       const int oc = idx / kWgTPK, pp = idx - oc * kWgTPK;
       const int p = pc0 + pp;
-      dzs[pp * OTP + oc] = (p < positions && co0 + oc < a.Cout_g) ? __ldg(dzb + (int64_t)oc * positions + p) : 0.0f;
+      const bool ok = p < positions && co0 + oc < a.Cout_g;
+      cp_async4_zfill(dzs + pp * OTP + oc, dzb + (ok ? (int64_t)oc * positions + p : 0), ok);
+    }
+    cp_async_commit();
+  };
+  if (c_begin < c_end) stage(c_begin, 0);
+  for (int ch = c_begin; ch < c_end; ++ch) {
+    const int buf = (ch - c_begin) & 1;
+    if (ch + 1 < c_end) {
+      stage(ch + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    const float* xp = xs + pl0;
-    const float* dp = dzs + ty * NCO;
+    const int pc0 = (ch % a.chunks_per_b) * kWgTPK;
+    const int pl0 = pc0 - (pc0 / W) * W;
+    const float* xp = smem + buf * buf_floats + pl0;
+    const float* dp = smem + buf * buf_floats + xs_floats + ty * NCO;
 #pragma unroll 4
     for (int pp = 0; pp < kWgTPK; ++pp) {
       float dv[NCO], xv[kWgNCJ];
@@ -266,6 +385,7 @@ __global__ void __launch_bounds__(kDThreads) dwgrad_kernel(const DWgradArgs a) {
 #pragma unroll
         for (int i = 0; i < kWgNCJ; ++i) acc[c][i] = fmaf(dv[c], xv[i], acc[c][i]);
     }
+    __syncthreads();
   }
   float* dst = a.dst + (int64_t)blockIdx.z * a.groups * a.Cout_g * ncols;
 #pragma unroll
@@ -295,7 +415,7 @@ struct WgradPlan {
 
 WgradPlan wgrad_plan(int64_t B, int Cin_g, int Cout_g, int groups, int Lo, int W, int k, int stride) {
   WgradPlan p;
-  p.nco = Cout_g >= 64 ? 8 : (Cout_g >= 32 ? 4 : 2);
+  p.nco = Cout_g >= 128 ? 16 : (Cout_g >= 64 ? 8 : (Cout_g >= 32 ? 4 : 2));
   const int TCO = 8 * p.nco, TC = 32 * kWgNCJ;
   const int nm_max = kWgTPK / W + 2;
   const int nrel = stride * (nm_max - 1) + k;
@@ -303,7 +423,7 @@ WgradPlan wgrad_plan(int64_t B, int Cin_g, int Cout_g, int groups, int Lo, int W
   if ((qn * W) % 2 == 0 && W % 2 == 1) ++qn;  // odd pitch where that is possible: fewer bank conflicts between phases
   p.pitch = qn * W;
   p.nic_max = std::min(Cin_g, TC / k + 2);
-  p.smem = sizeof(float) * (size_t)(((p.nic_max * stride * p.pitch + 3) & ~3) + kWgTPK * (TCO + 4));
+  p.smem = 2 * sizeof(float) * (size_t)(((p.nic_max * stride * p.pitch + 3) & ~3) + kWgTPK * (TCO + 4));
   p.chunks_per_b = (Lo * W + kWgTPK - 1) / kWgTPK;
   p.total_chunks = (int)(B * p.chunks_per_b);
   const int tiles = ((Cin_g * k + TC - 1) / TC) * groups * ((Cout_g + TCO - 1) / TCO);
@@ -477,7 +597,7 @@ extern "C" int nvse_disc_conv_backward_f32(const float* x, const float* w, const
     {
       ProfScope prof("dwgrad", Cin, Cout, 2.0 * B * Lo * W * Cout * (double)Cin_g * k,
                      4.0 * B * ((double)Lo * W * Cout + (double)L * W * Cin), st);
-      int rc = p.nco == 8 ? go(dwgrad_kernel<8>) : (p.nco == 4 ? go(dwgrad_kernel<4>) : go(dwgrad_kernel<2>));
+      int rc = p.nco == 16 ? go(dwgrad_kernel<16>) : p.nco == 8 ? go(dwgrad_kernel<8>) : (p.nco == 4 ? go(dwgrad_kernel<4>) : go(dwgrad_kernel<2>));
       if (rc) return rc;
     }
     if (p.nsplit > 1) {
