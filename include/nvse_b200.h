@@ -150,7 +150,8 @@ NVSE_API int nvse_generator_forward(nvse_generator* g, const float* mel, int64_t
  * frames of each utterance (1 <= frames_dev[b] <= frames).  Utterance b is computed exactly -- bit for bit -- as if it were
  * passed alone with frames_dev[b] frames: every kernel treats its rows beyond that length like rows beyond the end of the
  * sequence.  out [B, out_samples(frames)]; the samples of utterance b beyond out_samples(frames_dev[b]) are undefined.
- * HiFiGAN, NVSE_PRECISION_BF16 (the fused tensor-core plan) only. */
+ * NVSE_PRECISION_BF16 (the fused tensor-core plan) only; HiFiGAN and iSTFTNet (whose reflection-padded conv_post and iSTFT
+ * overlap-add stop at every utterance's own last frame). */
 NVSE_API int nvse_generator_forward_ragged(nvse_generator* g, const float* mel, int64_t B, int64_t frames, const int32_t* frames_dev,
                                   float* out, void* workspace, size_t workspace_bytes, int precision, void* stream);
 /* The same forward with the waveform delivered as PCM_16 (int16 [B, out_samples]) instead of float: the quantisation of

@@ -206,7 +206,7 @@ class GeneratorEngine:
         """``pcm16=True`` (inference only): the waveform as int16 PCM, quantised like ``sf.write(..., 'PCM_16')``
         (infers/inference_hifigan.py:93) inside the last kernel instead of float32.  ``out`` (inference only): a
         contiguous device tensor ``[B, samples]`` of the result's dtype to write into instead of allocating one.
-        ``frames`` (inference only, HiFiGAN on the 16-bit path): int tensor ``[B]``, the mel frames of each utterance of a
+        ``frames`` (inference only, the 16-bit tensor-core path of either generator): int tensor ``[B]``, the mel frames of each utterance of a
         batch padded to the longest one -- utterance ``b`` comes out bit-identical to passing ``x[b:b+1, :, :frames[b]]``
         alone (``nvse_generator_forward_ragged``); its samples beyond its own length are undefined."""
         if x.dim() != 3 or x.shape[1] != self.cfg.in_channels:

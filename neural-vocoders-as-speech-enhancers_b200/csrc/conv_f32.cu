@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
   const int t0 = blockIdx.x * THIN_ROWS;
   const float* __restrict__ xb = a.x + b * a.x_bstride;
   const int nrows = THIN_ROWS + span;
+  // ragged batch: rows of this utterance beyond its own length read as zero, like rows beyond the end of the sequence
+  const int tin = a.in_lens.lens ? valid_rows(a.in_lens, b, a.Tin - a.reflect_left) + a.reflect_left : a.Tin;
 
   float acc[NOUT];
 #pragma unroll
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(THIN_ROWS) conv_thin_f32_kernel(const ConvF32A
       const int c = a.x_t32 ? ((e & 3) | (((e >> 2) / nrows) << 2)) : e % THIN_CK;
       const int vrow = t0 + min_off + r;  // row in the (virtually reflection-padded) input
       float v = 0.0f;
-      if (c < ck && vrow >= 0 && vrow < a.Tin) {
+      if (c < ck && vrow >= 0 && vrow < tin) {
         const int arow = vrow < a.reflect_left ? a.reflect_left - vrow : vrow - a.reflect_left;
         v = lrelu(xb[a.x_t32 ? t32_off(arow, ci0 + c, a.Cin) : (int64_t)arow * a.Cin + ci0 + c], a.in_slope);
       }
@@ -293,7 +295,9 @@ int launch_conv_f32(const ConvF32Args& a, int64_t B, cudaStream_t st) {
   if (B == 0 || a.Trows <= 0) return NVSE_OK;
   const bool post_t32 = a.x_t32 && a.Cout == 1 && !a.reflect_left && !a.residual && !a.mask && a.out_mul == 1 && a.out_add == 0 &&
                         (a.Cin == 16 || a.Cin == 32 || a.Cin == 64);
-  NVSE_REQUIRE(!a.in_lens.lens || post_t32, NVSE_ERR_UNSUPPORTED, "fp32 conv: per-utterance lengths are only implemented by the T32 conv_post kernel");
+  const bool thin_kernel = a.Cout < 32 || a.reflect_left || (a.Cin % BK != 0 && a.Cout <= 32);
+  NVSE_REQUIRE(!a.in_lens.lens || post_t32 || (thin_kernel && a.in_stride <= 1), NVSE_ERR_UNSUPPORTED,
+               "fp32 conv: per-utterance lengths are only implemented by the thin (conv_post) kernels");
   int min_off = a.taps.off[0], max_off = a.taps.off[0];
   for (int i = 1; i < a.taps.ntaps; ++i) {
     min_off = std::min(min_off, a.taps.off[i]);

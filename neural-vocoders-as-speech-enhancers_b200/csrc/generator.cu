@@ -255,8 +255,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
       per_launch[(size_t)i * c.num_kernels + j] = per;
     }
   }
-  NVSE_REQUIRE(!frames_dev || (t32 && c.kind == NVSE_GEN_HIFIGAN), NVSE_ERR_UNSUPPORTED,
-               "ragged batches are implemented on the fused tensor-core HiFiGAN plan only");
+  NVSE_REQUIRE(!frames_dev || t32, NVSE_ERR_UNSUPPORTED, "ragged batches are implemented on the fused tensor-core plan only");
   RowLens lens{frames_dev, 1, 0};  // valid rows per utterance at the current stage (affine in the frame count)
   int64_t T = F;
   for (int i = 0; i < c.num_upsamples; ++i) {
@@ -366,10 +365,10 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   a.Tin = a.Tout = a.Trows = (int)T + 1; a.y = bufU; a.y_bstride = (T + 1) * post.Cout;
   if (int rc = launch_conv_f32(a, B, st)) return rc;
   if (out_i16) {  // the iSTFT head writes float; quantise from a workspace buffer
-    if (int rc = launch_istft_head(bufU, bufR, B, T + 1, c.istft_n_fft, c.istft_hop, st)) return rc;
+    if (int rc = launch_istft_head(bufU, bufR, B, T + 1, c.istft_n_fft, c.istft_hop, st, lens)) return rc;
     return launch_pcm16(bufR, out_i16, B * nvse_generator_out_samples(g, F), st);
   }
-  return launch_istft_head(bufU, out, B, T + 1, c.istft_n_fft, c.istft_hop, st);
+  return launch_istft_head(bufU, out, B, T + 1, c.istft_n_fft, c.istft_hop, st, lens);
 }
 
 static bool wants_tc(const Layer& L) { return L.name != "conv_pre" && L.name != "conv_post" && tc_supported(L.Cin, L.Cout); }

@@ -49,7 +49,8 @@ struct nvse_generator {
 
 namespace nvse {
 
-int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st);
+// lens: ragged batch, valid conv_post rows per utterance EXCLUDING the reflected one (null: all Tp - 1)
+int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st, RowLens lens = RowLens{nullptr, 1, 0});
 // dz rows have `pitch` >= n_fft + 2 floats (extra columns zeroed)
 int launch_istft_head_bwd(const float* z, const float* gout, float* dz, int64_t B, int64_t Tp, int n_fft, int hop, int pitch,
                           cudaStream_t st);

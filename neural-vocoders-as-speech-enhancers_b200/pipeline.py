@@ -129,13 +129,12 @@ class Vocoder:
         Here utterances of similar length (``bucket_padded``: at most ``max_pad`` of a batch is padding) share a batch that
         is zero-padded to its longest member and carries the per-utterance lengths: the front-end reflects every utterance
         at its own end and every generator kernel masks it at its own length, so each result is BIT-IDENTICAL to the
-        single-utterance result (tests/test_gpu_parity.py).  Generators without the ragged path (iSTFTNet, fp32 precision)
-        fall back to groups of exactly equal length."""
+        single-utterance result (tests/test_gpu_parity.py; HiFiGAN and iSTFTNet on the 16-bit path).  The fp32 precision path
+        has no ragged kernels and falls back to groups of exactly equal length."""
         outs = [None] * len(wavs)
         h = self.h
         lens = [int(w.shape[-1]) for w in wavs]
-        ragged_ok = (not hasattr(h, "gen_istft_hop_size") and getattr(self.generator, "precision", None) in (None, "bf16")
-                     and all(n > int(h.n_fft) // 2 for n in lens))
+        ragged_ok = getattr(self.generator, "precision", None) in (None, "bf16") and all(n > int(h.n_fft) // 2 for n in lens)
         if not ragged_ok:
             for group in bucket_by_length(lens, self.micro_batch):
                 batch = torch.stack([wavs[i].reshape(-1).to(torch.float32) for i in group]).to(self.device, non_blocking=True)
@@ -146,6 +145,8 @@ class Vocoder:
         up = 1
         for u in h.upsample_rates:
             up *= int(u)
+        if getattr(self.generator, "_kind", None) == _lib.GEN_ISTFTNET:
+            up *= int(h.gen_istft_hop_size)
         for group in bucket_padded(lens, self.micro_batch, max_pad):
             tmax = max(lens[i] for i in group)
             batch = torch.zeros((len(group), tmax), dtype=torch.float32, device=self.device)

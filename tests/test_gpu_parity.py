@@ -526,13 +526,15 @@ def test_vocoder_run_list_ragged_matches_single_utterance_runs():
         assert torch.equal(o, alone)
 
 
-def test_padded_ragged_batches_are_bit_identical_to_single_utterance_runs():
+@pytest.mark.parametrize("cfg_key", ["hifigan_v1", "istftnet"])
+def test_padded_ragged_batches_are_bit_identical_to_single_utterance_runs(cfg_key):
     """Utterances of DIFFERENT lengths in one zero-padded batch with per-utterance lengths (nvse_frontend_mel_ragged_f32,
     nvse_generator_forward_ragged): the front-end reflects each utterance at its own end and every generator kernel masks
     it at its own length, so each result equals -- bit for bit -- vocoding the utterance alone (the reference's per-file
     loop, infers/inference_hifigan.py:67-95).  Lengths chosen to end inside, on and just past tile / block boundaries of
-    the stages; one batch mixes a 0.4 s and a 1.6 s utterance (max_pad=0.9)."""
-    cfg = synth.HIFIGAN_V1
+    the stages; one batch mixes a 0.4 s and a 1.6 s utterance (max_pad=0.9).  iSTFTNet: the reflection-padded conv_post and
+    the iSTFT head's overlap-add stop at every utterance's own last frame."""
+    cfg = synth.CONFIGS[cfg_key]
     gen = build_generator(cfg, synth.make_state(cfg, 5, "init"), DEV, remove_wn=True)
     gen.precision = "bf16"
     h = synth.AttrDict(cfg)
@@ -559,7 +561,7 @@ def test_padded_ragged_batches_are_bit_identical_to_single_utterance_runs():
         f = 1 + lens[j] // cfg["hop_size"]
         assert torch.equal(mel[j, :, :f], _mel(w.to(DEV)[None])[0])
     assert not lib_mod.tc_abort_status()
-    report(f"padded ragged batches ({len(lens)} utterances, 4097 .. 35000 samples, up to 90 % padding): bit-identical to single-utterance runs")
+    report(f"padded ragged batches, {cfg['model_name']} ({len(lens)} utterances, 4097 .. 35000 samples, up to 90 % padding): bit-identical to single-utterance runs")
 
 
 def test_vocoder_run_host_overlapped_copies_match_device_run():
