@@ -1,8 +1,11 @@
 """``Models.models`` as train_time_wi_inv.py:18-26 imports it.
 
-``MultiPeriodDiscriminator`` / ``MultiScaleDiscriminator`` (with ``DiscriminatorP`` / ``DiscriminatorS``) are the B200-backed
-modules -- same constructors, checkpoint keys and random initialisation as Models/models.py:15-113,187-246, every
-convolution forward and backward in the sm_100a kernels of csrc/disc.cu.  Every other name of the reference's module (the
+With ``NVSE_B200_DISCRIMINATORS=1`` in the environment ``MultiPeriodDiscriminator`` / ``MultiScaleDiscriminator`` (with
+``DiscriminatorP`` / ``DiscriminatorS``) are the B200-backed modules -- same constructors, checkpoint keys and random
+initialisation as Models/models.py:15-113,187-246, every convolution forward and backward in the sm_100a kernels of
+csrc/disc.cu (fp32, bit-reproducible).  It is an opt-in because those kernels run on the fp32 CUDA cores and are today slower
+than the cuDNN TF32 convolutions the reference's own classes use on a GPU; without the variable the four
+names stay the reference's classes, like every other name of the reference's module (the
 losses, ``MultiResolutionDiscriminator``, the CQT discriminator, ``MultiResolutionMelLoss`` ...) is the reference's own object,
 taken from its ``Models/models.py`` when that file can be imported (it needs torchaudio; the CQT discriminator needs nnAudio
 at call time only); the loss functions the time-domain trainer uses are also provided by the package itself, so the trainer
@@ -18,8 +21,11 @@ except Exception:  # a missing optional dependency of the reference's module mus
 if _ref is not None:
     globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("__")})
 
-DiscriminatorP, MultiPeriodDiscriminator = _m.DiscriminatorP, _m.MultiPeriodDiscriminator
-DiscriminatorS, MultiScaleDiscriminator = _m.DiscriminatorS, _m.MultiScaleDiscriminator
+import os as _os
+
+if _ref is None or _os.environ.get("NVSE_B200_DISCRIMINATORS", "0") not in ("", "0"):
+    DiscriminatorP, MultiPeriodDiscriminator = _m.DiscriminatorP, _m.MultiPeriodDiscriminator
+    DiscriminatorS, MultiScaleDiscriminator = _m.DiscriminatorS, _m.MultiScaleDiscriminator
 for _name in ("feature_loss", "hinge_generator_loss", "hinge_discriminator_loss", "ls_generator_loss", "ls_discriminator_loss",
               "LRELU_SLOPE", "get_padding"):
     globals().setdefault(_name, getattr(_m, _name))

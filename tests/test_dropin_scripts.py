@@ -112,8 +112,12 @@ assert mel_spectrogram.__code__.co_filename.startswith({dropin!r})
 assert HiFiGAN.__module__.startswith("neural-vocoders-as-speech-enhancers_b200"), HiFiGAN.__module__
 assert iSTFTNet.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")
 assert HDDemucas.__module__ == "Models.hddemucas" and sys.modules["Models.hddemucas"].__file__.startswith({ref!r})
-assert MultiPeriodDiscriminator.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")  # B200-backed discriminators
-assert MultiScaleDiscriminator.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")
+import os
+if os.environ.get("NVSE_B200_DISCRIMINATORS", "0") == "1":   # opt-in: B200-backed discriminators
+    assert MultiPeriodDiscriminator.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")
+    assert MultiScaleDiscriminator.__module__.startswith("neural-vocoders-as-speech-enhancers_b200")
+else:                                                        # default: the reference's own classes
+    assert MultiPeriodDiscriminator.__module__ == "_nvse_reference_models" and MultiScaleDiscriminator.__module__ == "_nvse_reference_models"
 import Models.models
 assert Models.models.__file__.startswith({dropin!r})
 assert feature_loss.__code__.co_filename.startswith({ref!r})  # everything else of Models/models.py stays the reference's own
@@ -142,8 +146,9 @@ print("RESOLVE-OK")
 
 
 @needs_ref
-def test_names_resolve_to_dropin_even_behind_the_script_directory():
-    p = _run(["-c", _RESOLVE.format(ref=REF, dropin=DROPIN)], cwd=REF, env=_env(True))
+@pytest.mark.parametrize("b200_discriminators", ["0", "1"])
+def test_names_resolve_to_dropin_even_behind_the_script_directory(b200_discriminators):
+    p = _run(["-c", _RESOLVE.format(ref=REF, dropin=DROPIN)], cwd=REF, env=_env(True, {"NVSE_B200_DISCRIMINATORS": b200_discriminators}))
     assert "RESOLVE-OK" in p.stdout
 
 
@@ -224,7 +229,9 @@ def test_train_script_unmodified(tmp_path):
     tlist = tmp_path / "train.txt"
     tlist.write_text("".join(f"DUMMY1/{n}|t\n" for n in names[:4]))
     ck = {}
-    for arm, dropin, extra in (("reference", False, {"NVIDIA_TF32_OVERRIDE": "0"}), ("dropin", True, {})):
+    # NVSE_B200_DISCRIMINATORS=1: generator AND both discriminators on this repo's kernels (the drop-in's default keeps the
+    # reference's discriminator classes, which run cuDNN's faster TF32 convolutions)
+    for arm, dropin, extra in (("reference", False, {"NVIDIA_TF32_OVERRIDE": "0"}), ("dropin", True, {"NVSE_B200_DISCRIMINATORS": "1"})):
         c = dict(cfg, checkpoint_path=str(tmp_path / f"ckpt_{arm}"), input_training_wav_list=str(tlist), input_validation_wav_list=str(vlist))
         cp = tmp_path / f"train_{arm}.json"
         cp.write_text(json.dumps(c))
