@@ -578,7 +578,7 @@ def main():
                      "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"] + ", sustained bf16",
                      "launches": tc_n, "avg_launch_ms": tc_ms / tc_n if tc_n else None, "share_of_step": tc_ms / all_ms if all_ms else None,
                      "timing": "per-launch CUDA events on the launching stream, separate pass of the same K steps"},
-        "frontend": {"kernel": "mel_frontend_kernel", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": fe_gbs / pk["hbm_gbs"],
+        "frontend": {"kernel": "mel_frontend2_kernel (csrc/frontend.cu)", "achieved": fe_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": fe_gbs / pk["hbm_gbs"],
                      "achieved_alone": fe_alone_gbs, "frac_alone": fe_alone_gbs / pk["hbm_gbs"], "ms_alone": fe_alone_ms,
                      "note": "achieved = inside the timed step (per-launch events); achieved_alone = the kernel over the whole shard before the step",
                      "bound": "hbm (algorithmic bytes: waveform in + log-mel out)"},
