@@ -274,6 +274,37 @@ def disc_step(pkg, dev, batch=16, samples=8192, steps=3):
     return out
 
 
+def cfg4_istftnet(pkg, synth, dev, batch=32, frames=690, reps=5):
+    """cfg4 of BASELINE.json: the iSTFTNet generator (Models/istftnet.py:271-328) on mel [32, 80, 690] (32 x 8 s), 16-bit
+    tensor-core path, device-resident; algorithmic FLOPs = 4.116e8 per frame."""
+    cfg = synth.ISTFTNET
+    gen = pkg.iSTFTNet(synth.AttrDict(cfg))
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_state(cfg, 1234, "init").items()})
+    gen = gen.to(dev).eval()
+    gen.remove_weight_norm()
+    gen.precision = "bf16"
+    mel = torch.from_numpy(synth.make_mel(batch, frames, 1)).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            out = gen(mel)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            gen(mel)
+        e1.record()
+        torch.cuda.synchronize()
+        gen.precision = "fp32"
+        ref = gen(mel[:2]).double()
+    ms = e0.elapsed_time(e1) / reps
+    deg = out[:2].double()
+    ref, deg = ref - ref.mean(-1, keepdim=True), deg - deg.mean(-1, keepdim=True)
+    snr = float((10 * torch.log10(ref.pow(2).sum(-1) / (ref - deg).pow(2).sum(-1).clamp_min(1e-30))).min())
+    return {"config": f"cfg4: iSTFTNet, mel [{batch}, 80, {frames}] -> wav, device-resident, 16-bit tensor-core path", "ms": ms,
+            "value": batch * out.shape[-1] / SR / (ms * 1e-3), "unit": "audio-sec/sec", "tflops_algorithmic": 4.116e8 * batch * frames / ms / 1e9,
+            "parity_snr_db_vs_fp32_path": snr}
+
+
 def cfg1_gpu(voc, synth, dev, reps=30):
     """cfg1 of BASELINE.json on the GPU through the public host-to-host call: batch 1, 2 s -> mel -> HiFi-GAN V1 -> wav."""
     wav = torch.from_numpy(synth.make_wave(1, 2 * SR, 3)).pin_memory()
@@ -590,6 +621,7 @@ def main():
     extras = world == 1 and not args.no_extras
     if extras:  # secondary numbers: none of them may cost the headline line
         for key, fn in (("cfg1_gpu", lambda: cfg1_gpu(voc, synth, dev)), ("cfg2_frontend", lambda: cfg2_frontend(voc, synth, cfg, dev, pk)),
+                        ("cfg4_istftnet", lambda: cfg4_istftnet(pkg, synth, dev)),
                         ("eager_b200", lambda: eager_competitor(args, synth, cfg, dev, wav_dev)),
                         ("train_step", lambda: train_step(pkg, synth, cfg, dev)), ("disc_step", lambda: disc_step(pkg, dev))):
             try:

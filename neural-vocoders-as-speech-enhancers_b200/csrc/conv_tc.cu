@@ -359,8 +359,8 @@ done:
   if (warp == kEpiWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// fp32 [j][ci][co] -> bf16 [j][ci/KC][(ci%KC)/8][co][ci%8]; the source may be wider (cout_src, first column co0) and have fewer
-// input channels (cin_src <= Cin: the rest of the image is zero)
+// fp32 [j][ci][co] -> bf16 [j][ci/KC][(ci%KC)/8][co][ci%8]; the source may be wider (cout_src, first column co0), or narrower
+// (columns at or beyond cout_src are zero), and have fewer input channels (cin_src <= Cin: the rest of the image is zero)
 __global__ void __launch_bounds__(256) pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img,
                                                               int Cin, int Cout, int ktaps, int kc, int as_fp16, int cin_src,
                                                               int cout_src, int co0) {
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) pack_weight_tc_kernel(const float* __rest
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     const int co = e % Cout, ci = (e / Cout) % Cin, j = e / ((int64_t)Cout * Cin);
     const int64_t dst = ((((int64_t)j * (Cin / kc) + ci / kc) * (kc / 8) + (ci % kc) / 8) * Cout + co) * 8 + (ci % 8);
-    const float v = ci < cin_src ? w[((int64_t)j * cin_src + ci) * cout_src + co0 + co] : 0.0f;
+    const float v = (ci < cin_src && co0 + co < cout_src) ? w[((int64_t)j * cin_src + ci) * cout_src + co0 + co] : 0.0f;
     if (as_fp16) reinterpret_cast<__half*>(img)[dst] = __float2half_rn(v);  // same 16-bit slots, IEEE half
     else img[dst] = __float2bfloat16_rn(v);
   }
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) pack_weight_tc_kernel(const float* __rest
 int launch_pack_weight_tc_slice(const float* w_kio, int cin_src, int cout_src, int co0, __nv_bfloat16* img, int Cin, int Cout,
                                 int ktaps, cudaStream_t st, bool as_fp16) {
   NVSE_REQUIRE(tc_supported(Cin, Cout), NVSE_ERR_UNSUPPORTED, "tensor-core conv: Cin=%d / Cout=%d unsupported", Cin, Cout);
-  NVSE_REQUIRE(cin_src <= Cin && co0 >= 0 && co0 + Cout <= cout_src, NVSE_ERR_INVALID, "tensor-core conv: bad weight slice");
+  NVSE_REQUIRE(cin_src <= Cin && co0 >= 0 && co0 < cout_src, NVSE_ERR_INVALID, "tensor-core conv: bad weight slice");
   const int64_t n = (int64_t)Cin * Cout * ktaps;
   pack_weight_tc_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, st>>>(w_kio, img, Cin, Cout, ktaps, tc_kchunk(Cin),
                                                                                             as_fp16 ? 1 : 0, cin_src, cout_src, co0);

@@ -182,6 +182,30 @@ int ensure_side_streams(nvse_generator* g) {
 
 // out_i16 != null: the waveform is wanted as PCM_16 (int16) INSTEAD of float: fused into conv_post where the last
 // kernel is the T32 conv_post kernel (HiFiGAN on the tensor-core plan), a separate quantisation pass otherwise.
+// z[b][t][co] += sum_ci w[pad - t][ci][co] * lrelu(x[b][1][ci], 0.01) for t = 0 .. pad: the contribution of row 0 of
+// ReflectionPad1d((1, 0)) (= x row 1; istftnet.py:296,312) to the first output rows of conv_post, which the shifted plain
+// convolution of the tensor-core path reads as zero.  x in the T32 layout, z rows `pitch` floats apart, w = Layer::w [k][Cin][Cout].
+__global__ void post_reflect_fix_kernel(const float* __restrict__ x, int64_t x_bstride, const float* __restrict__ w, float* __restrict__ z,
+                                        int64_t z_bstride, int pitch, int Cin, int Cout, int pad) {
+  const int64_t b = blockIdx.x;
+  for (int e = threadIdx.x; e < (pad + 1) * Cout; e += blockDim.x) {
+    const int t = e / Cout, co = e - t * Cout;
+    float acc = 0.0f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float v = x[b * x_bstride + t32_off(1, ci, Cin)];
+      acc = fmaf(w[((int64_t)(pad - t) * Cin + ci) * Cout + co], v >= 0.0f ? v : v * 0.01f, acc);
+    }
+    z[b * z_bstride + (int64_t)t * pitch + co] += acc;
+  }
+}
+static int launch_post_reflect_fix(const float* x_t32, const Layer& post, float* z, int pitch, int64_t B, int64_t T, cudaStream_t st) {
+  const int pad = (post.k - 1) / 2;
+  NVSE_REQUIRE(T >= pad + 1, NVSE_ERR_UNSUPPORTED, "iSTFTNet conv_post on the tensor cores needs at least %d rows", pad + 1);
+  post_reflect_fix_kernel<<<(unsigned)B, 128, 0, st>>>(x_t32, t32_rows(T) * post.Cin, post.w, z, (T + 1) * pitch, pitch, post.Cin, post.Cout, pad);
+  NVSE_LAUNCH_CHECK("post_reflect_fix_kernel");
+  return NVSE_OK;
+}
+
 // frames_dev != null (ragged batch): mel frames per utterance on the device; utterance b is computed exactly as if it were
 // alone with frames_dev[b] frames (every kernel treats its rows beyond that like rows beyond the end of the sequence); its
 // output samples beyond its own length are undefined.  Tensor-core HiFiGAN plan only.
@@ -361,6 +385,29 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
     return launch_conv_f32(a, B, st);
   }
   // istftnet.py:311-318: lrelu(0.01) -> ReflectionPad1d((1,0)) -> conv_post -> exp / sin -> iSTFT
+  static const bool post_tc_env = [] { const char* e = std::getenv("NVSE_POST_TC"); return !(e && e[0] == '0'); }();
+  if (tc && t32 && post.w_post && post_tc_env && T >= 2) {
+    // 16-bit path: conv_post as a tensor-core GEMM (IEEE-half operands like conv_pre; 26 % of an iSTFTNet forward on the fp32
+    // CUDA cores otherwise).  Row v of the reflection-padded input is row v - 1 of x (v >= 1), so the layer is a plain
+    // convolution with every tap offset shifted by -1 ... except for padded row 0 (= x row 1), which only the first
+    // (k - 1) / 2 + 1 output rows read: post_reflect_fix_kernel adds that term.
+    const int pitch = post.post_cout;
+    ConvTcArgs ta{};
+    ta.x = bufA; ta.x_bstride = t32_rows(T) * post.Cin; ta.Tin = (int)T; ta.Cin = post.Cin; ta.Cout = pitch; ta.x_t32 = 1;
+    ta.wimg = reinterpret_cast<const __nv_bfloat16*>(post.w_post); ta.bias = post.bias_post; ta.ops_f16 = 1;
+    ta.y = bufU; ta.y_bstride = (T + 1) * pitch; ta.y_ld = pitch; ta.Tout = (int)T + 1;
+    conv1d_taps(post.k, 1, &ta.taps);
+    for (int i = 0; i < ta.taps.ntaps; ++i) ta.taps.off[i] -= 1;
+    ta.out_mul = 1; ta.out_add = 0; ta.Trows = (int)T + 1;
+    ta.in_slope = 0.01f; ta.out_slope = 1.0f; ta.out_scale = 1.0f;
+    ta.in_lens = lens;
+    if (int rc = launch_conv_tc(ta, B, st)) return rc;
+    if (int rc = launch_post_reflect_fix(bufA, post, bufU, pitch, B, T, st)) return rc;
+    float* wav = out_i16 ? bufR : out;
+    if (int rc = launch_istft_head(bufU, wav, B, T + 1, c.istft_n_fft, c.istft_hop, st, lens, pitch)) return rc;
+    if (out_i16) return launch_pcm16(bufR, out_i16, B * nvse_generator_out_samples(g, F), st);
+    return NVSE_OK;
+  }
   a.reflect_left = 1;
   a.Tin = a.Tout = a.Trows = (int)T + 1; a.y = bufU; a.y_bstride = (T + 1) * post.Cout;
   if (int rc = launch_conv_f32(a, B, st)) return rc;
@@ -394,6 +441,12 @@ int finalize_plan(nvse_generator* g) {
         L.pre_n = nsl;
       }
     }
+    if (L.name == "conv_post" && g->cfg.kind == NVSE_GEN_ISTFTNET && !L.w_post && L.Cout <= 32 && tc_supported(L.Cin, 32) &&
+        L.k <= kMaxTaps && (L.k & 1)) {
+      L.post_cout = 32;
+      NVSE_CUDA_CHECK(cudaMalloc(&L.w_post, sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.post_cout, L.k)));
+      NVSE_CUDA_CHECK(cudaMalloc(&L.bias_post, sizeof(float) * L.post_cout));
+    }
     if (!wants_tc(L)) continue;
     const size_t bytes = sizeof(__nv_bfloat16) * tc_weight_image_elems(L.Cin, L.Cout, L.k);
     if (!L.w_bf16) NVSE_CUDA_CHECK(cudaMalloc(&L.w_bf16, bytes));
@@ -417,6 +470,13 @@ int build_extra_images(nvse_generator* g, cudaStream_t st) {
       if (int rc = launch_pack_weight_tc_slice(L.w, L.Cin, L.Cout, sl * L.pre_cout, reinterpret_cast<__nv_bfloat16*>(L.w_pre[sl]),
                                                L.pre_cin, L.pre_cout, L.k, st, true))
         return rc;
+  for (Layer& L : g->layers)
+    if (L.w_post) {
+      if (int rc = launch_pack_weight_tc_slice(L.w, L.Cin, L.Cout, 0, reinterpret_cast<__nv_bfloat16*>(L.w_post), L.Cin, L.post_cout, L.k, st, true))
+        return rc;
+      NVSE_CUDA_CHECK(cudaMemsetAsync(L.bias_post, 0, sizeof(float) * L.post_cout, st));
+      NVSE_CUDA_CHECK(cudaMemcpyAsync(L.bias_post, L.bias, sizeof(float) * L.Cout, cudaMemcpyDeviceToDevice, st));
+    }
   return NVSE_OK;
 }
 
@@ -488,6 +548,8 @@ extern "C" int nvse_generator_destroy(nvse_generator* g) {
     cudaFree(L.wT);
     cudaFree(L.wT_bf16);
     for (void* q : L.w_pre) cudaFree(q);
+    cudaFree(L.w_post);
+    cudaFree(L.bias_post);
     cudaFree(L.w_ups);
   }
   delete g;

@@ -24,6 +24,11 @@ struct Layer {
   void* w_ups = nullptr;   // ConvTranspose1d with k = 2 * stride: stage-ordered half image of the persistent all-phase kernel (ups_tc.cuh)
   void* w_pre[4] = {nullptr, nullptr, nullptr, nullptr};
   int pre_cin = 0, pre_cout = 0, pre_n = 0;
+  // iSTFTNet's conv_post on the tensor cores (16-bit path): IEEE-half image with the output channels zero-padded to
+  // post_cout (n_fft + 2 = 18 -> 32), and the bias padded likewise
+  void* w_post = nullptr;
+  float* bias_post = nullptr;
+  int post_cout = 0;
   bool have_w = false, have_bias = false;
   float* wT = nullptr;     // training path: per-tap transposed weights [k][Cout][Cin] (the dgrad operand), built lazily
   void* wT_bf16 = nullptr; // training path, tensor-core dgrad: the bf16 image of wT (as a layer with Cin <-> Cout)
@@ -50,7 +55,9 @@ struct nvse_generator {
 namespace nvse {
 
 // lens: ragged batch, valid conv_post rows per utterance EXCLUDING the reflected one (null: all Tp - 1)
-int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st, RowLens lens = RowLens{nullptr, 1, 0});
+// zpitch: floats per row of z (0: n_fft + 2, dense)
+int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st, RowLens lens = RowLens{nullptr, 1, 0},
+                      int zpitch = 0);
 // dz rows have `pitch` >= n_fft + 2 floats (extra columns zeroed)
 int launch_istft_head_bwd(const float* z, const float* gout, float* dz, int64_t B, int64_t Tp, int n_fft, int hop, int pitch,
                           cudaStream_t st);

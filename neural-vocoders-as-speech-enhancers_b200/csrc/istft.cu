@@ -21,7 +21,7 @@ constexpr int kGroupsPerCta = 128;  // hop-groups (of `hop` output samples) per 
 
 template <int NFFT>
 __global__ void __launch_bounds__(kGroupsPerCta) istft_head_kernel(const float* __restrict__ z, float* __restrict__ out,
-                                                                    int64_t Tp_all, int hop, const RowLens lens) {
+                                                                    int64_t Tp_all, int hop, const RowLens lens, int zpitch) {
   constexpr int NB = NFFT / 2 + 1;
   constexpr int CH = NFFT + 2;
   constexpr int FS = NFFT + 1;  // padded frame stride in smem
@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(kGroupsPerCta) istft_head_kernel(const float* 
   }
   __syncthreads();
 
-  const float* zb = z + b * Tp_all * CH;
+  const float* zb = z + b * Tp_all * zpitch;
   for (int fi = tid; fi < nframes; fi += kGroupsPerCta) {
-    const float* zr = zb + (tau_lo + fi) * CH;
+    const float* zr = zb + (tau_lo + fi) * zpitch;
     float re[NB], im[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
@@ -185,30 +185,31 @@ __global__ void __launch_bounds__(256) unpad_reflect_left_kernel(const float* __
 }
 
 template <int NFFT>
-int launch_istft(const float* z, float* out, int64_t B, int64_t Tp, int hop, const RowLens& lens, cudaStream_t st) {
+int launch_istft(const float* z, float* out, int64_t B, int64_t Tp, int hop, const RowLens& lens, int zpitch, cudaStream_t st) {
   const int R = NFFT / hop;
   const int max_frames = kGroupsPerCta + R;
   const size_t smem = sizeof(float) * (3 * NFFT + (size_t)max_frames * (NFFT + 1));
   NVSE_CUDA_CHECK(cudaFuncSetAttribute(istft_head_kernel<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((Tp - 1 + kGroupsPerCta - 1) / kGroupsPerCta), (unsigned)B);
   ProfScope prof("istft_head", NFFT + 2, 1, 0.0, 4.0 * (double)B * ((double)Tp * (NFFT + 2) + (double)(Tp - 1) * hop), st);
-  istft_head_kernel<NFFT><<<grid, kGroupsPerCta, smem, st>>>(z, out, Tp, hop, lens);
+  istft_head_kernel<NFFT><<<grid, kGroupsPerCta, smem, st>>>(z, out, Tp, hop, lens, zpitch > 0 ? zpitch : NFFT + 2);
   NVSE_LAUNCH_CHECK("istft_head_kernel");
   return NVSE_OK;
 }
 
 }  // namespace
 
-int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st, RowLens lens) {
+int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, cudaStream_t st, RowLens lens, int zpitch) {
+  NVSE_REQUIRE(zpitch == 0 || zpitch >= n_fft + 2, NVSE_ERR_INVALID, "istft head: row pitch %d below n_fft + 2", zpitch);
   NVSE_REQUIRE(hop >= 1 && n_fft % hop == 0, NVSE_ERR_UNSUPPORTED, "istft head: hop=%d must divide n_fft=%d", hop, n_fft);
   NVSE_REQUIRE(B <= 65535, NVSE_ERR_INVALID, "istft head: batch too large");
   if (B == 0 || Tp <= 1) return NVSE_OK;
   switch (n_fft) {
-    case 4: return launch_istft<4>(z, out, B, Tp, hop, lens, st);
-    case 8: return launch_istft<8>(z, out, B, Tp, hop, lens, st);
-    case 16: return launch_istft<16>(z, out, B, Tp, hop, lens, st);
-    case 32: return launch_istft<32>(z, out, B, Tp, hop, lens, st);
-    case 64: return launch_istft<64>(z, out, B, Tp, hop, lens, st);
+    case 4: return launch_istft<4>(z, out, B, Tp, hop, lens, zpitch, st);
+    case 8: return launch_istft<8>(z, out, B, Tp, hop, lens, zpitch, st);
+    case 16: return launch_istft<16>(z, out, B, Tp, hop, lens, zpitch, st);
+    case 32: return launch_istft<32>(z, out, B, Tp, hop, lens, zpitch, st);
+    case 64: return launch_istft<64>(z, out, B, Tp, hop, lens, zpitch, st);
     default:
       return fail(NVSE_ERR_UNSUPPORTED, "istft head: n_fft=%d not supported (4, 8, 16, 32, 64)", n_fft);
   }
@@ -259,5 +260,5 @@ extern "C" int nvse_istft_head_backward_f32(const float* z, const float* dout, f
 extern "C" int nvse_istft_head_f32(const float* z, float* out, int64_t B, int64_t Tp, int n_fft, int hop, void* stream) {
   using namespace nvse;
   NVSE_REQUIRE(z && out && B >= 0 && Tp >= 1, NVSE_ERR_INVALID, "nvse_istft_head_f32: bad argument");
-  return launch_istft_head(z, out, B, Tp, n_fft, hop, as_stream(stream), RowLens{nullptr, 1, 0});
+  return launch_istft_head(z, out, B, Tp, n_fft, hop, as_stream(stream), RowLens{nullptr, 1, 0}, 0);
 }
