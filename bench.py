@@ -305,6 +305,27 @@ def cfg4_istftnet(pkg, synth, dev, batch=32, frames=690, reps=5):
             "parity_snr_db_vs_fp32_path": snr}
 
 
+def cfg3_hifigan(gen, synth, dev, pk, precision, batch=32, frames=690, reps=5):
+    """cfg3 of BASELINE.json: the HiFi-GAN V1 generator alone on mel [32, 80, 690] (32 x 8 s), device-resident; BASELINE.md 2:
+    1.3559e13 FLOP, the north star's >= 50 % of the sustained bf16 peak means <= 19.4 ms."""
+    mel = torch.from_numpy(synth.make_mel(batch, frames, 1)).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            gen(mel)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = gen(mel)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = FLOP_PER_FRAME * batch * frames / ms / 1e9
+    return {"config": f"cfg3: HiFi-GAN V1 generator, mel [{batch}, 80, {frames}] -> wav, device-resident, precision {precision}", "ms": ms,
+            "value": batch * out.shape[-1] / SR / (ms * 1e-3), "unit": "audio-sec/sec", "tflops_algorithmic": tf,
+            "frac_of_sustained_bf16_peak": tf / pk["bf16_tflops_sustained"]}
+
+
 def cfg1_gpu(voc, synth, dev, reps=30):
     """cfg1 of BASELINE.json on the GPU through the public host-to-host call: batch 1, 2 s -> mel -> HiFi-GAN V1 -> wav."""
     wav = torch.from_numpy(synth.make_wave(1, 2 * SR, 3)).pin_memory()
@@ -621,6 +642,7 @@ def main():
     extras = world == 1 and not args.no_extras
     if extras:  # secondary numbers: none of them may cost the headline line
         for key, fn in (("cfg1_gpu", lambda: cfg1_gpu(voc, synth, dev)), ("cfg2_frontend", lambda: cfg2_frontend(voc, synth, cfg, dev, pk)),
+                        ("cfg3_hifigan", lambda: cfg3_hifigan(gen, synth, dev, pk, args.precision)),
                         ("cfg4_istftnet", lambda: cfg4_istftnet(pkg, synth, dev)),
                         ("eager_b200", lambda: eager_competitor(args, synth, cfg, dev, wav_dev)),
                         ("train_step", lambda: train_step(pkg, synth, cfg, dev)), ("disc_step", lambda: disc_step(pkg, dev))):
