@@ -459,7 +459,7 @@ int launch_conv_tc_phases(const ConvTcArgs& a, const ConvTaps* phase_taps, const
     static const int forced = [] { const char* e = std::getenv("NVSE_TC_NTILE"); return e ? std::atoi(e) : 0; }();
     // ConvTranspose1d launches (several phases, double-buffered TMEM) are memory-bound: small tiles keep
     // several CTAs resident per SM (TMEM columns = Cout * 2 * ntile), which hides the staging latency
-    const int want = forced > 0 ? forced : (nphase > 1 ? (a.Cout >= 64 ? 1 : 2) : (a.Cout >= 128 ? 2 : 4));
+    const int want = forced > 0 ? forced : a.ntile_hint > 0 ? a.ntile_hint : (nphase > 1 ? (a.Cout >= 64 ? 1 : 2) : (a.Cout >= 128 ? 2 : 4));
     const int64_t tiles_needed = ((int64_t)a.Trows + kTileM - 1) / kTileM;
     while (ntile * 2 <= want && a.Cout * gsz * nbuf * ntile * 2 <= 512 && ntile * 2 <= tiles_needed &&
            tc_smem_bytes_rows(a.Cin, a.Cout, kTileM * ntile * 2 + (mx - mn), a.split_act != 0, 2) <= kSmemBudget)

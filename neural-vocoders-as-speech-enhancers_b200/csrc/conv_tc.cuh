@@ -42,6 +42,7 @@ struct ConvTcArgs {
   int ops_f16;            // stage the (fp32) activations as IEEE half; `wimg` must then be a half image.  Used by the
                           // upsamplers, where bf16 rounding of the WEIGHTS is the largest error of the whole path
   RowLens in_lens;        // ragged batch: valid INPUT rows per utterance (rows beyond read as zero); lens == null: Tin
+  int ntile_hint;         // 128-row tiles per CTA (0: chosen by the launcher).  Memory-bound thin layers want 1: several small CTAs per SM
 };
 
 // shared memory one CTA of the kernel needs for this shape (used to decide whether split fits)

@@ -401,6 +401,7 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
     ta.out_mul = 1; ta.out_add = 0; ta.Trows = (int)T + 1;
     ta.in_slope = 0.01f; ta.out_slope = 1.0f; ta.out_scale = 1.0f;
     ta.in_lens = lens;
+    ta.ntile_hint = 1;  // HBM-bound (128 -> 32 channels): 0.70 -> 0.45 ms per 32 x 44161 rows with several 128-row CTAs per SM
     if (int rc = launch_conv_tc(ta, B, st)) return rc;
     if (int rc = launch_post_reflect_fix(bufA, post, bufU, pitch, B, T, st)) return rc;
     float* wav = out_i16 ? bufR : out;
