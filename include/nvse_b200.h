@@ -294,6 +294,21 @@ NVSE_API int nvse_weight_norm_backward_f32(const float* v, const float* g, const
 NVSE_API int nvse_istft_head_backward_f32(const float* z, const float* dout, float* dz, int64_t B, int64_t Tp, int n_fft,
                                  int hop, void* stream);
 
+/* ---- fused wav -> wav call: the loop body of infers/inference_hifigan.py:82-95 for a batch ------------
+ *   x = mel_spectrogram(wav, ...);  y = generator(x);  [sf.write(..., 'PCM_16')]
+ * in one library call on the 16-bit tensor-core path: the front-end writes its log-mel straight into the channels-last,
+ * zero-padded layout conv_pre's tensor-core launch stages from (no [B, 80, F] tensor, no transpose pass), the generator runs
+ * as nvse_generator_forward / _pcm16 / _ragged do, bit-identical to calling the two stages separately.
+ * wav [B, T] (row stride wav_row_stride); samples_dev: NULL, or [B] int32 on the device = samples per utterance of a padded
+ * batch (float output only); exactly one of out [B, out_samples(frames)] / out_pcm16 (same shape, int16) is non-NULL;
+ * frames = nvse_frontend_num_frames(fe, T).  workspace: nvse_vocoder_workspace_bytes.  nvse_vocoder_mel_pitch: channels per
+ * frame of that internal layout (0 when this generator's conv_pre cannot run on the tensor cores: use the two-call path). */
+NVSE_API int nvse_vocoder_mel_pitch(const nvse_generator* g);
+NVSE_API size_t nvse_vocoder_workspace_bytes(const nvse_frontend* fe, const nvse_generator* g, int64_t B, int64_t T);
+NVSE_API int nvse_vocoder_forward(const nvse_frontend* fe, nvse_generator* g, const float* wav, int64_t B, int64_t T,
+                         int64_t wav_row_stride, const int32_t* samples_dev, float* out, int16_t* out_pcm16, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* ---- discriminators: MultiPeriodDiscriminator / MultiScaleDiscriminator -------------------------
  * Replaces the convolution stacks of DiscriminatorP (Models/models.py:15-87: Conv2d (k,1) / (stride,1) over
  * [B, C, T/period, period]) and DiscriminatorS (Models/models.py:187-214: grouped strided Conv1d over [B, C, T]) and what

@@ -258,6 +258,57 @@ class GeneratorEngine:
                                _lib.ptr(self.workspace), self.workspace.numel(), prec, stream))
         return out if x.is_cuda else out.to(x.device)
 
+    # ---- fused wav -> wav (inference, 16-bit path) -------------------------------------------
+    def can_vocode(self, module, dev):
+        """True when ``vocode`` applies: 16-bit tensor-core precision and a conv_pre the tensor-core launch takes."""
+        if resolve_precision(getattr(module, "precision", None)) != _lib.PRECISION_BF16:
+            return False
+        if self.handle is None or self.device != dev or self.weights_key is None:
+            self._ensure(module, dev)  # the pitch is a property of the configuration: a loaded handle answers without a re-check
+        return int(_lib.load().nvse_vocoder_mel_pitch(self.handle)) > 0
+
+    def vocode(self, module, frontend, wav, lengths=None, pcm16=False, out=None):
+        """``nvse_vocoder_forward``: wav ``[B, T]`` on the device -> waveform ``[B, samples]`` (int16 PCM with ``pcm16``) in one
+        library call -- the front-end writes the log-mel straight into conv_pre's staging layout (no ``[B, 80, F]`` tensor, no
+        transpose pass); bit-identical to ``generator(mel_spectrogram(wav))``.  ``lengths``: int tensor ``[B]`` of samples per
+        utterance of a padded batch (float output only)."""
+        lib = _lib.load()
+        dev = wav.device
+        self._ensure(module, dev)
+        wd = wav.detach().to(torch.float32)
+        if wd.dim() != 2 or wd.stride(-1) != 1:
+            wd = wd.reshape(wd.shape[0], -1).contiguous()
+        batch, samples = wd.shape
+        frames = int(lib.nvse_frontend_num_frames(frontend, samples))
+        n_out = int(lib.nvse_generator_out_samples(self.handle, frames))
+        odt = torch.int16 if pcm16 else torch.float32
+        if out is not None:
+            if not (out.is_cuda and out.device == dev and out.dtype == odt and tuple(out.shape) == (batch, n_out) and out.is_contiguous()):
+                raise RuntimeError(f"out must be a contiguous {odt} tensor of shape {(batch, n_out)} on {dev}")
+        else:
+            out = torch.empty((batch, n_out), dtype=odt, device=dev)
+        if batch == 0:
+            return out
+        need = int(lib.nvse_vocoder_workspace_bytes(frontend, self.handle, batch, samples))
+        if need == 0:
+            raise _lib.NvseError("the fused wav -> wav call does not apply to this generator (conv_pre is not on the tensor cores)")
+        if self.workspace is None or self.workspace.numel() < need or self.workspace.device != dev:
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        ld = None
+        if lengths is not None:
+            if pcm16:
+                raise RuntimeError("ragged batches deliver float output (quantise with Vocoder.pcm16)")
+            ld = torch.as_tensor(lengths).to(dev, torch.int32).contiguous()
+            if ld.shape != (batch,):
+                raise RuntimeError(f"lengths must have shape [{batch}], got {tuple(ld.shape)}")
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(lib.nvse_vocoder_forward(frontend, self.handle, _lib.ptr(wd), batch, samples, wd.stride(0) if batch > 1 else samples,
+                                                _lib.ptr(ld), None if pcm16 else _lib.ptr(out), _lib.ptr(out) if pcm16 else None,
+                                                _lib.ptr(self.workspace), self.workspace.numel(), stream))
+        return out
+
     # ---- training ---------------------------------------------------------------------
     def forward_train(self, module, x):
         """Forward that keeps every convolution input on an fp32 tape; returns (out, tape, precision).  The arithmetic is

@@ -92,6 +92,9 @@ PROTOTYPES = {
     "nvse_conv_transpose1d_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_weight_norm_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "nvse_istft_head_backward_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _vp]),
+    "nvse_vocoder_mel_pitch": (_i, [_vp]),
+    "nvse_vocoder_workspace_bytes": (_sz, [_vp, _vp, _i64, _i64]),
+    "nvse_vocoder_forward": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nvse_disc_conv_out_len": (_i64, [_i64, _i, _i, _i]),
     "nvse_disc_conv_forward_f32": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "nvse_disc_conv_backward_scratch_bytes": (_sz, [_i64, _i, _i, _i64, _i, _i, _i, _i, _i]),

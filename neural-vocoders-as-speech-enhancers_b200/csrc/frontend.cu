@@ -247,6 +247,8 @@ struct Frontend2Params {
   const int4* items;         // mel projection work items: (mel row, first tap, taps, slices of the row | slice index << 8)
   int nitems;                // padded so that the slices of a row never straddle a warp
   const int* lens;           // ragged batch: samples per utterance (<= T; reflect padding and frame count follow it), or null
+  int out_cl_pitch;          // > 0: store the log-mel CHANNELS-LAST, out [B, F, pitch] with channels n_mels .. pitch - 1 zero -- the
+                             // layout conv_pre's tensor-core launch stages from (the fused wav -> wav call), no transpose pass
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -398,6 +400,14 @@ __global__ void __launch_bounds__(kFe2Threads, 4) mel_frontend2_kernel(const Fro
     __syncthreads();  // output tile complete
 
     // coalesced store of the [n_mels][8] tile: 8 consecutive lanes write 8 consecutive frames of one mel row
+    if (q.out_cl_pitch > 0) {  // [frame][channel]: a frame's n_mels values (+ zero padding) are one contiguous run
+      float* ob = p.out + (b * p.F + f0) * q.out_cl_pitch;
+      for (int e = tid; e < kFe2Frames * q.out_cl_pitch; e += kFe2Threads) {
+        const int j = e / q.out_cl_pitch, m = e - j * q.out_cl_pitch;
+        if (j < nf) ob[e] = m < p.n_mels ? sout[m * kFe2Frames + j] : 0.0f;
+      }
+      continue;
+    }
     float* obase = p.out + b * p.n_mels * p.F + f0;
     for (int e = tid; e < p.n_mels * kFe2Frames; e += kFe2Threads) {
       const int m = e >> 3, j = e & 7;
@@ -1051,7 +1061,26 @@ extern "C" int64_t nvse_frontend_num_frames(const nvse_frontend* fe, int64_t T) 
 }
 
 static int frontend_mel_impl(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride, const int* lens,
-                             float* out, void* stream);
+                             float* out, void* stream, int cl_pitch = 0);
+
+namespace nvse {
+// the log-mel written channels-last [B, F, pitch] (zero above n_mels): what conv_pre's tensor-core launch reads (generator.cu)
+int frontend_mel_cl(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride, const int* lens, int pitch,
+                    float* out, cudaStream_t st) {
+  NVSE_REQUIRE(fe && pitch >= fe->n_mels, NVSE_ERR_INVALID, "frontend_mel_cl: pitch %d below n_mels", pitch);
+  return frontend_mel_impl(fe, y, B, T, y_row_stride, lens, out, st, pitch);
+}
+// frames_dev[b] = 1 + samples_dev[b] / hop
+__global__ void frames_from_samples_kernel(const int* __restrict__ samples, int* __restrict__ frames, int64_t B, int hop) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) frames[i] = 1 + samples[i] / hop;
+}
+int launch_frames_from_samples(const nvse_frontend* fe, const int* samples_dev, int* frames_dev, int64_t B, cudaStream_t st) {
+  frames_from_samples_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(samples_dev, frames_dev, B, fe->hop);
+  NVSE_LAUNCH_CHECK("frames_from_samples_kernel");
+  return NVSE_OK;
+}
+}  // namespace nvse
 
 extern "C" int nvse_frontend_mel_f32(const nvse_frontend* fe, const float* y, int64_t B, int64_t T,
                                      int64_t y_row_stride, float* out, void* stream) {
@@ -1065,7 +1094,7 @@ extern "C" int nvse_frontend_mel_ragged_f32(const nvse_frontend* fe, const float
 }
 
 static int frontend_mel_impl(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride, const int* lens,
-                             float* out, void* stream) {
+                             float* out, void* stream, int cl_pitch) {
   using namespace nvse;
   NVSE_REQUIRE(fe && y && out, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: null argument");
   NVSE_REQUIRE(B >= 0 && y_row_stride >= T, NVSE_ERR_INVALID, "nvse_frontend_mel_f32: bad B/stride");
@@ -1103,6 +1132,7 @@ static int frontend_mel_impl(const nvse_frontend* fe, const float* y, int64_t B,
   q.items = fe->items;
   q.nitems = fe->nitems;
   q.lens = lens;
+  q.out_cl_pitch = cl_pitch;
   const size_t smem2 = sizeof(float) * ((size_t)q.nsmp_pad + (size_t)kFe2Warps * 2 * kFe2Scratch);
   if (!legacy && smem2 <= 100 * 1024 && fe->n_mels <= kFe2MaxMels) {  // the staged kernel (persistent CTAs, 8 consecutive frames per step)
     static const int ctas_per_sm = [] { const char* e = std::getenv("NVSE_FE_CTAS"); const int v = e ? std::atoi(e) : 0; return v > 0 ? v : 4; }();
@@ -1118,6 +1148,7 @@ static int frontend_mel_impl(const nvse_frontend* fe, const float* y, int64_t B,
     return NVSE_OK;
   }
   // very large hops: one warp per frame pair straight from global memory
+  NVSE_REQUIRE(cl_pitch == 0, NVSE_ERR_UNSUPPORTED, "the fused wav -> wav call needs the staged front-end kernel (hop too large)");
   NVSE_REQUIRE(!lens, NVSE_ERR_UNSUPPORTED, "nvse_frontend_mel_ragged_f32: per-utterance lengths need the staged kernel (hop too large)");
   const int64_t tasks = B * p.pairs;
   const int64_t ctas = (tasks + kWarpsPerCta - 1) / kWarpsPerCta;

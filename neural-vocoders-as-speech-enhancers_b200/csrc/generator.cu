@@ -210,7 +210,8 @@ static int launch_post_reflect_fix(const float* x_t32, const Layer& post, float*
 // alone with frames_dev[b] frames (every kernel treats its rows beyond that like rows beyond the end of the sequence); its
 // output samples beyond its own length are undefined.  Tensor-core HiFiGAN plan only.
 static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B, int64_t F, float* out, float* ws,
-                        int64_t buf_elems, int nbuf, cudaStream_t st, int16_t* out_i16 = nullptr, const int* frames_dev = nullptr) {
+                        int64_t buf_elems, int nbuf, cudaStream_t st, int16_t* out_i16 = nullptr, const int* frames_dev = nullptr,
+                        const float* mel_cl = nullptr) {  // mel_cl: the log-mel channels-last [B, F, conv_pre.pre_cin] (fused call)
   const nvse_generator_config& c = g->cfg;
   float* bufA = ws;  // conv_pre output, then the MRF accumulator of every stage
   float* bufU = ws + buf_elems;
@@ -224,11 +225,13 @@ static int forward_impl(nvse_generator* g, bool tc, const float* mel, int64_t B,
   {
     const Layer& pre = g->layer("conv_pre");
     static const bool pre_tc_env = [] { const char* e = std::getenv("NVSE_PRE_TC"); return !(e && e[0] == '0'); }();
+    NVSE_REQUIRE(!mel_cl || (tc && pre_tc_env && pre.pre_n > 0), NVSE_ERR_UNSUPPORTED, "the fused wav -> wav call needs conv_pre on the tensor cores");
     if (tc && pre_tc_env && pre.pre_n > 0) {
-      if (int rc = launch_transpose_pad(mel, bufR, B, c.in_channels, F, pre.pre_cin, st)) return rc;
+      if (!mel_cl)
+        if (int rc = launch_transpose_pad(mel, bufR, B, c.in_channels, F, pre.pre_cin, st)) return rc;
       for (int sl = 0; sl < pre.pre_n; ++sl) {
         ConvTcArgs a{};
-        a.x = bufR; a.x_bstride = F * pre.pre_cin; a.Tin = (int)F; a.Cin = pre.pre_cin; a.Cout = pre.pre_cout;
+        a.x = mel_cl ? mel_cl : bufR; a.x_bstride = F * pre.pre_cin; a.Tin = (int)F; a.Cin = pre.pre_cin; a.Cout = pre.pre_cout;
         a.wimg = reinterpret_cast<const __nv_bfloat16*>(pre.w_pre[sl]); a.bias = pre.bias + sl * pre.pre_cout; a.ops_f16 = 1;
         a.y = bufA + sl * pre.pre_cout; a.y_bstride = F * pre.Cout; a.y_ld = pre.Cout; a.Tout = (int)F;
         conv1d_taps(pre.k, 1, &a.taps);
@@ -663,4 +666,52 @@ extern "C" int nvse_generator_forward_pcm16(nvse_generator* g, const float* mel,
   float* ws = reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   return forward_impl(g, precision == NVSE_PRECISION_BF16, mel, B, frames, nullptr, ws, buf_elems,
                       workspace_buffers(g, B, frames, precision), as_stream(stream), out);
+}
+
+// ---- fused wav -> wav call ---------------------------------------------------------------------------
+extern "C" int nvse_vocoder_mel_pitch(const nvse_generator* g) {
+  if (!g || !g->finalized) return 0;
+  const Layer& pre = g->layer("conv_pre");
+  return pre.pre_n > 0 ? pre.pre_cin : 0;
+}
+
+extern "C" size_t nvse_vocoder_workspace_bytes(const nvse_frontend* fe, const nvse_generator* g, int64_t B, int64_t T) {
+  if (!fe || !g || B < 0 || T < 0) return 0;
+  const int64_t frames = nvse_frontend_num_frames(fe, T);
+  const int pitch = nvse_vocoder_mel_pitch(g);
+  if (frames < 1 || pitch == 0) return 0;
+  return nvse_generator_workspace_bytes(g, B, frames, NVSE_PRECISION_BF16) + align_up((size_t)B * frames * pitch * sizeof(float), 256) +
+         align_up((size_t)B * sizeof(int), 256) + 256;
+}
+
+extern "C" int nvse_vocoder_forward(const nvse_frontend* fe, nvse_generator* g, const float* wav, int64_t B, int64_t T,
+                                    int64_t wav_row_stride, const int32_t* samples_dev, float* out, int16_t* out_pcm16, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  NVSE_REQUIRE(fe && g && wav && ((out != nullptr) != (out_pcm16 != nullptr)), NVSE_ERR_INVALID,
+               "nvse_vocoder_forward: null argument (exactly one of out / out_pcm16)");
+  NVSE_REQUIRE(g->finalized, NVSE_ERR_STATE, "nvse_vocoder_forward: the generator has no weights yet");
+  NVSE_REQUIRE(!(samples_dev && out_pcm16), NVSE_ERR_UNSUPPORTED, "nvse_vocoder_forward: ragged batches deliver float output");
+  NVSE_REQUIRE(B >= 0 && T >= 1 && wav_row_stride >= T, NVSE_ERR_INVALID, "nvse_vocoder_forward: bad shape");
+  if (B == 0) return NVSE_OK;
+  cudaStream_t st = as_stream(stream);
+  if (int rc = tc_abort_poll(st)) return rc;
+  const int pitch = nvse_vocoder_mel_pitch(g);
+  NVSE_REQUIRE(pitch > 0 && g->cfg.in_channels <= pitch, NVSE_ERR_UNSUPPORTED, "nvse_vocoder_forward: conv_pre is not on the tensor cores");
+  const int64_t frames = nvse_frontend_num_frames(fe, T);
+  const size_t need = nvse_vocoder_workspace_bytes(fe, g, B, T);
+  NVSE_REQUIRE(workspace && need > 0 && workspace_bytes >= need, NVSE_ERR_INVALID, "nvse_vocoder_forward: workspace too small: %zu < %zu bytes",
+               workspace_bytes, need);
+  NVSE_REQUIRE(max_activation_elems(g, frames) * 4 < (int64_t)1 << 40, NVSE_ERR_INVALID, "utterance too long");
+  const size_t gen_bytes = nvse_generator_workspace_bytes(g, B, frames, NVSE_PRECISION_BF16);
+  const int64_t buf_elems = (int64_t)(align_up((size_t)B * (size_t)max_activation_elems(g, frames) * sizeof(float), 256) / sizeof(float));
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  float* ws = reinterpret_cast<float*>(base);
+  float* mel_cl = reinterpret_cast<float*>(base + align_up(gen_bytes, 256));
+  int* frames_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(mel_cl) + align_up((size_t)B * frames * pitch * sizeof(float), 256));
+  // front-end: the log-mel goes straight into the channels-last, zero-padded layout conv_pre's tensor-core launch stages from
+  if (int rc = frontend_mel_cl(fe, wav, B, T, wav_row_stride, samples_dev, pitch, mel_cl, st)) return rc;
+  if (samples_dev)
+    if (int rc = launch_frames_from_samples(fe, samples_dev, frames_dev, B, st)) return rc;
+  return forward_impl(g, true, nullptr, B, frames, out, ws, buf_elems, workspace_buffers(g, B, frames, NVSE_PRECISION_BF16), st, out_pcm16,
+                      samples_dev ? frames_dev : nullptr, mel_cl);
 }

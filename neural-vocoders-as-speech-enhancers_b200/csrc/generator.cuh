@@ -61,6 +61,10 @@ int launch_istft_head(const float* z, float* out, int64_t B, int64_t Tp, int n_f
 // dz rows have `pitch` >= n_fft + 2 floats (extra columns zeroed)
 int launch_istft_head_bwd(const float* z, const float* gout, float* dz, int64_t B, int64_t Tp, int n_fft, int hop, int pitch,
                           cudaStream_t st);
+// frontend.cu: the log-mel channels-last [B, F, pitch] for the fused wav -> wav call; frames per utterance of a ragged batch
+int frontend_mel_cl(const nvse_frontend* fe, const float* y, int64_t B, int64_t T, int64_t y_row_stride, const int* lens, int pitch,
+                    float* out, cudaStream_t st);
+int launch_frames_from_samples(const nvse_frontend* fe, const int* samples_dev, int* frames_dev, int64_t B, cudaStream_t st);
 int launch_pad_reflect_left(const float* x, float* y, int64_t B, int64_t T, int C, cudaStream_t st);      // [B,T,C] -> [B,T+1,C]
 int launch_unpad_reflect_left(const float* dy, float* dx, int64_t B, int64_t T, int C, cudaStream_t st);  // the adjoint
 

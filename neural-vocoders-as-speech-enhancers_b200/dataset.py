@@ -65,6 +65,19 @@ def _frontend(sampling_rate, n_fft, num_mels, hop_size, win_size, fmin, fmax, ba
     return fe
 
 
+def frontend_handle(n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, dev):
+    """The native front-end handle (``nvse_frontend*``) of this parameter set on CUDA device ``dev`` -- what ``mel_spectrogram``
+    uses and what the fused wav -> wav call (``nvse_vocoder_forward``, pipeline.Vocoder) takes."""
+    ps = param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, dev)
+    if ps in mel_window:
+        mel_basis, hann_window = mel_window[ps]
+    else:
+        mel_basis = torch.from_numpy(slaney_mel_basis(sampling_rate, n_fft, num_mels, fmin, fmax)).float().to(dev)
+        hann_window = torch.hann_window(win_size).to(dev)
+        mel_window[ps] = (mel_basis, hann_window)
+    return _frontend(sampling_rate, n_fft, num_mels, hop_size, win_size, fmin, fmax, mel_basis, hann_window, dev)
+
+
 def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax,
                     center=True, in_dataset=False, *, lengths=None):
     """log-mel spectrogram ``[B, num_mels, 1 + T // hop_size]`` (or ``[num_mels, F]`` for 1-D

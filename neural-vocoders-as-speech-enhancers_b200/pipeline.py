@@ -12,7 +12,8 @@ import ctypes
 import torch
 
 from . import _lib
-from .dataset import mel_spectrogram
+from .dataset import mel_spectrogram, frontend_handle
+from ._engine import GeneratorEngine
 from .shard import bucket_by_length, bucket_padded
 
 
@@ -27,12 +28,41 @@ class Vocoder:
         h = self.h
         return mel_spectrogram(wav_dev, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax)
 
+    def _engine(self):
+        gen = self.generator
+        if gen._engine is None:
+            object.__setattr__(gen, "_engine", GeneratorEngine(gen, gen._kind))
+        return gen._engine
+
+    def fused(self):
+        """True when wav -> mel -> generator runs as ONE library call (``nvse_vocoder_forward``: the front-end writes the log-mel
+        straight into conv_pre's tensor-core staging layout): the 16-bit path of a generator whose conv_pre the tensor-core
+        launch takes.  Otherwise the two stages are called one after the other -- the results are bit-identical."""
+        gen = self.generator
+        if gen is None or not hasattr(gen, "_kind") or gen.training or getattr(self, "no_fuse", False):
+            return False
+        return self._engine().can_vocode(gen, self.device)
+
+    def vocode(self, wav_dev, lengths=None, pcm16=False, out=None):
+        """One micro-batch on the device: wav ``[B, T]`` -> waveform ``[B, samples]`` (fused call where it applies)."""
+        h = self.h
+        if self.fused() and wav_dev.shape[-1] > int(h.n_fft) // 2:
+            fe = frontend_handle(h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax, self.device)
+            return self._engine().vocode(self.generator, fe, wav_dev, lengths=lengths, pcm16=pcm16, out=out)
+        if lengths is not None:
+            n = torch.as_tensor(lengths).to(self.device, torch.int32)
+            mel = mel_spectrogram(wav_dev, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax, lengths=n)
+            frames = (1 + torch.div(n, int(h.hop_size), rounding_mode="floor")).to(torch.int32)
+            return self.generator(mel, frames=frames)
+        mel = self.mel(wav_dev)
+        return self.generator.forward_pcm16(mel, out=out) if pcm16 else self.generator(mel, out=out)
+
     @torch.no_grad()
     def run_device(self, wav_dev, out_dev=None):
         """Device-resident variant: wav_dev [U, T] on the GPU -> [U, T_out] on the GPU."""
         outs = []
         for s in range(0, wav_dev.shape[0], self.micro_batch):
-            y = self.generator(self.mel(wav_dev[s:s + self.micro_batch]))
+            y = self.vocode(wav_dev[s:s + self.micro_batch])
             if out_dev is not None:
                 out_dev[s:s + y.shape[0]].copy_(y)
             else:
@@ -89,15 +119,14 @@ class Vocoder:
             k = i & 1
             nxt = upload(i + 1) if i + 1 < len(starts) else None
             cur.wait_event(ev)
-            mel = self.mel(chunk)
-            stg["consumed"][k] = torch.cuda.Event()
-            stg["consumed"][k].record(cur)
             if stg["drained"][k] is not None:
                 cur.wait_event(stg["drained"][k])
             obuf = stg["out"][k]
             obuf = obuf[:chunk.shape[0]] if obuf is not None and obuf.shape[0] >= chunk.shape[0] else None
             # quantised inside the generator's last kernel with pcm16: half the bytes cross PCIe, no extra pass
-            y = self.generator.forward_pcm16(mel, out=obuf) if pcm16 else self.generator(mel, out=obuf)
+            y = self.vocode(chunk, pcm16=pcm16, out=obuf)
+            stg["consumed"][k] = torch.cuda.Event()
+            stg["consumed"][k].record(cur)
             if stg["out"][k] is None or stg["out"][k].shape[0] < y.shape[0]:
                 stg["out"][k] = y
             y = y.reshape(y.shape[0], -1)
@@ -153,9 +182,7 @@ class Vocoder:
             for j, i in enumerate(group):
                 batch[j, :lens[i]].copy_(wavs[i].reshape(-1).to(torch.float32), non_blocking=True)
             n = torch.tensor([lens[i] for i in group], dtype=torch.int32, device=self.device)
-            frames = 1 + torch.div(n, int(h.hop_size), rounding_mode="floor")
-            mel = mel_spectrogram(batch, h.n_fft, h.num_mels, h.sampling_rate, h.hop_size, h.win_size, h.fmin, h.fmax, lengths=n)
-            y = self.generator(mel, frames=frames.to(torch.int32)).reshape(len(group), -1).cpu()
+            y = self.vocode(batch, lengths=n).reshape(len(group), -1).cpu()
             for j, i in enumerate(group):
                 outs[i] = y[j, :(1 + lens[i] // int(h.hop_size)) * up].clone()
         return outs

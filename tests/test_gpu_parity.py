@@ -564,6 +564,41 @@ def test_padded_ragged_batches_are_bit_identical_to_single_utterance_runs(cfg_ke
     report(f"padded ragged batches, {cfg['model_name']} ({len(lens)} utterances, 4097 .. 35000 samples, up to 90 % padding): bit-identical to single-utterance runs")
 
 
+@pytest.mark.parametrize("cfg_key", ["hifigan_v1", "istftnet"])
+def test_fused_wav_to_wav_call_is_bit_identical_to_the_two_stage_path(cfg_key):
+    """nvse_vocoder_forward (the front-end writes the log-mel straight into conv_pre's channels-last staging layout, then the
+    generator: one library call, no [B, 80, F] tensor, no transpose pass) against mel_spectrogram + generator called one after
+    the other: float, PCM_16 and ragged output, both generators."""
+    cfg = synth.CONFIGS[cfg_key]
+    gen = build_generator(cfg, synth.make_state(cfg, 8, "init"), DEV, remove_wn=True)
+    gen.precision = "bf16"
+    voc = pkg.Vocoder(gen, synth.AttrDict(cfg), micro_batch=3, device=DEV)
+    assert voc.fused()
+    wav = torch.from_numpy(synth.make_wave(5, 5000, 81)).to(DEV)
+    l0 = lib_mod.launch_count()
+    fused = voc.run_device(wav)
+    n_fused = lib_mod.launch_count() - l0
+    voc.no_fuse = True
+    assert not voc.fused()
+    l0 = lib_mod.launch_count()
+    two = voc.run_device(wav)
+    n_two = lib_mod.launch_count() - l0
+    assert torch.equal(fused, two) and n_fused == n_two - 2   # one transpose launch fewer per micro-batch
+    p_two = voc.vocode(wav[:2], pcm16=True)
+    lens = torch.tensor([5000, 3100, 4097], dtype=torch.int32)
+    r_two = voc.vocode(wav[:3], lengths=lens)
+    voc.no_fuse = False
+    assert torch.equal(voc.vocode(wav[:2], pcm16=True), p_two) and p_two.dtype == torch.int16
+    r_fused = voc.vocode(wav[:3], lengths=lens)
+    up = fused.shape[1] // (1 + 5000 // cfg["hop_size"])
+    for b, n in enumerate(lens.tolist()):
+        k = (1 + n // cfg["hop_size"]) * up
+        assert torch.equal(r_fused[b, :k], r_two[b, :k])
+    gen.precision = "fp32"     # the fp32 path has no fused call: the same entry point falls back to the two stages
+    assert not voc.fused() and voc.run_device(wav[:1]).shape == fused[:1].shape
+    assert not lib_mod.tc_abort_status()
+
+
 def test_vocoder_run_host_overlapped_copies_match_device_run():
     """Host-buffer pipeline (copies on side streams, overlapped with the kernels): identical to the
     device-resident run, with an utterance count that is not a multiple of the micro-batch."""
