@@ -5,7 +5,7 @@ set -e
 tag=$1; flags=$2
 cd "$(dirname "$0")/../neural-vocoders-as-speech-enhancers_b200/csrc"
 mkdir -p build_$tag
-for f in core frontend conv_f32 istft conv_tc resblock_tc pair_tc ups_tc layers_tc tc_abort generator weights grad wgrad_tc generator_train; do
+for f in core frontend conv_f32 istft conv_tc resblock_tc pair_tc ups_tc layers_tc tc_abort generator weights grad wgrad_tc generator_train disc; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
        --expt-relaxed-constexpr -cudart static $flags -c $f.cu -o build_$tag/$f.o &
 done
