@@ -68,6 +68,15 @@ def make_config(h, kind):
     return cfg
 
 
+def _with_index(dev):
+    """``torch.device("cuda")`` and ``torch.device("cuda", 0)`` compare unequal: every device the engine keys its native handle
+    on carries an explicit index (otherwise a caller mixing the two forms would rebuild the handle on every call)."""
+    dev = torch.device(dev)
+    if dev.type == "cuda" and dev.index is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 class GeneratorEngine:
     """One per nn.Module instance; created lazily on the first forward."""
 
@@ -161,6 +170,7 @@ class GeneratorEngine:
 
     def _ensure(self, module, dev, train=False):
         lib = _lib.load()
+        dev = _with_index(dev)
         if self.handle is not None and self.device != dev:
             self.close()
         if self.handle is None:
@@ -263,7 +273,7 @@ class GeneratorEngine:
         """True when ``vocode`` applies: 16-bit tensor-core precision and a conv_pre the tensor-core launch takes."""
         if resolve_precision(getattr(module, "precision", None)) != _lib.PRECISION_BF16:
             return False
-        if self.handle is None or self.device != dev or self.weights_key is None:
+        if self.handle is None or self.device != _with_index(dev) or self.weights_key is None:
             self._ensure(module, dev)  # the pitch is a property of the configuration: a loaded handle answers without a re-check
         return int(_lib.load().nvse_vocoder_mel_pitch(self.handle)) > 0
 

@@ -23,6 +23,8 @@ class Vocoder:
         self.h = h
         self.micro_batch = int(micro_batch)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type == "cuda" and self.device.index is None:  # "cuda" != "cuda:0" for torch: always carry the index
+            self.device = torch.device("cuda", torch.cuda.current_device())
 
     def mel(self, wav_dev):
         h = self.h

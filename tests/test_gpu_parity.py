@@ -594,6 +594,10 @@ def test_fused_wav_to_wav_call_is_bit_identical_to_the_two_stage_path(cfg_key):
     for b, n in enumerate(lens.tolist()):
         k = (1 + n // cfg["hop_size"]) * up
         assert torch.equal(r_fused[b, :k], r_two[b, :k])
+    # a Vocoder built with an index-less device ("cuda" != "cuda:0" for torch) must not make the engine rebuild its handle
+    h0 = gen._engine.handle.value
+    voc2 = pkg.Vocoder(gen, synth.AttrDict(cfg), micro_batch=3, device="cuda")
+    assert voc2.fused() and torch.equal(voc2.run_device(wav), fused) and gen._engine.handle.value == h0
     gen.precision = "fp32"     # the fp32 path has no fused call: the same entry point falls back to the two stages
     assert not voc.fused() and voc.run_device(wav[:1]).shape == fused[:1].shape
     assert not lib_mod.tc_abort_status()
