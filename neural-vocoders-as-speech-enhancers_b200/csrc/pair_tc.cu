@@ -348,8 +348,14 @@ struct PairPlan {
 };
 
 bool make_pair_plan(int C, int k, int dil, PairPlan* p) {
-  if (C != 128 || k < 1 || !(k & 1) || k > kMaxTaps || dil < 1) return false;
-  const int NT = 2, R = kTileM * NT;
+  // C = 128: two 128-row tiles per item (ACC1 + ACC2 = 512 TMEM columns).  C = 256, one tile per item in the same 512 columns,
+  // is instantiated but OFF (NVSE_PAIR_C256=1 to try it): two operand buffers of 70-80 KB leave room for a two-stage ring of
+  // 32 KB weight stages only (and for six of HiFi-GAN V1's nine C = 256 pairs only: context P = (k-1)/2 * d <= 12 rows), and with
+  // 1 024 MMA cycles of weights buffered the ring starves -- 916 TFLOP/s against 956 for resblock_tc_kernel<256, 1>, whose phases
+  // run back to back but whose ring is 3-4 stages deep (same-box A/B, 32 x 862 frames)
+  static const bool c256 = [] { const char* e = std::getenv("NVSE_PAIR_C256"); return e && e[0] == '1'; }();
+  if ((C != 128 && !(C == 256 && c256)) || k < 1 || !(k & 1) || k > kMaxTaps || dil < 1) return false;
+  const int NT = C == 128 ? 2 : 1, R = kTileM * NT;
   // c1 reads its context (P rows on either side of the tile) from global memory: only c2 costs halo
   const int halo = (k - 1) / 2, P = (k - 1) / 2 * dil;
   if (R - 2 * halo < 64) return false;
@@ -392,13 +398,13 @@ int launch_pair_tc(const ResblockTcArgs& a, int64_t B, cudaStream_t st) {
   const unsigned grid = (unsigned)std::min<int64_t>(n_items, sm_count);
   const double rows = (double)B * a.T;
   ProfScope prof("pair_tc", a.C, a.C, 2.0 * rows * a.C * a.C * a.k * 2.0, rows * a.C * 4.0 * (a.accumulate ? 3.0 : 2.0), st);
-  if (a.accumulate) {
-    NVSE_CUDA_CHECK(cudaFuncSetAttribute(pair_tc_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    pair_tc_kernel<128, 2, true><<<grid, kThreads, p.smem, st>>>(k);
-  } else {
-    NVSE_CUDA_CHECK(cudaFuncSetAttribute(pair_tc_kernel<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-    pair_tc_kernel<128, 2, false><<<grid, kThreads, p.smem, st>>>(k);
+#define PAIR_LAUNCH(CC, NN, AC)                                                                                                  \
+  if (a.C == CC && (a.accumulate != 0) == AC) {                                                                                  \
+    NVSE_CUDA_CHECK(cudaFuncSetAttribute(pair_tc_kernel<CC, NN, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); \
+    pair_tc_kernel<CC, NN, AC><<<grid, kThreads, p.smem, st>>>(k);                                                               \
   }
+  PAIR_LAUNCH(128, 2, true) PAIR_LAUNCH(128, 2, false) PAIR_LAUNCH(256, 1, true) PAIR_LAUNCH(256, 1, false)
+#undef PAIR_LAUNCH
   NVSE_LAUNCH_CHECK("pair_tc_kernel");
   return NVSE_OK;
 }
