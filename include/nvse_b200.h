@@ -258,6 +258,10 @@ NVSE_API int nvse_inverse_mel_f32(const float* inv_basis, const float* mel, floa
 NVSE_API size_t nvse_frontend_istft_scratch_bytes(const nvse_frontend* fe, int64_t B, int64_t frames);
 NVSE_API int nvse_frontend_istft_f32(const nvse_frontend* fe, const float* real, const float* imag, int64_t B, int64_t frames,
                             float* out, void* scratch, size_t scratch_bytes, void* stream);
+/* The same from a complex64 spectrum [B, n_fft/2+1, frames] (interleaved re, im: the tensor torch.istft takes, 8-byte aligned):
+ * no de-interleaving pass in front of the kernel. */
+NVSE_API int nvse_frontend_istft_c64(const nvse_frontend* fe, const float* spec_c64, int64_t B, int64_t frames, float* out,
+                            void* scratch, size_t scratch_bytes, void* stream);
 
 /* Backward of nvse_frontend_mel_f32 (the mel-L1 term of the generator loss differentiates
  * mel_spectrogram(y_g_hat), train_time_wi_inv.py:173-179,231-235): dmel [B, n_mels, frames] -> dy [B, T] (dense).

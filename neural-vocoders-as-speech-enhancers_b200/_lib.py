@@ -56,6 +56,7 @@ PROTOTYPES = {
     "nvse_frontend_backward_scratch_bytes": (_sz, [_vp, _i64, _i64]),
     "nvse_frontend_istft_scratch_bytes": (_sz, [_vp, _i64, _i64]),
     "nvse_frontend_istft_f32": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "nvse_frontend_istft_c64": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _sz, _vp]),
     "nvse_frontend_mel_backward_f32": (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "nvse_generator_create": (_i, [C.POINTER(GeneratorConfig), C.POINTER(_vp)]),
     "nvse_generator_destroy": (_i, [_vp]),

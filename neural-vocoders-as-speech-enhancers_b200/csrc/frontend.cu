@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(256) mel_overlap_add_kernel(const float* __res
 // by the window envelope: bit-reproducible, no atomics.
 // ------------------------------------------------------------------------------------------------
 struct IstftParams {
-  const float* re;     // [B, 513, F]
+  const float* re;     // [B, 513, F]; with im == null: complex64 [B, 513, F] (interleaved re, im -- torch's layout)
   const float* im;
   int64_t B, F;
   int hop;
@@ -823,13 +823,23 @@ __global__ void __launch_bounds__(kIsWarps * 32) istft1024_frames_kernel(const I
   const int64_t b = blockIdx.x / groups;
   const int64_t f0 = (blockIdx.x - b * groups) * kIsFrames;
   const int nf = (int)((q.F - f0) < kIsFrames ? (q.F - f0) : kIsFrames);
-  const float* __restrict__ gre = q.re + b * kBins * q.F + f0;
-  const float* __restrict__ gim = q.im + b * kBins * q.F + f0;
-  for (int e = tid; e < kBins * kIsFrames; e += kIsWarps * 32) {
-    const int k = e >> 3, j = e & 7;
-    const bool in = j < nf;
-    tre[e] = in ? __ldg(gre + (int64_t)k * q.F + j) : 0.0f;
-    tim[e] = in ? __ldg(gim + (int64_t)k * q.F + j) : 0.0f;
+  if (q.im) {
+    const float* __restrict__ gre = q.re + b * kBins * q.F + f0;
+    const float* __restrict__ gim = q.im + b * kBins * q.F + f0;
+    for (int e = tid; e < kBins * kIsFrames; e += kIsWarps * 32) {
+      const int k = e >> 3, j = e & 7;
+      const bool in = j < nf;
+      tre[e] = in ? __ldg(gre + (int64_t)k * q.F + j) : 0.0f;
+      tim[e] = in ? __ldg(gim + (int64_t)k * q.F + j) : 0.0f;
+    }
+  } else {  // complex64 input: one 8-byte load per bin and frame, no de-interleaving pass before the kernel
+    const float2* __restrict__ gc = reinterpret_cast<const float2*>(q.re) + b * kBins * q.F + f0;
+    for (int e = tid; e < kBins * kIsFrames; e += kIsWarps * 32) {
+      const int k = e >> 3, j = e & 7;
+      const float2 v = j < nf ? __ldg(gc + (int64_t)k * q.F + j) : make_float2(0.0f, 0.0f);
+      tre[e] = v.x;
+      tim[e] = v.y;
+    }
   }
   __syncthreads();
   const int fa = 2 * warp;
@@ -1245,10 +1255,25 @@ extern "C" size_t nvse_frontend_istft_scratch_bytes(const nvse_frontend* fe, int
   return (size_t)B * (size_t)frames * nvse::kNfft * sizeof(float) + 256;
 }
 
+static int frontend_istft_impl(const nvse_frontend* fe, const float* real, const float* imag, int64_t B, int64_t frames, float* out,
+                               void* scratch, size_t scratch_bytes, void* stream);
+
 extern "C" int nvse_frontend_istft_f32(const nvse_frontend* fe, const float* real, const float* imag, int64_t B, int64_t frames,
                                        float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  NVSE_REQUIRE(imag, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: null argument");
+  return frontend_istft_impl(fe, real, imag, B, frames, out, scratch, scratch_bytes, stream);
+}
+
+extern "C" int nvse_frontend_istft_c64(const nvse_frontend* fe, const float* spec_c64, int64_t B, int64_t frames, float* out,
+                                       void* scratch, size_t scratch_bytes, void* stream) {
+  NVSE_REQUIRE((reinterpret_cast<size_t>(spec_c64) & 7) == 0, NVSE_ERR_INVALID, "nvse_frontend_istft_c64: the spectrum must be 8-byte aligned");
+  return frontend_istft_impl(fe, spec_c64, nullptr, B, frames, out, scratch, scratch_bytes, stream);
+}
+
+static int frontend_istft_impl(const nvse_frontend* fe, const float* real, const float* imag, int64_t B, int64_t frames, float* out,
+                               void* scratch, size_t scratch_bytes, void* stream) {
   using namespace nvse;
-  NVSE_REQUIRE(fe && real && imag && out && scratch, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: null argument");
+  NVSE_REQUIRE(fe && real && out && scratch, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: null argument");
   NVSE_REQUIRE(B >= 0 && frames >= 1, NVSE_ERR_INVALID, "nvse_frontend_istft_f32: bad B=%lld / frames=%lld", (long long)B, (long long)frames);
   NVSE_REQUIRE(fe->hop <= kNfft, NVSE_ERR_UNSUPPORTED, "nvse_frontend_istft_f32: hop %d > n_fft leaves gaps (torch.istft rejects it: zero envelope)", fe->hop);
   NVSE_REQUIRE(scratch_bytes >= nvse_frontend_istft_scratch_bytes(fe, B, frames), NVSE_ERR_INVALID, "nvse_frontend_istft_f32: scratch too small");

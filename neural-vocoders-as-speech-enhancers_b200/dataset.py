@@ -21,6 +21,7 @@ from .melbasis import slaney_mel_basis
 mel_window = {}      # param_string -> (mel_basis, hann_window) tensors, as in dataset.py:45
 inv_mel_window = {}  # kept for dataset.inverse_mel compatibility (dataset.py:46)
 _frontends = {}      # (param_string without device, hop, cuda index) -> nvse_frontend*
+_istft_idents = []   # identity keys of window tensors that alias entries of _frontends (istft)
 
 
 def param_string(sampling_rate, n_fft, num_mels, fmin, fmax, win_size, device):
@@ -219,25 +220,40 @@ def istft(spec, n_fft, hop_length=None, win_length=None, window=None, center=Tru
     if spec.shape[-2] != n_fft // 2 + 1:
         raise RuntimeError(f"istft: expected {n_fft // 2 + 1} frequency bins, got {spec.shape[-2]}")
     dev = _cuda_device_for(spec)
-    win = torch.hann_window(win_length) if window is None else window.detach().to("cpu", torch.float32)
-    key = ("istft", n_fft, 1, hash(win.numpy().tobytes()), 0, win_length, hop_length, dev.index)
-    fe = _frontends.get(key)
-    if fe is None:  # a front-end handle without a mel basis: window + twiddles only
-        _frontend("istft", n_fft, 1, hop_length, win_length, hash(win.numpy().tobytes()), 0, torch.zeros(1, n_fft // 2 + 1), win, dev)
-        fe = _frontends[key]
+    # the handle of a window tensor seen before is found by its identity (storage address + version): hashing its values means
+    # a device -> host copy and a synchronisation on every call, which is what the reference's call sites would pay
+    ident = None if window is None else ("istft-window", window.data_ptr(), window._version, tuple(window.shape), str(window.device),
+                                         n_fft, win_length, hop_length, dev.index)
+    fe = _frontends.get(ident) if ident is not None else None
+    if fe is None:
+        win = torch.hann_window(win_length) if window is None else window.detach().to("cpu", torch.float32)
+        key = ("istft", n_fft, 1, hash(win.numpy().tobytes()), 0, win_length, hop_length, dev.index)
+        fe = _frontends.get(key)
+        if fe is None:  # a front-end handle without a mel basis: window + twiddles only
+            _frontend("istft", n_fft, 1, hop_length, win_length, hash(win.numpy().tobytes()), 0, torch.zeros(1, n_fft // 2 + 1), win, dev)
+            fe = _frontends[key]
+        if ident is not None:
+            if len(_istft_idents) > 64:  # bounded: windows that are re-created on every call must not grow the table
+                for k in _istft_idents:
+                    _frontends.pop(k, None)
+                _istft_idents.clear()
+            _frontends[ident] = fe
+            _istft_idents.append(ident)
     squeeze = spec.dim() == 2
     sd = spec.detach().to(dev)
     if squeeze:
         sd = sd.unsqueeze(0)
-    re = sd.real.to(torch.float32).contiguous()
-    im = sd.imag.to(torch.float32).contiguous()
-    batch, _, frames = re.shape
+    if sd.dtype != torch.complex64:
+        sd = sd.to(torch.complex64)
+    sd = sd.contiguous()             # torch's complex64 layout (interleaved re, im) is read by the kernel as it is
+    cview = torch.view_as_real(sd)   # [B, bins, F, 2] float32, same storage
+    batch, _, frames = sd.shape
     out = torch.empty((batch, hop_length * (frames - 1)), dtype=torch.float32, device=dev)
     lib = _lib.load()
     scratch = torch.empty(lib.nvse_frontend_istft_scratch_bytes(fe, batch, frames), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(lib.nvse_frontend_istft_f32(fe, _lib.ptr(re), _lib.ptr(im), batch, frames, _lib.ptr(out), _lib.ptr(scratch),
+        _lib.check(lib.nvse_frontend_istft_c64(fe, _lib.ptr(cview), batch, frames, _lib.ptr(out), _lib.ptr(scratch),
                                                scratch.numel(), stream))
     if squeeze:
         out = out[0]

@@ -47,3 +47,11 @@ ms = timed(lambda: pkg.inverse_mel(mel, *margs))
 ms_t = timed(lambda: inv @ torch.exp(mel))
 byt = 4 * B * F * (80 + 513)
 print(f"inverse_mel {B} x 80 x {F}: {ms:.3f} ms ({byt / ms / 1e6:.0f} GB/s algorithmic) vs stock torch {ms_t:.3f} ms -> {ms_t / ms:.2f}x")
+
+# n_fft = 1024 inverse STFT (the T-F vocoders' head) against torch.istft on the same GPU
+spec = torch.stft(y, 1024, hop_length=256, win_length=1024, window=win, center=True, return_complex=True)
+ms = timed(lambda: pkg.istft(spec, 1024, 256, 1024, win))
+ms_t = timed(lambda: torch.istft(spec, 1024, hop_length=256, win_length=1024, window=win, center=True))
+err = float((pkg.istft(spec, 1024, 256, 1024, win) - torch.istft(spec, 1024, hop_length=256, win_length=1024, window=win, center=True)).abs().max())
+print(f"  kernels alone: {kernel_ms(lambda: pkg.istft(spec, 1024, 256, 1024, win), 'istft1024'):.3f} ms")
+print(f"istft {B} x 513 x {F}: {ms:.3f} ms vs stock torch.istft {ms_t:.3f} ms -> {ms_t / ms:.2f}x  (max |difference| {err:.1e})")
