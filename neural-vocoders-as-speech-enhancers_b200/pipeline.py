@@ -178,13 +178,84 @@ class Vocoder:
             up *= int(u)
         if getattr(self.generator, "_kind", None) == _lib.GEN_ISTFTNET:
             up *= int(h.gen_istft_hop_size)
-        for group in bucket_padded(lens, self.micro_batch, max_pad):
-            tmax = max(lens[i] for i in group)
-            batch = torch.zeros((len(group), tmax), dtype=torch.float32, device=self.device)
+        # Host tensors in, host tensors out, two groups in flight: a group's padded batch is assembled in a PINNED staging buffer
+        # (plain memcpys), goes up in one asynchronous copy on a side stream and comes back into a pinned buffer on another,
+        # so the copies of group g + 1 / g - 1 overlap the kernels of group g (the same choreography as run_host); the results
+        # are cut out of the pinned buffer on the host once their copy has landed.  Device-resident inputs skip the staging.
+        groups = list(bucket_padded(lens, self.micro_batch, max_pad))
+        if not groups:
+            return outs
+        dev = self.device
+        on_host = all(not w.is_cuda for w in wavs)
+        if not on_host:
+            for group in groups:
+                tmax = max(lens[i] for i in group)
+                batch = torch.zeros((len(group), tmax), dtype=torch.float32, device=dev)
+                for j, i in enumerate(group):
+                    batch[j, :lens[i]].copy_(wavs[i].reshape(-1).to(torch.float32), non_blocking=True)
+                n = torch.tensor([lens[i] for i in group], dtype=torch.int32, device=dev)
+                y = self.vocode(batch, lengths=n).reshape(len(group), -1).cpu()
+                for j, i in enumerate(group):
+                    outs[i] = y[j, :(1 + lens[i] // int(h.hop_size)) * up].clone()
+            return outs
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_h2d"):
+            self._h2d, self._d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._stage = None
+        self._h2d.wait_stream(cur)
+        self._d2h.wait_stream(cur)
+        rows = max(len(g) for g in groups)
+        t_in = max(max(lens[i] for i in g) for g in groups)
+        t_out = (1 + t_in // int(h.hop_size)) * up
+        pin = getattr(self, "_list_stage", None)
+        if pin is None or pin["rows"] < rows or pin["t_in"] < t_in or pin["t_out"] < t_out:
+            pin = self._list_stage = {"rows": rows, "t_in": t_in, "t_out": t_out,
+                                      "in": [torch.empty(rows * t_in, dtype=torch.float32).pin_memory() for _ in range(2)],
+                                      "out": [torch.empty(rows * t_out, dtype=torch.float32).pin_memory() for _ in range(2)],
+                                      "len": [torch.empty(rows, dtype=torch.int32).pin_memory() for _ in range(2)]}
+        uploaded, landed, pending = [None, None], [None, None], [None, None]
+
+        def collect(k):  # cut the results of the group that used staging slot k out of its pinned output buffer
+            if pending[k] is None:
+                return
+            group, hout = pending[k]
+            landed[k].synchronize()
             for j, i in enumerate(group):
-                batch[j, :lens[i]].copy_(wavs[i].reshape(-1).to(torch.float32), non_blocking=True)
-            n = torch.tensor([lens[i] for i in group], dtype=torch.int32, device=self.device)
-            y = self.vocode(batch, lengths=n).reshape(len(group), -1).cpu()
+                outs[i] = hout[j, :(1 + lens[i] // int(h.hop_size)) * up].clone()
+            pending[k] = None
+
+        for g, group in enumerate(groups):
+            k = g & 1
+            collect(k)                      # slot k's previous results are read before its buffers are reused
+            if uploaded[k] is not None:
+                uploaded[k].synchronize()   # ... and its previous input has left the pinned buffer
+            nb, tmax = len(group), max(lens[i] for i in group)
+            hin = pin["in"][k][:nb * tmax].view(nb, tmax)
+            hlen = pin["len"][k][:nb]
             for j, i in enumerate(group):
-                outs[i] = y[j, :(1 + lens[i] // int(h.hop_size)) * up].clone()
+                hin[j, :lens[i]].copy_(wavs[i].reshape(-1))
+                hin[j, lens[i]:].zero_()
+                hlen[j] = lens[i]
+            with torch.cuda.stream(self._h2d):
+                batch = hin.to(dev, non_blocking=True)
+                n = hlen.to(dev, non_blocking=True)
+                uploaded[k] = torch.cuda.Event()
+                uploaded[k].record(self._h2d)
+            cur.wait_event(uploaded[k])
+            y = self.vocode(batch, lengths=n).reshape(nb, -1)
+            batch.record_stream(cur)
+            n.record_stream(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            hout = pin["out"][k][:nb * y.shape[1]].view(nb, y.shape[1])
+            with torch.cuda.stream(self._d2h):
+                self._d2h.wait_event(done)
+                hout.copy_(y, non_blocking=True)
+                y.record_stream(self._d2h)
+                landed[k] = torch.cuda.Event()
+                landed[k].record(self._d2h)
+            pending[k] = (group, hout)
+        collect(0)
+        collect(1)
+        cur.wait_stream(self._d2h)
         return outs
